@@ -1,0 +1,937 @@
+// b200sgd_api.cu -- the engine behind include/b200sgd.h: context, data residency in HBM, the
+// per-epoch permutation pipeline, kernel dispatch, timing, multi-GPU peer plumbing.
+//
+// Reference correspondence (all under /root/reference/c_code):
+//   sgd_create / sgd_load_rows   <-> main.cu:381-433  (device vectors, weight init, index vector)
+//   sgd_shuffle                  <-> main.cu:90-91, :207-211 (+ removes sgd_thrust.cu:374-402)
+//   sgd_epoch                    <-> main.cu:94-160, :227-300 (the batch loop)
+//   sgd_run                      <-> main.cu:456-508
+//   sgd_mean_abs_error           <-> sgd_thrust.cu:79-135
+// No Thrust, no cuBLAS, no CPU fallback: every compute entry point needs an sm_100 device.
+#include "b200sgd.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstddef>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "host_io.hpp"
+#include "host_rng.hpp"
+#include "sgd_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                      \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess)                                                                  \
+      return fail(SGD_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" + \
+                                    __FILE__ + ":" + std::to_string(__LINE__) + ")");       \
+  } while (0)
+#define SGD_TRY(expr)             \
+  do {                            \
+    int _rc = (expr);             \
+    if (_rc != SGD_OK) return _rc; \
+  } while (0)
+
+using clk = std::chrono::steady_clock;
+double ms_since(clk::time_point t0) {
+  return std::chrono::duration<double, std::milli>(clk::now() - t0).count();
+}
+
+constexpr size_t kMaxDynSmem = 232448;  // 227 KB: sm_100 per-CTA opt-in maximum
+constexpr int kGraphChunk = 256;        // step-kernel nodes per instantiated graph
+
+struct KernelChoice {
+  int KC = 0, U = 0, NW = 0;
+  const void* fn = nullptr;
+  size_t fixed_smem = 0;
+};
+
+template <int KC, int U, int NW>
+KernelChoice make_choice() {
+  KernelChoice k;
+  k.KC = KC; k.U = U; k.NW = NW;
+  k.fn = (const void*)b200sgd::sgd_epoch_kernel<KC, U, NW>;
+  k.fixed_smem = b200sgd::EpochSmem<KC, NW>::kFixed;
+  return k;
+}
+
+bool choose_kernel(int C4, KernelChoice* out) {
+  if (C4 <= 32) *out = make_choice<1, 4, 16>();
+  else if (C4 <= 64) *out = make_choice<2, 4, 16>();
+  else if (C4 <= 128) *out = make_choice<4, 2, 16>();
+  else if (C4 <= 256) *out = make_choice<8, 2, 8>();
+  else if (C4 <= 512) *out = make_choice<16, 1, 8>();
+  else return false;
+  return true;
+}
+
+}  // namespace
+
+struct sgd_ctx {
+  sgd_config cfg{};
+  int64_t R = 0;  // rows of the whole data set
+  int32_t C = 0, B = 0, nb = 0;
+  int64_t ld = 0;  // floats per record
+  int32_t C4 = 0;
+  int64_t rows_per_rank = 0, row_begin = 0, row_end = 0, local_rows = 0;
+  int device = 0, num_sms = 0;
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev_perm[2] = {nullptr, nullptr};  // upload of d_perm[i] finished
+  cudaEvent_t ev_done[2] = {nullptr, nullptr};  // last kernel reading d_perm[i] finished
+
+  // device state
+  float* d_rec = nullptr;
+  float* d_w = nullptr;
+  float* d_wtrue = nullptr;
+  int32_t* d_perm[2] = {nullptr, nullptr};  // global permutation, double-buffered across epochs
+  int32_t* d_perm_local = nullptr;          // nranks > 1: bucketed local rows
+  int64_t* d_step_off = nullptr;            // nranks > 1: nb+1 offsets
+  int64_t* d_counts = nullptr;
+  float4* d_partials = nullptr;
+  float4* d_wstage = nullptr;
+  float* d_glast = nullptr;
+  float* d_rout = nullptr;
+  int64_t rout_len = 0;
+  unsigned int* d_bar = nullptr;  // [0] barrier counter, [1] watchdog error word
+  b200sgd::StepCtl* d_ctl = nullptr;
+  double* d_mae = nullptr;
+  int mae_blocks = 0;
+
+  // host permutation state
+  std::vector<int32_t> h_ind;                // the reference's ind_vector (main.cu:421-424)
+  int32_t* h_stage[2] = {nullptr, nullptr};  // pinned upload staging
+  b200sgd::GlibcRand rng;
+  int cur = 0;  // which d_perm / h_stage holds the active permutation
+  bool perm_valid = false, data_loaded = false, have_true_w = false;
+  float last_shuffle_ms = 0.f;
+
+  // kernel configuration
+  KernelChoice kc{};
+  int grid = 0, reduce_mode = 0, nslots = 0, slot_log2 = 0, engine = SGD_ENGINE_PERSISTENT;
+  size_t smem_bytes = 0;
+  cudaGraphExec_t graph_exec = nullptr;
+  int graph_nodes = 0;
+
+  // multi-GPU
+  void* d_xchg_block = nullptr;  // [xchg float4 2*nranks*C4][flags 2*nranks*grid]
+  size_t xchg_bytes = 0, flag_off = 0;
+  void* peer_block[8] = {nullptr};
+  bool peer_open[8] = {false};
+  bool peers_ready = false;
+  uint32_t epoch_tag = 0;
+};
+
+namespace {
+
+int check_ctx(const sgd_ctx* c) {
+  if (!c) return fail(SGD_ERR_ARG, "null context");
+  return SGD_OK;
+}
+
+int bind(const sgd_ctx* c) {
+  CUDA_TRY(cudaSetDevice(c->device));
+  return SGD_OK;
+}
+
+// main.cu:343-344
+void batch_geometry(int64_t R, int32_t batch_arg, int32_t* B, int32_t* nb) {
+  *B = batch_arg == 0 ? (int32_t)R : batch_arg;
+  *nb = (*B > 0) ? (int32_t)std::floor((float)R / (float)(*B)) : 0;
+}
+
+void free_all(sgd_ctx* c) {
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+  for (int i = 0; i < 8; ++i)
+    if (c->peer_open[i] && c->peer_block[i]) cudaIpcCloseMemHandle(c->peer_block[i]);
+  if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+  cudaFree(c->d_rec); cudaFree(c->d_w); cudaFree(c->d_wtrue);
+  cudaFree(c->d_perm[0]); cudaFree(c->d_perm[1]); cudaFree(c->d_perm_local);
+  cudaFree(c->d_step_off); cudaFree(c->d_counts); cudaFree(c->d_partials); cudaFree(c->d_wstage);
+  cudaFree(c->d_glast); cudaFree(c->d_rout); cudaFree(c->d_bar); cudaFree(c->d_ctl);
+  cudaFree(c->d_mae); cudaFree(c->d_xchg_block);
+  if (c->h_stage[0]) cudaFreeHost(c->h_stage[0]);
+  if (c->h_stage[1]) cudaFreeHost(c->h_stage[1]);
+  cudaEvent_t evs[] = {c->ev0, c->ev1, c->ev_perm[0], c->ev_perm[1], c->ev_done[0], c->ev_done[1]};
+  for (cudaEvent_t e : evs)
+    if (e) cudaEventDestroy(e);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+}
+
+// Decide grid size, reduction mode and ring depth for this shape (DESIGN.md "launch geometry").
+int configure_launch(sgd_ctx* c) {
+  if (!choose_kernel(c->C4, &c->kc))
+    return fail(SGD_ERR_ARG, "cols > 2048 is not supported by this build of the step kernel");
+  const size_t slot_bytes = (size_t)c->ld * 4;
+  if (c->kc.fixed_smem + 2 * slot_bytes > kMaxDynSmem)
+    return fail(SGD_ERR_ARG, "row too wide for the shared-memory ring");
+  int nslots = 2, lg = 1;
+  while (nslots * 2 <= b200sgd::kMaxSlots &&
+         c->kc.fixed_smem + (size_t)(nslots * 2) * slot_bytes <= kMaxDynSmem) {
+    nslots *= 2;
+    ++lg;
+  }
+  c->nslots = nslots;
+  c->slot_log2 = lg;
+  c->smem_bytes = c->kc.fixed_smem + (size_t)nslots * slot_bytes;
+  CUDA_TRY(cudaFuncSetAttribute(c->kc.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
+  int occ = 0;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, c->kc.fn, 32 * (c->kc.NW + 1), c->smem_bytes));
+  if (occ < 1) return fail(SGD_ERR_CUDA, "step kernel does not fit on an SM");
+  // rows this rank sees per step
+  const int64_t rows_step = std::max<int64_t>(1, (int64_t)c->B / std::max(1, c->cfg.nranks));
+  int grid = c->cfg.grid;
+  if (grid <= 0) {
+    // one CTA per SM once every CTA gets a few rows per step; fewer CTAs for tiny batches keep
+    // the grid barrier and the partial-gradient reduction cheap
+    grid = (int)std::min<int64_t>(c->num_sms, std::max<int64_t>(1, rows_step / 2));
+  }
+  grid = std::max(1, std::min(grid, c->num_sms * occ));
+  c->grid = grid;
+  int mode = c->cfg.reduce;
+  if (c->cfg.nranks > 1) mode = SGD_REDUCE_SCATTER;
+  if (mode != SGD_REDUCE_ALLGATHER && mode != SGD_REDUCE_SCATTER)
+    mode = ((int64_t)grid * c->C4 <= 1024) ? SGD_REDUCE_ALLGATHER : SGD_REDUCE_SCATTER;
+  c->reduce_mode = mode;
+  c->engine = (c->cfg.engine == SGD_ENGINE_GRAPH) ? SGD_ENGINE_GRAPH : SGD_ENGINE_PERSISTENT;
+  if (c->engine == SGD_ENGINE_GRAPH && c->cfg.nranks > 1)
+    return fail(SGD_ERR_ARG, "the graph engine is single-GPU; use the persistent engine with nranks > 1");
+  return SGD_OK;
+}
+
+void fill_params(sgd_ctx* c, b200sgd::EpochParams* p, int32_t epoch, int buf) {
+  std::memset(p, 0, sizeof(*p));
+  p->rec = c->d_rec;
+  p->ld = c->ld;
+  p->C = c->C;
+  p->C4 = c->C4;
+  p->perm = c->cfg.nranks > 1 ? c->d_perm_local : c->d_perm[buf];
+  p->step_off = c->cfg.nranks > 1 ? c->d_step_off : nullptr;
+  p->B = c->B;
+  p->nb = c->nb;
+  p->first_step = 0;
+  // main.cu:144 / :282: float a = -(learning_rate / std::pow(epoch, 0.25));
+  p->a = (float)(-((double)c->cfg.learning_rate / std::pow((double)epoch, 0.25)));
+  p->w = c->d_w;
+  p->partials = c->d_partials;
+  p->w_stage = c->d_wstage;
+  p->g_last = c->d_glast;
+  p->r_out = c->d_rout;
+  p->bar = c->d_bar;
+  p->err = c->d_bar + 1;
+  p->reduce_mode = c->reduce_mode;
+  p->nslots = c->nslots;
+  p->slot_log2 = c->slot_log2;
+  p->slot_bytes = (uint32_t)(c->ld * 4);
+  p->rank = c->cfg.rank;
+  p->nranks = c->cfg.nranks;
+  p->ctl = nullptr;
+}
+
+int upload_perm(sgd_ctx* c, int buf) {
+  // h_stage[buf] -> d_perm[buf] on the copy stream, once the last reader of d_perm[buf] is done;
+  // the compute stream waits on ev_perm[buf] before it uses the buffer
+  CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->ev_done[buf], 0));
+  CUDA_TRY(cudaMemcpyAsync(c->d_perm[buf], c->h_stage[buf], sizeof(int32_t) * (size_t)c->R,
+                           cudaMemcpyHostToDevice, c->copy_stream));
+  CUDA_TRY(cudaEventRecord(c->ev_perm[buf], c->copy_stream));
+  return SGD_OK;
+}
+
+// nranks > 1: keep, per step, the rows this rank owns.  Runs on the compute stream.
+int bucket_perm(sgd_ctx* c, int buf, int* launches) {
+  if (c->cfg.nranks == 1 || c->nb == 0) return SGD_OK;
+  const int blocks = std::min(c->nb, 4 * c->num_sms);
+  b200sgd::sgd_bucket_count_kernel<<<blocks, 256, 0, c->stream>>>(
+      c->d_perm[buf], c->B, c->nb, c->row_begin, c->row_end, c->d_counts);
+  b200sgd::sgd_scan_kernel<<<1, 1024, 0, c->stream>>>(c->d_counts, c->nb, c->d_step_off);
+  b200sgd::sgd_bucket_write_kernel<<<blocks, 256, 0, c->stream>>>(
+      c->d_perm[buf], c->B, c->nb, c->row_begin, c->row_end, c->d_step_off, c->d_perm_local);
+  *launches += 3;
+  CUDA_TRY(cudaGetLastError());
+  return SGD_OK;
+}
+
+// GRAPH engine: capture kGraphChunk parameter-free step kernels once; replay per epoch.
+int build_graph(sgd_ctx* c) {
+  if (c->graph_exec) return SGD_OK;
+  const int nodes = std::max(1, std::min(c->nb, kGraphChunk));
+  b200sgd::EpochParams p;
+  fill_params(c, &p, 1, 0);
+  p.nb = 1;
+  p.ctl = c->d_ctl;
+  void* args[] = {&p};
+  cudaGraph_t graph = nullptr;
+  CUDA_TRY(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+  cudaError_t e = cudaSuccess;
+  for (int i = 0; i < nodes && e == cudaSuccess; ++i)
+    e = cudaLaunchKernel(c->kc.fn, dim3(c->grid), dim3(32 * (c->kc.NW + 1)), args, c->smem_bytes, c->stream);
+  cudaError_t e2 = cudaStreamEndCapture(c->stream, &graph);
+  if (e != cudaSuccess || e2 != cudaSuccess) {
+    if (graph) cudaGraphDestroy(graph);
+    return fail(SGD_ERR_CUDA, std::string("graph capture failed: ") +
+                                  cudaGetErrorString(e != cudaSuccess ? e : e2));
+  }
+  cudaError_t e3 = cudaGraphInstantiate(&c->graph_exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e3 != cudaSuccess) return fail(SGD_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e3));
+  c->graph_nodes = nodes;
+  return SGD_OK;
+}
+
+// Enqueues the step loop of one epoch on the compute stream (no host sync).
+int launch_epoch(sgd_ctx* c, int32_t epoch, int buf, int* launches) {
+  if (c->nb == 0) return SGD_OK;
+  b200sgd::EpochParams p;
+  fill_params(c, &p, epoch, buf);
+  if (c->cfg.nranks > 1) {
+    if (!c->peers_ready) return fail(SGD_ERR_STATE, "nranks > 1 but sgd_peer_ready was not called");
+    p.xchg_local = (float4*)c->d_xchg_block;
+    p.flag_local = (unsigned int*)((char*)c->d_xchg_block + c->flag_off);
+    for (int r = 0; r < c->cfg.nranks; ++r) {
+      p.xchg_peer[r] = (float4*)c->peer_block[r];
+      p.flag_peer[r] = (unsigned int*)((char*)c->peer_block[r] + c->flag_off);
+    }
+    p.epoch_tag = c->epoch_tag;
+    c->epoch_tag += (uint32_t)c->nb;
+  }
+  if (c->engine == SGD_ENGINE_GRAPH) {
+    SGD_TRY(build_graph(c));
+    // per-epoch state of the parameter-free nodes: {perm, a, step = 0, nb}; bar_base keeps counting
+    b200sgd::StepCtl head{};
+    head.perm = p.perm;
+    head.a = p.a;
+    head.step = 0;
+    head.nb_total = c->nb;
+    CUDA_TRY(cudaMemcpyAsync(c->d_ctl, &head, offsetof(b200sgd::StepCtl, bar_base), cudaMemcpyHostToDevice, c->stream));
+    const int replays = (c->nb + c->graph_nodes - 1) / c->graph_nodes;
+    for (int i = 0; i < replays; ++i) CUDA_TRY(cudaGraphLaunch(c->graph_exec, c->stream));
+    *launches += c->nb;
+    return SGD_OK;
+  }
+  CUDA_TRY(cudaMemsetAsync(c->d_bar, 0, sizeof(unsigned int), c->stream));
+  void* args[] = {&p};
+  CUDA_TRY(cudaLaunchCooperativeKernel(c->kc.fn, dim3(c->grid), dim3(32 * (c->kc.NW + 1)), args,
+                                       c->smem_bytes, c->stream));
+  *launches += 1;
+  return SGD_OK;
+}
+
+int check_watchdog(sgd_ctx* c) {
+  unsigned int err = 0;
+  CUDA_TRY(cudaMemcpy(&err, c->d_bar + 1, sizeof(err), cudaMemcpyDeviceToHost));
+  if (err != 0) {
+    cudaMemset(c->d_bar + 1, 0, sizeof(unsigned int));
+    return fail(err == 2 ? SGD_ERR_COMM : SGD_ERR_CUDA,
+                err == 2 ? "peer gradient exchange timed out (a rank did not arrive)"
+                         : "grid barrier timed out (CTAs not co-resident?)");
+  }
+  return SGD_OK;
+}
+
+void fill_timings(const sgd_ctx* c, sgd_timings* t, float shuffle_ms, float loop_ms, int launches, int epochs) {
+  if (!t) return;
+  t->shuffle_ms = shuffle_ms;
+  t->steploop_ms = loop_ms;
+  t->epoch_ms = shuffle_ms + loop_ms;
+  t->steps = c->nb * epochs;
+  t->launches = launches;
+  t->samples = (int64_t)c->nb * c->B * epochs;
+  // DESIGN.md / SURVEY 8d: per step 4*B*C (features, read once) + 4*B (labels) + 4*B (indices)
+  // + 4*C (w read) + 4*C (w write); summed over ranks this is what one rank sees / nranks
+  const int64_t rows = (int64_t)c->nb * c->B / std::max(1, c->cfg.nranks);
+  t->bytes = ((int64_t)4 * rows * c->C + 8 * rows + (int64_t)c->nb * 8 * c->C) * epochs;
+}
+
+}  // namespace
+
+// ================================================================================================
+// C-ABI
+// ================================================================================================
+extern "C" {
+
+int sgd_abi_version(void) { return B200SGD_ABI_VERSION; }
+
+const char* sgd_last_error(void) { return g_last_error.c_str(); }
+
+int sgd_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  int ok = 0;
+  for (int i = 0; i < n; ++i) {
+    cudaDeviceProp pr;
+    if (cudaGetDeviceProperties(&pr, i) == cudaSuccess && pr.major == 10) ++ok;
+  }
+  return ok;
+}
+
+int sgd_read_csv(const char* path, int64_t rows, int32_t cols, float* X, float* y) {
+  if (!path || !X || !y || rows < 0 || cols < 0) return fail(SGD_ERR_ARG, "sgd_read_csv: bad argument");
+  std::string err;
+  const int rc = b200sgd::read_csv(path, rows, cols, X, y, &err);
+  if (rc == -2) return fail(SGD_ERR_IO, err);
+  if (rc == -3) return fail(SGD_ERR_PARSE, err);
+  return SGD_OK;
+}
+
+int sgd_get_filename_from_path(const char* path, char* out, size_t out_cap) {
+  if (!path || !out || out_cap == 0) return fail(SGD_ERR_ARG, "sgd_get_filename_from_path: bad argument");
+  const std::string s = b200sgd::filename_from_path(path);
+  if (s.size() + 1 > out_cap) return fail(SGD_ERR_ARG, "output buffer too small");
+  std::memcpy(out, s.c_str(), s.size() + 1);
+  return SGD_OK;
+}
+
+int sgd_write_experiment_output(const char* path, float shuffle_time, float total_gradient_time,
+                                float gpu_time, float transfer_time, float error) {
+  if (!path) return fail(SGD_ERR_ARG, "null path");
+  if (b200sgd::write_experiment_json(path, shuffle_time, total_gradient_time, gpu_time, transfer_time, error) != 0)
+    return fail(SGD_ERR_IO, std::string("cannot write ") + path);
+  return SGD_OK;
+}
+
+int sgd_init_weights(float* w, int32_t cols) {
+  if (!w || cols < 0) return fail(SGD_ERR_ARG, "sgd_init_weights: bad argument");
+  b200sgd::thrust_minstd_weights(w, cols);
+  return SGD_OK;
+}
+
+int sgd_batch_geometry(int64_t rows, int32_t batch_arg, int32_t* batch_out, int32_t* steps_out) {
+  if (rows <= 0 || rows > 2147483647ll || batch_arg < 0) return fail(SGD_ERR_ARG, "bad rows / batch");
+  int32_t B, nb;
+  batch_geometry(rows, batch_arg, &B, &nb);
+  if (batch_out) *batch_out = B;
+  if (steps_out) *steps_out = nb;
+  return SGD_OK;
+}
+
+int sgd_host_shuffle(int32_t* ind, int64_t rows, uint32_t seed, int32_t skip_epochs, int32_t epochs) {
+  if (!ind || rows < 0 || skip_epochs < 0 || epochs < 0) return fail(SGD_ERR_ARG, "sgd_host_shuffle: bad argument");
+  b200sgd::GlibcRand g(seed);
+  // every pass consumes rows-1 values of the stream (stl_algo.h random_shuffle)
+  if (skip_epochs > 0 && rows > 1) {
+    std::vector<uint32_t> sink(1 << 16);
+    uint64_t left = (uint64_t)skip_epochs * (uint64_t)(rows - 1);
+    while (left) {
+      const size_t n = (size_t)std::min<uint64_t>(left, sink.size());
+      g.raw(sink.data(), n);
+      left -= n;
+    }
+  }
+  for (int e = 0; e < epochs; ++e) b200sgd::exact_shuffle(g, ind, rows);
+  return SGD_OK;
+}
+
+int sgd_create(const sgd_config* cfg, const float* X, const float* y, sgd_ctx** out) {
+  if (!cfg || !out) return fail(SGD_ERR_ARG, "sgd_create: null argument");
+  *out = nullptr;
+  if (cfg->rows <= 0 || cfg->rows > 2147483647ll) return fail(SGD_ERR_ARG, "rows must be in [1, 2^31-1]");
+  if (cfg->cols <= 0) return fail(SGD_ERR_ARG, "cols must be positive");
+  if (cfg->batch < 0 || cfg->batch > cfg->rows) return fail(SGD_ERR_ARG, "batch must be in [0, rows]");
+  if (cfg->nranks < 1 || cfg->nranks > 8 || cfg->rank < 0 || cfg->rank >= cfg->nranks)
+    return fail(SGD_ERR_ARG, "need 1 <= nranks <= 8 and 0 <= rank < nranks");
+  if ((X == nullptr) != (y == nullptr)) return fail(SGD_ERR_ARG, "X and y must both be given or both be NULL");
+
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(SGD_ERR_CUDA, "no CUDA device: libb200sgd has no CPU fallback");
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(SGD_ERR_ARG, "device ordinal out of range");
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major != 10)
+    return fail(SGD_ERR_CUDA, std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) +
+                                  "; this library contains sm_100a code only");
+
+  sgd_ctx* c = new (std::nothrow) sgd_ctx();
+  if (!c) return fail(SGD_ERR_NOMEM, "out of host memory");
+  c->cfg = *cfg;
+  if (c->cfg.shuffle_seed == 0) c->cfg.shuffle_seed = 1;
+  c->R = cfg->rows;
+  c->C = cfg->cols;
+  batch_geometry(c->R, cfg->batch, &c->B, &c->nb);
+  c->ld = ((int64_t)c->C + 1 + 7) / 8 * 8;
+  c->C4 = (c->C + 3) / 4;
+  c->rows_per_rank = (c->R + cfg->nranks - 1) / cfg->nranks;
+  c->row_begin = std::min<int64_t>(c->R, c->rows_per_rank * cfg->rank);
+  c->row_end = std::min<int64_t>(c->R, c->row_begin + c->rows_per_rank);
+  c->local_rows = c->row_end - c->row_begin;
+  c->device = cfg->device;
+  c->num_sms = prop.multiProcessorCount;
+  c->rng.reseed(c->cfg.shuffle_seed);
+
+  auto bail = [&](int rc) {
+    const std::string keep = g_last_error;
+    free_all(c);
+    delete c;
+    g_last_error = keep;
+    return rc;
+  };
+  auto setup = [&]() -> int {
+    SGD_TRY(bind(c));
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreate(&c->ev0));
+    CUDA_TRY(cudaEventCreate(&c->ev1));
+    for (int i = 0; i < 2; ++i) {
+      CUDA_TRY(cudaEventCreateWithFlags(&c->ev_perm[i], cudaEventDisableTiming));
+      CUDA_TRY(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
+    }
+    SGD_TRY(configure_launch(c));
+    const size_t rec_bytes = sizeof(float) * (size_t)std::max<int64_t>(1, c->local_rows) * (size_t)c->ld;
+    if (cudaMalloc(&c->d_rec, rec_bytes) != cudaSuccess) {
+      cudaGetLastError();
+      return fail(SGD_ERR_NOMEM, "cannot allocate " + std::to_string(rec_bytes >> 20) + " MiB of HBM for the data");
+    }
+    CUDA_TRY(cudaMalloc(&c->d_w, sizeof(float) * c->C));
+    CUDA_TRY(cudaMalloc(&c->d_wtrue, sizeof(float) * c->C));
+    for (int i = 0; i < 2; ++i) {
+      CUDA_TRY(cudaMalloc(&c->d_perm[i], sizeof(int32_t) * (size_t)c->R));
+      CUDA_TRY(cudaMallocHost(&c->h_stage[i], sizeof(int32_t) * (size_t)c->R));
+    }
+    if (c->cfg.nranks > 1) {
+      CUDA_TRY(cudaMalloc(&c->d_perm_local, sizeof(int32_t) * (size_t)std::max<int64_t>(1, c->local_rows)));
+      CUDA_TRY(cudaMalloc(&c->d_step_off, sizeof(int64_t) * ((size_t)c->nb + 1)));
+      CUDA_TRY(cudaMalloc(&c->d_counts, sizeof(int64_t) * ((size_t)c->nb + 1)));
+    }
+    CUDA_TRY(cudaMalloc(&c->d_partials, sizeof(float4) * 2 * (size_t)c->grid * c->C4));
+    CUDA_TRY(cudaMemset(c->d_partials, 0, sizeof(float4) * 2 * (size_t)c->grid * c->C4));
+    CUDA_TRY(cudaMalloc(&c->d_wstage, sizeof(float4) * c->C4));
+    CUDA_TRY(cudaMalloc(&c->d_glast, sizeof(float4) * c->C4));
+    CUDA_TRY(cudaMemset(c->d_glast, 0, sizeof(float4) * c->C4));
+    CUDA_TRY(cudaMalloc(&c->d_bar, sizeof(unsigned int) * 2));
+    CUDA_TRY(cudaMemset(c->d_bar, 0, sizeof(unsigned int) * 2));
+    CUDA_TRY(cudaMalloc(&c->d_ctl, sizeof(b200sgd::StepCtl)));
+    CUDA_TRY(cudaMemset(c->d_ctl, 0, sizeof(b200sgd::StepCtl)));
+    if (c->cfg.flags & SGD_FLAG_RESIDUALS) {
+      c->rout_len = c->cfg.nranks > 1 ? c->local_rows : (int64_t)c->nb * c->B;
+      CUDA_TRY(cudaMalloc(&c->d_rout, sizeof(float) * (size_t)std::max<int64_t>(1, c->rout_len)));
+      CUDA_TRY(cudaMemset(c->d_rout, 0, sizeof(float) * (size_t)std::max<int64_t>(1, c->rout_len)));
+    }
+    c->mae_blocks = c->num_sms * 8;
+    CUDA_TRY(cudaMalloc(&c->d_mae, sizeof(double) * c->mae_blocks));
+    if (c->cfg.nranks > 1) {
+      const size_t xb = sizeof(float4) * 2 * (size_t)c->cfg.nranks * c->C4;
+      c->flag_off = (xb + 255) / 256 * 256;
+      c->xchg_bytes = c->flag_off + sizeof(unsigned int) * 2 * (size_t)c->cfg.nranks * c->grid;
+      CUDA_TRY(cudaMalloc(&c->d_xchg_block, c->xchg_bytes));
+      CUDA_TRY(cudaMemset(c->d_xchg_block, 0, c->xchg_bytes));
+      c->peer_block[c->cfg.rank] = c->d_xchg_block;
+    }
+    // main.cu:389-395: weights ~ U(0, 0.01) from the Thrust minstd stream, drawn on the host
+    std::vector<float> w0(c->C);
+    b200sgd::thrust_minstd_weights(w0.data(), c->C);
+    CUDA_TRY(cudaMemcpy(c->d_w, w0.data(), sizeof(float) * c->C, cudaMemcpyHostToDevice));
+    // main.cu:421-426: identity index vector, on host and device
+    c->h_ind.resize((size_t)c->R);
+    for (int64_t i = 0; i < c->R; ++i) c->h_ind[(size_t)i] = (int32_t)i;
+    CUDA_TRY(cudaDeviceSynchronize());
+    return SGD_OK;
+  };
+  int rc = setup();
+  if (rc != SGD_OK) return bail(rc);
+  if (X) {
+    rc = sgd_load_rows(c, 0, c->R, X, y);
+    if (rc != SGD_OK) return bail(rc);
+  }
+  *out = c;
+  return SGD_OK;
+}
+
+void sgd_destroy(sgd_ctx* ctx) {
+  if (!ctx) return;
+  free_all(ctx);
+  delete ctx;
+}
+
+int sgd_load_rows(sgd_ctx* c, int64_t row_begin, int64_t nrows, const float* X, const float* y) {
+  SGD_TRY(check_ctx(c));
+  if (!X || !y || row_begin < 0 || nrows < 0 || row_begin + nrows > c->R)
+    return fail(SGD_ERR_ARG, "sgd_load_rows: bad range");
+  SGD_TRY(bind(c));
+  // intersect with this rank's shard
+  const int64_t lo = std::max(row_begin, c->row_begin), hi = std::min(row_begin + nrows, c->row_end);
+  if (hi > lo) {
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(hi - lo, (64ll << 20) / (4ll * (c->C + 1))));
+    float *dX = nullptr, *dy = nullptr;
+    CUDA_TRY(cudaMalloc(&dX, sizeof(float) * (size_t)chunk * c->C));
+    if (cudaMalloc(&dy, sizeof(float) * (size_t)chunk) != cudaSuccess) {
+      cudaFree(dX);
+      return fail(SGD_ERR_NOMEM, "staging allocation failed");
+    }
+    int rc = SGD_OK;
+    for (int64_t r0 = lo; r0 < hi && rc == SGD_OK; r0 += chunk) {
+      const int64_t n = std::min(chunk, hi - r0);
+      const float* hx = X + (r0 - row_begin) * c->C;
+      const float* hy = y + (r0 - row_begin);
+      cudaError_t e = cudaMemcpyAsync(dX, hx, sizeof(float) * (size_t)n * c->C, cudaMemcpyHostToDevice, c->stream);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(dy, hy, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, c->stream);
+      if (e == cudaSuccess) {
+        const int blocks = (int)std::min<int64_t>((n * c->ld + 255) / 256, (int64_t)c->num_sms * 16);
+        b200sgd::sgd_pack_kernel<<<blocks, 256, 0, c->stream>>>(dX, dy, n, c->C, c->ld,
+                                                                c->d_rec + (r0 - c->row_begin) * c->ld);
+        e = cudaGetLastError();
+      }
+      if (e != cudaSuccess) rc = fail(SGD_ERR_CUDA, std::string("upload failed: ") + cudaGetErrorString(e));
+    }
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    cudaFree(dX);
+    cudaFree(dy);
+    if (rc != SGD_OK) return rc;
+    if (e != cudaSuccess) return fail(SGD_ERR_CUDA, std::string("upload failed: ") + cudaGetErrorString(e));
+  }
+  c->data_loaded = true;
+  return SGD_OK;
+}
+
+int sgd_load_synthetic(sgd_ctx* c, uint64_t seed, int32_t round_fp16) {
+  SGD_TRY(check_ctx(c));
+  SGD_TRY(bind(c));
+  b200sgd::sgd_true_weights_kernel<<<(c->C + 255) / 256, 256, 0, c->stream>>>(seed, c->C, c->d_wtrue);
+  if (c->local_rows > 0) {
+    const int blocks = (int)std::min<int64_t>((c->local_rows + 7) / 8, (int64_t)c->num_sms * 16);
+    b200sgd::sgd_synth_kernel<<<blocks, 256, 0, c->stream>>>(seed, c->row_begin, c->local_rows, c->C, c->ld,
+                                                             c->d_wtrue, round_fp16, c->d_rec);
+  }
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  c->data_loaded = true;
+  c->have_true_w = true;
+  return SGD_OK;
+}
+
+int sgd_get_rows(sgd_ctx* c, int64_t row_begin, int64_t nrows, float* X, float* y) {
+  SGD_TRY(check_ctx(c));
+  if (!X || !y || nrows < 0 || row_begin < c->row_begin || row_begin + nrows > c->row_end)
+    return fail(SGD_ERR_ARG, "sgd_get_rows: range outside this rank's shard");
+  if (!c->data_loaded) return fail(SGD_ERR_STATE, "no data loaded");
+  if (nrows == 0) return SGD_OK;
+  SGD_TRY(bind(c));
+  const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(nrows, (64ll << 20) / (4ll * (c->C + 1))));
+  float *dX = nullptr, *dy = nullptr;
+  CUDA_TRY(cudaMalloc(&dX, sizeof(float) * (size_t)chunk * c->C));
+  if (cudaMalloc(&dy, sizeof(float) * (size_t)chunk) != cudaSuccess) {
+    cudaFree(dX);
+    return fail(SGD_ERR_NOMEM, "staging allocation failed");
+  }
+  cudaError_t e = cudaSuccess;
+  for (int64_t r0 = row_begin; r0 < row_begin + nrows && e == cudaSuccess; r0 += chunk) {
+    const int64_t n = std::min(chunk, row_begin + nrows - r0);
+    const int blocks = (int)std::min<int64_t>((n * (c->C + 1) + 255) / 256, (int64_t)c->num_sms * 16);
+    b200sgd::sgd_unpack_kernel<<<blocks, 256, 0, c->stream>>>(c->d_rec + (r0 - c->row_begin) * c->ld, n, c->C,
+                                                              c->ld, dX, dy);
+    e = cudaGetLastError();
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(X + (r0 - row_begin) * c->C, dX, sizeof(float) * (size_t)n * c->C, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(y + (r0 - row_begin), dy, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  }
+  cudaFree(dX);
+  cudaFree(dy);
+  if (e != cudaSuccess) return fail(SGD_ERR_CUDA, std::string("sgd_get_rows: ") + cudaGetErrorString(e));
+  return SGD_OK;
+}
+
+int sgd_get_true_weights(sgd_ctx* c, float* w_true) {
+  SGD_TRY(check_ctx(c));
+  if (!w_true) return fail(SGD_ERR_ARG, "null output");
+  if (!c->have_true_w) return fail(SGD_ERR_STATE, "sgd_load_synthetic was not called");
+  SGD_TRY(bind(c));
+  CUDA_TRY(cudaMemcpy(w_true, c->d_wtrue, sizeof(float) * c->C, cudaMemcpyDeviceToHost));
+  return SGD_OK;
+}
+
+int sgd_get_weights(sgd_ctx* c, float* w) {
+  SGD_TRY(check_ctx(c));
+  if (!w) return fail(SGD_ERR_ARG, "null output");
+  SGD_TRY(bind(c));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(cudaMemcpy(w, c->d_w, sizeof(float) * c->C, cudaMemcpyDeviceToHost));
+  return SGD_OK;
+}
+
+int sgd_set_weights(sgd_ctx* c, const float* w) {
+  SGD_TRY(check_ctx(c));
+  if (!w) return fail(SGD_ERR_ARG, "null input");
+  SGD_TRY(bind(c));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(cudaMemcpy(c->d_w, w, sizeof(float) * c->C, cudaMemcpyHostToDevice));
+  return SGD_OK;
+}
+
+int sgd_get_config(const sgd_ctx* c, sgd_config* out) {
+  SGD_TRY(check_ctx(c));
+  if (!out) return fail(SGD_ERR_ARG, "null output");
+  *out = c->cfg;
+  out->grid = c->grid;
+  out->reduce = c->reduce_mode;
+  out->engine = c->engine;
+  out->batch = c->B;
+  out->reserved[0] = c->nb;
+  out->reserved[1] = c->nslots;
+  out->reserved[2] = (int32_t)c->smem_bytes;
+  out->reserved[3] = c->kc.KC;
+  out->reserved[4] = c->kc.U;
+  out->reserved[5] = c->kc.NW;
+  out->reserved[6] = (int32_t)c->ld;
+  return SGD_OK;
+}
+
+int64_t sgd_local_rows(const sgd_ctx* c) { return c ? c->local_rows : 0; }
+int64_t sgd_local_row_begin(const sgd_ctx* c) { return c ? c->row_begin : 0; }
+
+// ---- permutation --------------------------------------------------------------------------------
+int sgd_shuffle(sgd_ctx* c) {
+  SGD_TRY(check_ctx(c));
+  SGD_TRY(bind(c));
+  const auto t0 = clk::now();
+  // main.cu:90 / :207: std::random_shuffle(ind_vector.begin(), ind_vector.end()), cumulative
+  b200sgd::exact_shuffle(c->rng, c->h_ind.data(), c->R);
+  const int buf = c->cur ^ 1;
+  CUDA_TRY(cudaEventSynchronize(c->ev_perm[buf]));  // earlier upload out of this staging buffer
+  std::memcpy(c->h_stage[buf], c->h_ind.data(), sizeof(int32_t) * (size_t)c->R);
+  SGD_TRY(upload_perm(c, buf));  // main.cu:91 / :211: batch_indices = ind_vector
+  CUDA_TRY(cudaEventSynchronize(c->ev_perm[buf]));
+  c->cur = buf;
+  c->perm_valid = true;
+  c->last_shuffle_ms = (float)ms_since(t0);
+  return SGD_OK;
+}
+
+int sgd_set_permutation(sgd_ctx* c, const int32_t* perm) {
+  SGD_TRY(check_ctx(c));
+  if (!perm) return fail(SGD_ERR_ARG, "null permutation");
+  for (int64_t i = 0; i < c->R; ++i)
+    if (perm[i] < 0 || perm[i] >= c->R) return fail(SGD_ERR_ARG, "permutation entry out of range");
+  SGD_TRY(bind(c));
+  std::memcpy(c->h_ind.data(), perm, sizeof(int32_t) * (size_t)c->R);
+  const int buf = c->cur ^ 1;
+  CUDA_TRY(cudaEventSynchronize(c->ev_perm[buf]));
+  std::memcpy(c->h_stage[buf], perm, sizeof(int32_t) * (size_t)c->R);
+  SGD_TRY(upload_perm(c, buf));
+  CUDA_TRY(cudaEventSynchronize(c->ev_perm[buf]));
+  c->cur = buf;
+  c->perm_valid = true;
+  c->last_shuffle_ms = 0.f;
+  return SGD_OK;
+}
+
+int sgd_get_permutation(sgd_ctx* c, int32_t* perm) {
+  SGD_TRY(check_ctx(c));
+  if (!perm) return fail(SGD_ERR_ARG, "null output");
+  SGD_TRY(bind(c));
+  if (c->perm_valid) {
+    // read it back from the DEVICE copy the step kernel consumes
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaMemcpy(perm, c->d_perm[c->cur], sizeof(int32_t) * (size_t)c->R, cudaMemcpyDeviceToHost));
+  } else {
+    std::memcpy(perm, c->h_ind.data(), sizeof(int32_t) * (size_t)c->R);
+  }
+  return SGD_OK;
+}
+
+// ---- the step loop ------------------------------------------------------------------------------
+int sgd_epoch(sgd_ctx* c, int32_t epoch, sgd_timings* out) {
+  SGD_TRY(check_ctx(c));
+  if (epoch < 1) return fail(SGD_ERR_ARG, "epoch is 1-based");
+  if (!c->data_loaded) return fail(SGD_ERR_STATE, "no data loaded");
+  if (!c->perm_valid) return fail(SGD_ERR_STATE, "no permutation: call sgd_shuffle or sgd_set_permutation first");
+  SGD_TRY(bind(c));
+  int launches = 0;
+  CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_perm[c->cur], 0));
+  SGD_TRY(bucket_perm(c, c->cur, &launches));
+  CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+  SGD_TRY(launch_epoch(c, epoch, c->cur, &launches));
+  CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+  CUDA_TRY(cudaEventRecord(c->ev_done[c->cur], c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  SGD_TRY(check_watchdog(c));
+  float ms = 0.f;
+  CUDA_TRY(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  fill_timings(c, out, c->last_shuffle_ms, ms, launches, 1);
+  c->last_shuffle_ms = 0.f;
+  return SGD_OK;
+}
+
+int sgd_iteration(sgd_ctx* c, int32_t epoch, sgd_timings* out) {
+  SGD_TRY(sgd_shuffle(c));
+  return sgd_epoch(c, epoch, out);
+}
+
+int sgd_run(sgd_ctx* c, int32_t first_epoch, int32_t num_epochs, sgd_timings* total) {
+  SGD_TRY(check_ctx(c));
+  if (first_epoch < 1 || num_epochs < 0) return fail(SGD_ERR_ARG, "bad epoch range");
+  if (!c->data_loaded) return fail(SGD_ERR_STATE, "no data loaded");
+  SGD_TRY(bind(c));
+  if (num_epochs == 0) {
+    fill_timings(c, total, 0.f, 0.f, 0, 0);
+    return SGD_OK;
+  }
+  const auto t0 = clk::now();
+  std::vector<cudaEvent_t> evs(2 * (size_t)num_epochs, nullptr);
+  auto cleanup = [&] {
+    for (cudaEvent_t e : evs)
+      if (e) cudaEventDestroy(e);
+  };
+  for (auto& e : evs)
+    if (cudaEventCreate(&e) != cudaSuccess) {
+      cleanup();
+      return fail(SGD_ERR_CUDA, "cudaEventCreate failed");
+    }
+  int launches = 0;
+  int rc = SGD_OK;
+  auto stage_next = [&]() -> int {  // shuffle on this thread while the GPU runs the previous epoch
+    b200sgd::exact_shuffle(c->rng, c->h_ind.data(), c->R);
+    const int buf = c->cur ^ 1;
+    CUDA_TRY(cudaEventSynchronize(c->ev_perm[buf]));
+    std::memcpy(c->h_stage[buf], c->h_ind.data(), sizeof(int32_t) * (size_t)c->R);
+    SGD_TRY(upload_perm(c, buf));
+    c->cur = buf;
+    c->perm_valid = true;
+    return SGD_OK;
+  };
+  rc = stage_next();
+  for (int e = 0; e < num_epochs && rc == SGD_OK; ++e) {
+    const int buf = c->cur;
+    auto enqueue = [&]() -> int {
+      CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_perm[buf], 0));
+      SGD_TRY(bucket_perm(c, buf, &launches));
+      CUDA_TRY(cudaEventRecord(evs[2 * e], c->stream));
+      SGD_TRY(launch_epoch(c, first_epoch + e, buf, &launches));
+      CUDA_TRY(cudaEventRecord(evs[2 * e + 1], c->stream));
+      CUDA_TRY(cudaEventRecord(c->ev_done[buf], c->stream));
+      return SGD_OK;
+    };
+    rc = enqueue();
+    if (rc == SGD_OK && e + 1 < num_epochs) rc = stage_next();  // overlaps with the kernel above
+  }
+  cudaError_t se = cudaStreamSynchronize(c->stream);
+  if (rc == SGD_OK && se != cudaSuccess) rc = fail(SGD_ERR_CUDA, std::string("epoch loop: ") + cudaGetErrorString(se));
+  if (rc == SGD_OK) rc = check_watchdog(c);
+  float loop_ms = 0.f;
+  if (rc == SGD_OK) {
+    for (int e = 0; e < num_epochs; ++e) {
+      float ms = 0.f;
+      if (c->nb > 0 && cudaEventElapsedTime(&ms, evs[2 * e], evs[2 * e + 1]) == cudaSuccess) loop_ms += ms;
+    }
+  }
+  cleanup();
+  if (rc != SGD_OK) return rc;
+  const float wall = (float)ms_since(t0);
+  fill_timings(c, total, std::max(0.f, wall - loop_ms), loop_ms, launches, num_epochs);
+  if (total) total->epoch_ms = wall;
+  return SGD_OK;
+}
+
+int sgd_get_residuals(sgd_ctx* c, float* r, int64_t count) {
+  SGD_TRY(check_ctx(c));
+  if (!c->d_rout) return fail(SGD_ERR_STATE, "context was created without SGD_FLAG_RESIDUALS");
+  if (!r || count < 0 || count > c->rout_len) return fail(SGD_ERR_ARG, "bad residual count");
+  SGD_TRY(bind(c));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(cudaMemcpy(r, c->d_rout, sizeof(float) * (size_t)count, cudaMemcpyDeviceToHost));
+  return SGD_OK;
+}
+
+int sgd_get_last_gradient(sgd_ctx* c, float* g) {
+  SGD_TRY(check_ctx(c));
+  if (!g) return fail(SGD_ERR_ARG, "null output");
+  SGD_TRY(bind(c));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  std::vector<float> tmp((size_t)c->C4 * 4);
+  CUDA_TRY(cudaMemcpy(tmp.data(), c->d_glast, sizeof(float) * tmp.size(), cudaMemcpyDeviceToHost));
+  std::memcpy(g, tmp.data(), sizeof(float) * c->C);
+  return SGD_OK;
+}
+
+int sgd_mean_abs_error(sgd_ctx* c, float* mae_out, double* sum_out) {
+  SGD_TRY(check_ctx(c));
+  if (!c->data_loaded) return fail(SGD_ERR_STATE, "no data loaded");
+  SGD_TRY(bind(c));
+  double total = 0.0;
+  if (c->local_rows > 0) {
+    const int blocks = (int)std::min<int64_t>(c->mae_blocks, (c->local_rows + 7) / 8);
+    b200sgd::sgd_mae_kernel<<<blocks, 256, sizeof(float) * 4 * c->C4, c->stream>>>(
+        c->d_rec, c->ld, c->C, c->local_rows, c->d_w, c->d_mae);
+    CUDA_TRY(cudaGetLastError());
+    std::vector<double> h((size_t)blocks);
+    CUDA_TRY(cudaMemcpyAsync(h.data(), c->d_mae, sizeof(double) * blocks, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    for (double v : h) total += v;
+  }
+  if (sum_out) *sum_out = total;
+  // sgd_thrust.cu:134: return error_sum / R
+  if (mae_out) *mae_out = (float)(total / (double)(c->cfg.nranks > 1 ? std::max<int64_t>(1, c->local_rows) : c->R));
+  return SGD_OK;
+}
+
+// ---- peers --------------------------------------------------------------------------------------
+int sgd_peer_export(sgd_ctx* c, void* handle_out) {
+  SGD_TRY(check_ctx(c));
+  if (!handle_out) return fail(SGD_ERR_ARG, "null handle");
+  if (c->cfg.nranks < 2) return fail(SGD_ERR_STATE, "single-rank context has no exchange buffer");
+  SGD_TRY(bind(c));
+  static_assert(sizeof(cudaIpcMemHandle_t) + 16 <= SGD_PEER_HANDLE_BYTES, "handle too small");
+  std::memset(handle_out, 0, SGD_PEER_HANDLE_BYTES);
+  cudaIpcMemHandle_t h;
+  CUDA_TRY(cudaIpcGetMemHandle(&h, c->d_xchg_block));
+  std::memcpy(handle_out, &h, sizeof(h));
+  const uint64_t meta[2] = {(uint64_t)c->xchg_bytes, (uint64_t)c->grid};
+  std::memcpy((char*)handle_out + sizeof(h), meta, sizeof(meta));
+  return SGD_OK;
+}
+
+int sgd_peer_import(sgd_ctx* c, int32_t peer_rank, const void* handle) {
+  SGD_TRY(check_ctx(c));
+  if (!handle || peer_rank < 0 || peer_rank >= c->cfg.nranks) return fail(SGD_ERR_ARG, "bad peer");
+  if (peer_rank == c->cfg.rank) return SGD_OK;
+  SGD_TRY(bind(c));
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle, sizeof(h));
+  uint64_t meta[2];
+  std::memcpy(meta, (const char*)handle + sizeof(h), sizeof(meta));
+  if (meta[0] != c->xchg_bytes || meta[1] != (uint64_t)c->grid)
+    return fail(SGD_ERR_COMM, "peer was configured with a different shape / grid");
+  void* ptr = nullptr;
+  cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(SGD_ERR_COMM, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+  }
+  c->peer_block[peer_rank] = ptr;
+  c->peer_open[peer_rank] = true;
+  return SGD_OK;
+}
+
+int sgd_peer_ready(sgd_ctx* c) {
+  SGD_TRY(check_ctx(c));
+  for (int r = 0; r < c->cfg.nranks; ++r)
+    if (!c->peer_block[r]) return fail(SGD_ERR_STATE, "peer " + std::to_string(r) + " was not imported");
+  c->peers_ready = true;
+  return SGD_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,188 @@
+// host_io.cpp -- host-side L1 layer of the reference behind the C-ABI:
+//   read_csv                 (sgd_io.cu:38-77)   -> b200sgd::read_csv   (parallel, bounds-checked)
+//   get_filename_from_path   (sgd_io.cu:107-113) -> b200sgd::filename_from_path
+//   ExperimentOutput/write_json (sgd_io.cuh:28-60, sgd_io.cu:82-105) -> b200sgd::write_experiment_json
+// No jsoncpp: the five-key object is emitted directly in the byte layout jsoncpp 0.10.5's
+// StyledWriter produces (3-space indent, `"key" : value`, keys sorted, "%.17g", trailing newline).
+#include "host_io.hpp"
+
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <atomic>
+#include <charconv>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+namespace b200sgd {
+
+namespace {
+
+// One cell -> float with std::stof's semantics (strtof: leading blanks, optional sign, longest
+// valid prefix, trailing junk ignored).  from_chars is the fast path; anything it does not take
+// verbatim goes through strtof so that odd spellings ("+2", " .5", "1e3", "inf") agree with stof.
+inline bool parse_cell(const char* b, const char* e, float* out) {
+  while (b < e && (*b == ' ' || *b == '\t')) ++b;
+  if (b == e) return false;
+  if (*b != '+') {
+    auto res = std::from_chars(b, e, *out);
+    if (res.ec == std::errc()) return true;
+  }
+  char tmp[64];
+  size_t n = (size_t)(e - b);
+  if (n >= sizeof(tmp)) n = sizeof(tmp) - 1;
+  std::memcpy(tmp, b, n);
+  tmp[n] = 0;
+  char* end = tmp;
+  float v = std::strtof(tmp, &end);
+  if (end == tmp) return false;  // std::stof would throw std::invalid_argument
+  *out = v;
+  return true;
+}
+
+// Parses the lines in [b, e) (whole lines) starting at row `row`.  Returns 0 or a negative code.
+int parse_lines(const char* b, const char* e, int64_t row, int64_t R, int32_t C, float* X, float* y) {
+  while (b < e) {
+    const char* eol = (const char*)std::memchr(b, '\n', (size_t)(e - b));
+    if (!eol) eol = e;
+    const char* le = eol;
+    if (le > b && le[-1] == '\r') --le;
+    if (le > b) {
+      if (row >= R) return -3;
+      int32_t col = 0;
+      const char* p = b;
+      while (true) {
+        const char* q = (const char*)std::memchr(p, ',', (size_t)(le - p));
+        const char* ce = q ? q : le;
+        float v;
+        if (!parse_cell(p, ce, &v)) return -3;
+        if (col > C) return -3;  // the reference would write into the next row here
+        if (col != C) X[row * (int64_t)C + col] = v; else y[row] = v;
+        ++col;
+        if (!q) break;
+        p = q + 1;
+        if (p == le) break;  // trailing comma: getline yields no further cell
+      }
+    }  // a blank line only bumps the row counter, exactly as the reference's getline loop does
+    ++row;
+    b = eol + 1;
+  }
+  return 0;
+}
+
+}  // namespace
+
+int read_csv(const char* path, int64_t R, int32_t C, float* X, float* y, std::string* err) {
+  int fd = ::open(path, O_RDONLY);
+  if (fd < 0) {
+    if (err) *err = std::string("Could not open file: ") + path;
+    return -2;
+  }
+  struct stat st;
+  if (fstat(fd, &st) != 0) { ::close(fd); if (err) *err = "fstat failed"; return -2; }
+  const size_t len = (size_t)st.st_size;
+  std::memset(X, 0, sizeof(float) * (size_t)R * (size_t)C);  // thrust::host_vector zero-fills
+  std::memset(y, 0, sizeof(float) * (size_t)R);
+  if (len == 0) { ::close(fd); return 0; }
+  const char* base = (const char*)mmap(nullptr, len, PROT_READ, MAP_PRIVATE, fd, 0);
+  ::close(fd);
+  if (base == MAP_FAILED) { if (err) *err = "mmap failed"; return -2; }
+  madvise((void*)base, len, MADV_SEQUENTIAL);
+
+  unsigned hw = std::thread::hardware_concurrency();
+  size_t nchunks = len < (size_t)(4u << 20) ? 1 : (hw ? hw : 4);
+  if (nchunks > 64) nchunks = 64;
+  // chunk boundaries snapped to line starts
+  std::vector<size_t> cut(nchunks + 1, len);
+  cut[0] = 0;
+  for (size_t k = 1; k < nchunks; ++k) {
+    size_t pos = len / nchunks * k;
+    if (pos < cut[k - 1]) pos = cut[k - 1];
+    const char* nl = (const char*)std::memchr(base + pos, '\n', len - pos);
+    cut[k] = nl ? (size_t)(nl - base) + 1 : len;
+  }
+  // rows (= newline count) per chunk -> first row of every chunk
+  std::vector<int64_t> rows_in(nchunks, 0);
+  {
+    std::vector<std::thread> th;
+    for (size_t k = 0; k < nchunks; ++k)
+      th.emplace_back([&, k] {
+        int64_t n = 0;
+        const char* p = base + cut[k];
+        const char* e = base + cut[k + 1];
+        while (p < e) {
+          const char* nl = (const char*)std::memchr(p, '\n', (size_t)(e - p));
+          if (!nl) { ++n; break; }  // last line without EOL
+          ++n;
+          p = nl + 1;
+        }
+        rows_in[k] = n;
+      });
+    for (auto& t : th) t.join();
+  }
+  std::vector<int64_t> row0(nchunks, 0);
+  for (size_t k = 1; k < nchunks; ++k) row0[k] = row0[k - 1] + rows_in[k - 1];
+  std::atomic<int> rc{0};
+  {
+    std::vector<std::thread> th;
+    for (size_t k = 0; k < nchunks; ++k)
+      th.emplace_back([&, k] {
+        int r = parse_lines(base + cut[k], base + cut[k + 1], row0[k], R, C, X, y);
+        if (r != 0) rc.store(r);
+      });
+    for (auto& t : th) t.join();
+  }
+  munmap((void*)base, len);
+  if (rc.load() != 0 && err)
+    *err = std::string("CSV has more rows/columns than announced or an unparsable cell: ") + path;
+  return rc.load();
+}
+
+std::string filename_from_path(const std::string& filepath) {
+  // sgd_io.cu:107-113: strip up to the last '/', then from the last '.'
+  auto pos = filepath.find_last_of('/');
+  std::string name = filepath.substr(pos + 1);  // npos + 1 == 0
+  pos = name.find_last_of('.');
+  return name.substr(0, pos);
+}
+
+static std::string json_number(float f) {
+  // Json::Value(float) promotes to double; valueToString(double) prints "%.17g"
+  const double v = (double)f;
+  char buf[40];
+  if (std::isfinite(v)) std::snprintf(buf, sizeof(buf), "%.17g", v);
+  else if (v != v) std::snprintf(buf, sizeof(buf), "null");
+  else std::snprintf(buf, sizeof(buf), v < 0 ? "-1e+9999" : "1e+9999");
+  return buf;
+}
+
+std::string experiment_json(float shuffle_time, float total_gradient_time, float gpu_time,
+                            float transfer_time, float error) {
+  // keys in jsoncpp's (sorted) order
+  std::string s = "{\n";
+  s += "   \"error\" : " + json_number(error) + ",\n";
+  s += "   \"gpu_time\" : " + json_number(gpu_time) + ",\n";
+  s += "   \"shuffle_time\" : " + json_number(shuffle_time) + ",\n";
+  s += "   \"total_gradient_time\" : " + json_number(total_gradient_time) + ",\n";
+  s += "   \"transfer_time\" : " + json_number(transfer_time) + "\n";
+  s += "}\n";
+  return s;
+}
+
+int write_experiment_json(const char* path, float shuffle_time, float total_gradient_time,
+                          float gpu_time, float transfer_time, float error) {
+  FILE* f = std::fopen(path, "w");
+  if (!f) return -2;
+  const std::string s = experiment_json(shuffle_time, total_gradient_time, gpu_time, transfer_time, error);
+  const size_t n = std::fwrite(s.data(), 1, s.size(), f);
+  std::fclose(f);
+  return n == s.size() ? 0 : -2;
+}
+
+}  // namespace b200sgd

@@ -1,0 +1,830 @@
+// sgd_kernels.cuh -- hand-written sm_100a kernels of the fused SGD step.
+//
+// What the reference does per mini-batch with >= 7 launches (thrust::fill, cublasScopy+Sgemv or
+// calculate_gradients, scale_matrix_rows_by_vector, calculate_scaled_col_sums / reduce_by_key,
+// two thrust::transform; main.cu:94-160, :227-300, sgd_thrust.cu:140-402) and ~20*B*C bytes of HBM
+// traffic happens here in ONE kernel that reads every batch row from HBM exactly once:
+//
+//   producer warp : walks the permutation, one `cp.async.bulk` (TMA, SASS UBLKCP) per row from the
+//                   row's record in HBM into a ring of shared-memory row slots guarded by
+//                   full/empty mbarriers.  It runs ahead of the consumers by up to the whole ring,
+//                   ACROSS step boundaries: the rows of step k+1 do not depend on the weights, so
+//                   HBM keeps streaming while step k's grid reduction is in flight.
+//   consumer warps: one row per warp at a time (U rows unrolled): dot product of the staged row
+//                   with w (float4 smem reads, warp-shuffle reduction), residual r = x.w - y, and
+//                   g += r * x accumulated in registers FROM THE SAME staged row.
+//   step tail     : per-CTA partial gradient -> global, grid barrier (red.release / ld.acquire on
+//                   a monotone counter), deterministic fixed-order sum of the partials, fused
+//                   update w = a * (g / B) + w (sgd_thrust.cu:269 then main.cu:287-290), new
+//                   weights back into every CTA's shared memory.  No atomics on data, so replicas
+//                   and reruns are bit-identical.
+//
+// Record layout in HBM: row i = [x_0 .. x_{C-1}, y_i, 0-pad] with a leading dimension of
+// ld = roundup(C+1, 8) floats, so a row is one 32-byte-sector-aligned block that carries its label.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200sgd {
+
+constexpr int kMaxSlots = 256;  // ring slots (rows in flight per CTA), power of two
+
+// Device-resident control block of the GRAPH engine: the captured step kernels carry no per-step
+// arguments; they read the step index, the step size and the permutation from here and the last
+// CTA advances it, so one instantiated graph serves every epoch.
+struct StepCtl {
+  const int32_t* perm;  // permutation of the running epoch
+  float a;              // step size of the running epoch
+  int32_t step;         // next step to execute
+  int32_t nb_total;     // steps per epoch; launches beyond it exit at once
+  uint32_t bar_base;    // value of the grid-barrier counter when the next launch starts
+};
+
+struct EpochParams {
+  const float* rec;         // records, ld floats each
+  int64_t ld;               // floats per record (multiple of 8)
+  int32_t C;                // features
+  int32_t C4;               // float4 groups covering the features: ceil(C/4)
+  const int32_t* perm;      // LOCAL row numbers of this rank's rows, grouped by step
+  const int64_t* step_off;  // nb+1 offsets into perm, or nullptr: step s is [s*B, (s+1)*B)
+  int64_t B;                // global batch size (the divisor of the gradient, main.cu:274)
+  int32_t nb;               // steps in this launch
+  int32_t first_step;       // index of the first step (graph engine: one step per launch)
+  float a;                  // -(lr / pow(epoch, 0.25))              main.cu:144 / :282
+  float* w;                 // C weights (global), updated in place
+  float4* partials;         // [2][grid][C4] per-CTA partial gradients (double-buffered by step)
+  float4* w_stage;          // [C4] staging of new weights (SCATTER mode broadcast)
+  float* g_last;            // [4*C4] gradient of the most recent step (sgd_get_last_gradient)
+  float* r_out;             // optional residuals, indexed like perm
+  unsigned int* bar;        // grid barrier counter, zeroed by the host before the launch
+  unsigned int* err;        // watchdog error word (0 = fine), see SpinGuard
+  int32_t reduce_mode;      // 1 = ALLGATHER, 2 = SCATTER
+  int32_t nslots;           // ring slots (power of two)
+  int32_t slot_log2;
+  uint32_t slot_bytes;      // ld * 4
+  // multi-GPU exchange (nranks > 1): see sgd_peer_* in b200sgd.h
+  int32_t rank, nranks;
+  float4* xchg_local;       // [2][nranks][C4] inbox of this rank (peers write into it)
+  float4* xchg_peer[8];     // same buffer of every rank, mapped into this process
+  unsigned int* flag_local; // [2][nranks][grid-slices] arrival flags of this rank's inbox
+  unsigned int* flag_peer[8];
+  uint32_t epoch_tag;       // value flags must reach: monotone across launches
+  StepCtl* ctl;             // GRAPH engine only (nullptr for the persistent engine)
+};
+
+// ------------------------------------------------------------------------------------------------
+// PTX helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+// one row: global -> shared through the TMA unit, completion counted in bytes on `bar`
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes,
+                                         uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(dst),
+      "l"(src), "r"(bytes), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+template <int kThreads>
+__device__ __forceinline__ void consumer_bar() {
+  asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(unsigned int* p, unsigned int v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ float4 ld_cg_f4(const float4* p) { return __ldcg(p); }
+__device__ __forceinline__ void st_cg_f4(float4* p, float4 v) { __stcg(p, v); }
+__device__ __forceinline__ float4 ld_volatile_f4(const float4* p) {
+  float4 v;
+  asm volatile("ld.volatile.global.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 f4_add(float4 a, float4 b) {
+  return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+}
+__device__ __forceinline__ float4 f4_shfl_xor(float4 v, int m) {
+  v.x = __shfl_xor_sync(0xffffffffu, v.x, m);
+  v.y = __shfl_xor_sync(0xffffffffu, v.y, m);
+  v.z = __shfl_xor_sync(0xffffffffu, v.z, m);
+  v.w = __shfl_xor_sync(0xffffffffu, v.w, m);
+  return v;
+}
+
+// Grid barrier over the consumer threads of all CTAs.  `target` = arrivals expected in total since
+// the counter was zeroed.  All consumer threads call it; their earlier global stores are visible
+// to every CTA once it returns (bar.sync makes them cumulative to thread 0's release).
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// Watchdog for the inter-CTA / inter-GPU spin loops: a kernel that can never finish would take the
+// whole GPU box down with it.  After kSpinTimeoutNs the waiter records an error code in *err and
+// gives up (so does every later wait, at once); the host turns that into SGD_ERR_CUDA/COMM.
+constexpr unsigned long long kSpinTimeoutNs = 4000000000ull;
+struct SpinGuard {
+  unsigned int spins = 0;
+  unsigned long long t0 = 0;
+  __device__ __forceinline__ bool expired(unsigned int* err, unsigned int code) {
+    if ((++spins & 1023u) != 0) return false;
+    if (*reinterpret_cast<volatile unsigned int*>(err) != 0u) return true;
+    const unsigned long long now = global_timer_ns();
+    if (t0 == 0) { t0 = now; return false; }
+    if (now - t0 > kSpinTimeoutNs) { atomicCAS(err, 0u, code); return true; }
+    return false;
+  }
+};
+template <int kThreads>
+__device__ __forceinline__ void grid_barrier(unsigned int* ctr, unsigned int target, int ctid,
+                                             unsigned int* err) {
+  consumer_bar<kThreads>();
+  if (ctid == 0) {
+    red_release_gpu_add(ctr, 1u);
+    SpinGuard guard;
+    while ((int)(ld_acquire_gpu(ctr) - target) < 0) {
+      if (guard.expired(err, 1u)) break;
+    }
+  }
+  consumer_bar<kThreads>();
+}
+
+// Slice of [0, n) owned by part `k` of `parts` (balanced, contiguous).
+__device__ __forceinline__ int64_t slice_lo(int64_t n, int k, int parts) {
+  return (n * (int64_t)k) / parts;
+}
+
+// Deterministic sum over the `nsrc` float4 vectors src[i * stride + f], i ascending in a fixed tree:
+// thread q of a Q-lane group (Q power of two, lanes contiguous and group-aligned inside a warp) adds
+// sources q, q+Q, ... in order, then a xor-butterfly combines the Q partial sums.  Every lane of
+// the group ends with the same total.  All 32 lanes of a warp must call it together.
+template <bool kVolatile>
+__device__ __forceinline__ float4 tree_sum_sources(const float4* src, int64_t stride, int f,
+                                                   int nsrc, int q, int Q, bool active) {
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (active) {
+    int i = q;
+    // 4 independent loads in flight per thread
+    for (; i + 3 * Q < nsrc; i += 4 * Q) {
+      float4 v0, v1, v2, v3;
+      if (kVolatile) {
+        v0 = ld_volatile_f4(src + (int64_t)i * stride + f);
+        v1 = ld_volatile_f4(src + (int64_t)(i + Q) * stride + f);
+        v2 = ld_volatile_f4(src + (int64_t)(i + 2 * Q) * stride + f);
+        v3 = ld_volatile_f4(src + (int64_t)(i + 3 * Q) * stride + f);
+      } else {
+        v0 = ld_cg_f4(src + (int64_t)i * stride + f);
+        v1 = ld_cg_f4(src + (int64_t)(i + Q) * stride + f);
+        v2 = ld_cg_f4(src + (int64_t)(i + 2 * Q) * stride + f);
+        v3 = ld_cg_f4(src + (int64_t)(i + 3 * Q) * stride + f);
+      }
+      acc = f4_add(acc, v0);
+      acc = f4_add(acc, v1);
+      acc = f4_add(acc, v2);
+      acc = f4_add(acc, v3);
+    }
+    for (; i < nsrc; i += Q) {
+      float4 v = kVolatile ? ld_volatile_f4(src + (int64_t)i * stride + f)
+                           : ld_cg_f4(src + (int64_t)i * stride + f);
+      acc = f4_add(acc, v);
+    }
+  }
+  for (int m = 1; m < Q; m <<= 1) acc = f4_add(acc, f4_shfl_xor(acc, m));
+  return acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// The epoch kernel.
+//   KC = float4 column chunks per lane (covers C <= 128*KC)
+//   U  = rows a warp processes concurrently (independent chains hide the shuffle latency)
+//   NW = consumer warps; warp NW is the producer.  Block = 32*(NW+1) threads, 1 CTA per SM.
+// ------------------------------------------------------------------------------------------------
+template <int KC, int NW>
+struct EpochSmem {
+  static constexpr size_t kBarBytes = 2 * kMaxSlots * sizeof(uint64_t);
+  static constexpr size_t kWBytes = 32 * KC * sizeof(float4);
+  static constexpr size_t kGredBytes = (size_t)NW * 32 * KC * sizeof(float4);
+  static constexpr size_t kFixed = kBarBytes + kWBytes + kGredBytes;
+};
+
+template <int KC, int U, int NW>
+__global__ void __launch_bounds__(32 * (NW + 1), 1) sgd_epoch_kernel(const EpochParams p) {
+  constexpr int kThreads = 32 * (NW + 1);
+  constexpr int kCT = 32 * NW;  // consumer threads
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw);
+  uint64_t* empty_bar = full_bar + kMaxSlots;
+  float4* w_s = reinterpret_cast<float4*>(smem_raw + EpochSmem<KC, NW>::kBarBytes);
+  float4* gred = w_s + 32 * KC;
+  unsigned char* ring = smem_raw + EpochSmem<KC, NW>::kFixed;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const int cta = blockIdx.x;
+  const int G = gridDim.x;
+  const int nslots = p.nslots;
+  const uint32_t slot_mask = (uint32_t)nslots - 1u;
+  const uint32_t full0 = smem_u32(full_bar);
+  const uint32_t empty0 = smem_u32(empty_bar);
+  const uint32_t ring0 = smem_u32(ring);
+
+  // GRAPH engine: per-launch state comes from the control block (uniform over the whole grid)
+  int first_step = p.first_step;
+  float a_step = p.a;
+  const int32_t* perm = p.perm;
+  unsigned int bar_base = 0;
+  if (p.ctl != nullptr) {
+    first_step = p.ctl->step;
+    if (first_step >= p.ctl->nb_total) return;  // surplus node of the last graph replay
+    a_step = p.ctl->a;
+    perm = p.ctl->perm;
+    bar_base = p.ctl->bar_base;
+  }
+
+  if (tid == 0) {
+    for (int i = 0; i < nslots; ++i) {
+      mbar_init(full0 + 8u * i, 1);
+      mbar_init(empty0 + 8u * i, 1);
+    }
+    fence_barrier_init();
+  }
+  // weights -> shared (zero beyond C so that the label / pad columns never contribute)
+  for (int c = tid; c < 128 * KC; c += kThreads)
+    reinterpret_cast<float*>(w_s)[c] = (c < p.C) ? p.w[c] : 0.0f;
+  __syncthreads();
+
+  auto step_begin = [&](int s) -> int64_t {
+    const int64_t sa = (int64_t)first_step + s;
+    return p.step_off ? p.step_off[sa] : sa * p.B;
+  };
+  auto step_rows = [&](int s) -> int64_t {
+    const int64_t sa = (int64_t)first_step + s;
+    return p.step_off ? (p.step_off[sa + 1] - p.step_off[sa]) : p.B;
+  };
+
+  if (warp == NW) {
+    // ===================================== PRODUCER =====================================
+    // Row sequence of this CTA: for every step its contiguous slice of the batch, numbered
+    // q = 0,1,2,... across steps; row q lives in slot q % nslots.  One round = up to 32 rows,
+    // one per lane; the indices of round k+1 are loaded before round k is issued.
+    const int per_round = nslots < 32 ? nslots : 32;
+    int s = 0;
+    int64_t lo = 0, n = 0, j0 = 0;  // current step slice [lo, lo+n), next unissued row j0
+    int64_t off = 0;
+    uint64_t q0 = 0;                // sequence number of row j0
+    auto enter_step = [&](int ss) {
+      n = 0;
+      if (ss < p.nb) {
+        const int64_t rows = step_rows(ss);
+        off = step_begin(ss);
+        lo = slice_lo(rows, cta, G);
+        n = slice_lo(rows, cta + 1, G) - lo;
+      }
+    };
+    enter_step(0);
+    while (s < p.nb && n == 0) enter_step(++s);
+    int cnt = 0;
+    int32_t idx = 0;
+    if (s < p.nb) {
+      cnt = (int)((n - j0) < per_round ? (n - j0) : per_round);
+      if (lane < cnt) idx = __ldg(perm + off + lo + j0 + lane);
+    }
+    while (cnt > 0) {
+      const int cur_cnt = cnt;
+      const int32_t cur_idx = idx;
+      const uint64_t cur_q0 = q0;
+      // advance the iterator and prefetch the next round's indices
+      j0 += cur_cnt;
+      q0 += (uint64_t)cur_cnt;
+      if (j0 >= n) {
+        j0 = 0;
+        do { enter_step(++s); } while (s < p.nb && n == 0);
+      }
+      cnt = 0;
+      if (s < p.nb) {
+        cnt = (int)((n - j0) < per_round ? (n - j0) : per_round);
+        if (lane < cnt) idx = __ldg(perm + off + lo + j0 + lane);
+      }
+      // issue the current round: one TMA bulk copy per row
+      if (lane < cur_cnt) {
+        const uint64_t q = cur_q0 + (uint64_t)lane;
+        const uint32_t slot = (uint32_t)q & slot_mask;
+        const uint32_t use = (uint32_t)(q >> p.slot_log2);
+        mbar_wait(empty0 + 8u * slot, (use & 1u) ^ 1u);  // passes at once on the first use
+        const uint32_t fb = full0 + 8u * slot;
+        mbar_arrive_expect_tx(fb, p.slot_bytes);
+        bulk_g2s(ring0 + slot * p.slot_bytes, p.rec + (int64_t)cur_idx * p.ld, p.slot_bytes, fb);
+      }
+      __syncwarp();
+    }
+    return;
+  }
+
+  // ======================================= CONSUMERS =======================================
+  const int ctid = tid;  // consumer warps are warps 0..NW-1
+  const float Bf = (float)p.B;
+  const float a = a_step;
+  const int C4 = p.C4;
+  unsigned int bar_count = 0;  // grid barriers passed so far
+  uint64_t qbase = 0;          // sequence number of the first row of the current step
+  float4 g[KC];
+
+  // w = a * (g / B) + w for one float4 column group (sgd_thrust.cu:269, main.cu:147-150 / :287-290)
+  auto updated = [&](int f, float4 tot, float4* g_scaled) -> float4 {
+    float4 wv = w_s[f];
+    const float4 gs = make_float4(tot.x / Bf, tot.y / Bf, tot.z / Bf, tot.w / Bf);
+    wv.x = fmaf(a, gs.x, wv.x);
+    wv.y = fmaf(a, gs.y, wv.y);
+    wv.z = fmaf(a, gs.z, wv.z);
+    wv.w = fmaf(a, gs.w, wv.w);
+    const int c0 = f * 4;  // columns >= C (label, padding) keep weight 0
+    if (c0 + 0 >= p.C) wv.x = 0.f;
+    if (c0 + 1 >= p.C) wv.y = 0.f;
+    if (c0 + 2 >= p.C) wv.z = 0.f;
+    if (c0 + 3 >= p.C) wv.w = 0.f;
+    *g_scaled = gs;
+    return wv;
+  };
+
+  for (int s = 0; s < p.nb; ++s) {
+    const int64_t rows = step_rows(s);
+    const int64_t off = step_begin(s);
+    const int64_t lo = slice_lo(rows, cta, G);
+    const int64_t n = slice_lo(rows, cta + 1, G) - lo;
+#pragma unroll
+    for (int k = 0; k < KC; ++k) g[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    // ---- rows of this step: warp `warp` takes rows warp, warp+NW, ... ; U at a time ----
+    for (int64_t j = warp; j < n; j += (int64_t)NW * U) {
+      float4 x[U][KC];
+      float dot[U], y[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t ju = j + (int64_t)u * NW;
+        dot[u] = 0.f;
+        y[u] = 0.f;
+        if (ju < n) {  // warp-uniform
+          const uint64_t q = qbase + (uint64_t)ju;
+          const uint32_t slot = (uint32_t)q & slot_mask;
+          const uint32_t use = (uint32_t)(q >> p.slot_log2);
+          mbar_wait(full0 + 8u * slot, use & 1u);
+          const float4* row = reinterpret_cast<const float4*>(ring + (size_t)slot * p.slot_bytes);
+#pragma unroll
+          for (int k = 0; k < KC; ++k) {
+            const int f = k * 32 + lane;
+            x[u][k] = (f < C4) ? row[f] : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          y[u] = reinterpret_cast<const float*>(row)[p.C];  // label rides in the record
+          __syncwarp();
+          if (lane == 0) mbar_arrive(empty0 + 8u * slot);  // row is in registers: free the slot
+        } else {
+#pragma unroll
+          for (int k = 0; k < KC; ++k) x[u][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < KC; ++k) {
+        const float4 wv = w_s[k * 32 + lane];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          dot[u] = fmaf(x[u][k].x, wv.x, dot[u]);
+          dot[u] = fmaf(x[u][k].y, wv.y, dot[u]);
+          dot[u] = fmaf(x[u][k].z, wv.z, dot[u]);
+          dot[u] = fmaf(x[u][k].w, wv.w, dot[u]);
+        }
+      }
+#pragma unroll
+      for (int m = 16; m >= 1; m >>= 1) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) dot[u] += __shfl_xor_sync(0xffffffffu, dot[u], m);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        // r = x.w - y   (sgd_thrust.cu:43-48; Sgemv with beta = -1, sgd_thrust.cu:352-364);
+        // rows beyond the slice have x = 0, y = 0 -> r = 0 and contribute nothing
+        const float r = dot[u] - y[u];
+#pragma unroll
+        for (int k = 0; k < KC; ++k) {
+          g[k].x = fmaf(r, x[u][k].x, g[k].x);
+          g[k].y = fmaf(r, x[u][k].y, g[k].y);
+          g[k].z = fmaf(r, x[u][k].z, g[k].z);
+          g[k].w = fmaf(r, x[u][k].w, g[k].w);
+        }
+        if (p.r_out != nullptr && lane == 0) {
+          const int64_t ju = j + (int64_t)u * NW;
+          if (ju < n) p.r_out[off + lo + ju] = r;
+        }
+      }
+    }
+    qbase += (uint64_t)n;
+
+    // ---- CTA partial: fixed-order sum over the warps ----
+#pragma unroll
+    for (int k = 0; k < KC; ++k) gred[(warp * KC + k) * 32 + lane] = g[k];
+    consumer_bar<kCT>();
+    const int par = (first_step + s) & 1;
+    float4* my_part = p.partials + ((int64_t)par * G + cta) * C4;
+    for (int f = ctid; f < C4; f += kCT) {
+      const int k = f >> 5, l = f & 31;
+      float4 acc = gred[(0 * KC + k) * 32 + l];
+#pragma unroll
+      for (int wq = 1; wq < NW; ++wq) acc = f4_add(acc, gred[(wq * KC + k) * 32 + l]);
+      st_cg_f4(my_part + f, acc);
+    }
+
+    // ---- grid reduction + fused update ----
+    bar_count += 1;
+    grid_barrier<kCT>(p.bar, bar_base + bar_count * (unsigned)G, ctid, p.err);
+    const float4* parts = p.partials + (int64_t)par * G * C4;
+    if (p.reduce_mode == 1 && p.nranks == 1) {
+      // ALLGATHER: every CTA sums all G partials itself (same order everywhere -> same bits)
+      int Q = 1;
+      while (Q < 32 && (int64_t)C4 * (Q * 2) <= kCT) Q <<= 1;
+      for (int base = 0; base < C4; base += kCT / Q) {
+        const int fi = base + ctid / Q;
+        const int q = ctid % Q;
+        const bool active = fi < C4;
+        const float4 tot = tree_sum_sources<false>(parts, C4, active ? fi : 0, G, q, Q, active);
+        if (active && q == 0) {
+          float4 gs;
+          const float4 wv = updated(fi, tot, &gs);
+          w_s[fi] = wv;
+          if (cta == 0) reinterpret_cast<float4*>(p.g_last)[fi] = gs;
+        }
+      }
+      consumer_bar<kCT>();
+    } else {
+      // SCATTER: CTA k owns the float4 columns [f0, f0+nf); it sums them over all partials,
+      // (multi-GPU: exchanges the slice sums with the same CTA of every peer over NVLink),
+      // applies the update and publishes the new weights; after a second grid barrier every
+      // CTA reloads them.
+      const int f0 = (int)slice_lo(C4, cta, G);
+      const int nf = (int)slice_lo(C4, cta + 1, G) - f0;
+      int Q = 1;
+      while (Q < 32 && (int64_t)(nf > 0 ? nf : 1) * (Q * 2) <= kCT) Q <<= 1;
+      for (int base = 0; base < nf; base += kCT / Q) {
+        const int fi = base + ctid / Q;
+        const int q = ctid % Q;
+        const bool active = fi < nf;
+        const int f = f0 + (active ? fi : 0);
+        const float4 tot = tree_sum_sources<false>(parts, C4, f, G, q, Q, active);
+        if (active && q == 0) {
+          if (p.nranks == 1) {
+            float4 gs;
+            const float4 wv = updated(f, tot, &gs);
+            st_cg_f4(p.w_stage + f, wv);
+            reinterpret_cast<float4*>(p.g_last)[f] = gs;
+          } else {
+            // fused gradient exchange, part 1: my slice sum into slot [par][rank] of EVERY
+            // rank's inbox -- plain stores to peer-mapped memory, i.e. NVLink writes
+            for (int pr = 0; pr < p.nranks; ++pr)
+              p.xchg_peer[pr][((int64_t)par * p.nranks + p.rank) * C4 + f] = tot;
+            __threadfence_system();
+          }
+        }
+      }
+      if (p.nranks > 1 && nf > 0) {
+        // part 2: publish one flag per destination rank (release at system scope, after the
+        // CTA barrier that orders every thread's slice stores before it), then wait until
+        // every rank's slice for this step has landed in my inbox.
+        consumer_bar<kCT>();
+        const uint32_t tag = p.epoch_tag + (uint32_t)s + 1u;
+        if (ctid < p.nranks) {
+          st_release_sys(p.flag_peer[ctid] + ((int64_t)par * p.nranks + p.rank) * G + cta, tag);
+          const unsigned int* fl = p.flag_local + ((int64_t)par * p.nranks + ctid) * G + cta;
+          SpinGuard guard;
+          while ((int)(ld_acquire_sys(fl) - tag) < 0) {
+            if (guard.expired(p.err, 2u)) break;
+          }
+        }
+        consumer_bar<kCT>();
+        // part 3: add the ranks' slices in rank order (identical bits on every GPU) and update
+        const float4* inbox = p.xchg_local + (int64_t)par * p.nranks * C4;
+        for (int fi = ctid; fi < nf; fi += kCT) {
+          const int f = f0 + fi;
+          float4 tot = ld_volatile_f4(inbox + f);
+          for (int pr = 1; pr < p.nranks; ++pr)
+            tot = f4_add(tot, ld_volatile_f4(inbox + (int64_t)pr * C4 + f));
+          float4 gs;
+          const float4 wv = updated(f, tot, &gs);
+          st_cg_f4(p.w_stage + f, wv);
+          reinterpret_cast<float4*>(p.g_last)[f] = gs;
+        }
+      }
+      bar_count += 1;
+      grid_barrier<kCT>(p.bar, bar_base + bar_count * (unsigned)G, ctid, p.err);
+      for (int f = ctid; f < C4; f += kCT) w_s[f] = ld_cg_f4(p.w_stage + f);
+      consumer_bar<kCT>();
+    }
+  }
+
+  // final weights back to global (every CTA holds the same bits; CTA 0 writes)
+  if (cta == 0) {
+    for (int c = ctid; c < p.C; c += kCT) p.w[c] = reinterpret_cast<float*>(w_s)[c];
+    if (p.ctl != nullptr && ctid == 0) {  // every CTA has read ctl before its first grid barrier
+      p.ctl->step = first_step + p.nb;
+      p.ctl->bar_base = bar_base + bar_count * (unsigned)G;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Mean absolute error over the data in ORIGINAL order (replaces calculate_mean_abs_error_cublas,
+// sgd_thrust.cu:79-135: Scopy + Sgemv + Sasum).  One streaming pass, warp per row, float4 loads.
+// Per-block partial sums in double; the host adds the few hundred block sums.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sgd_mae_kernel(const float* __restrict__ rec, int64_t ld,
+                                                      int32_t C, int64_t rows,
+                                                      const float* __restrict__ w,
+                                                      double* __restrict__ block_sums) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* w_s = reinterpret_cast<float*>(smem_raw);
+  const int C4 = (C + 3) >> 2;
+  for (int c = threadIdx.x; c < C4 * 4; c += blockDim.x) w_s[c] = (c < C) ? w[c] : 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const int64_t gwarp = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * warps_per_block;
+  const float4* w4 = reinterpret_cast<const float4*>(w_s);
+  double acc = 0.0;
+  for (int64_t row = gwarp; row < rows; row += nwarps) {
+    const float4* x4 = reinterpret_cast<const float4*>(rec + row * ld);
+    float dot = 0.f;
+    for (int f = lane; f < C4; f += 32) {
+      const float4 xv = __ldcs(x4 + f);
+      const float4 wv = w4[f];
+      dot = fmaf(xv.x, wv.x, dot);
+      dot = fmaf(xv.y, wv.y, dot);
+      dot = fmaf(xv.z, wv.z, dot);
+      dot = fmaf(xv.w, wv.w, dot);
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, m);
+    if (lane == 0) acc += (double)fabsf(dot - __ldcs(rec + row * ld + C));
+  }
+  __shared__ double red[32];
+  if (lane == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < warps_per_block; ++i) t += red[i];
+    block_sums[blockIdx.x] = t;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host rows (row-major X[R][C], y[R]) -> records.  Runs once per upload chunk.
+// ------------------------------------------------------------------------------------------------
+__global__ void sgd_pack_kernel(const float* __restrict__ X, const float* __restrict__ y,
+                                int64_t nrows, int32_t C, int64_t ld, float* __restrict__ rec) {
+  const int64_t total = nrows * ld;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / ld;
+    const int32_t c = (int32_t)(i - row * ld);
+    float v = 0.f;
+    if (c < C) v = X[row * C + c];
+    else if (c == C) v = y[row];
+    rec[i] = v;
+  }
+}
+
+__global__ void sgd_unpack_kernel(const float* __restrict__ rec, int64_t nrows, int32_t C,
+                                  int64_t ld, float* __restrict__ X, float* __restrict__ y) {
+  const int64_t total = nrows * (C + 1);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / (C + 1);
+    const int32_t c = (int32_t)(i - row * (C + 1));
+    const float v = rec[row * ld + c];
+    if (c < C) X[row * C + c] = v; else y[row] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Synthetic data in the distribution of data_set_creation/generate_data.py:22-39 (sklearn
+// make_regression, all features informative, bias 0, no noise): X ~ N(0,1), w_true ~ 100*U(0,1),
+// y = X w_true.  Counter-based (Philox4x32-10 keyed by the seed, counter = global row, column
+// group) so a row's values do not depend on which GPU generates it.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0;
+    key.y += W1;
+  }
+  return ctr;
+}
+__device__ __forceinline__ float u01(uint32_t v) { return ((float)(v >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+
+__device__ __forceinline__ float true_weight(uint64_t seed, int32_t c) {
+  const uint4 r = philox4x32_10(make_uint4((uint32_t)c, 0u, 0x77747275u, 0u),
+                                make_uint2((uint32_t)seed, (uint32_t)(seed >> 32) ^ 0x5eedu));
+  return 100.0f * u01(r.x);
+}
+
+__global__ void sgd_true_weights_kernel(uint64_t seed, int32_t C, float* __restrict__ wt) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) wt[c] = true_weight(seed, c);
+}
+
+__device__ __forceinline__ float round_through_fp16(float v) { return __half2float(__float2half_rn(v)); }
+
+// one warp per row
+__global__ void __launch_bounds__(256) sgd_synth_kernel(uint64_t seed, int64_t row_begin,
+                                                        int64_t nrows, int32_t C, int64_t ld,
+                                                        const float* __restrict__ wt, int round16,
+                                                        float* __restrict__ rec) {
+  const int lane = threadIdx.x & 31;
+  const int64_t gwarp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int C4 = (C + 3) >> 2;
+  const int ld4 = (int)(ld >> 2);
+  const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+  for (int64_t lr = gwarp; lr < nrows; lr += nwarps) {
+    const uint64_t grow = (uint64_t)(row_begin + lr);
+    float4* out = reinterpret_cast<float4*>(rec + lr * ld);
+    float dot = 0.f;
+    for (int f = lane; f < ld4; f += 32) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (f < C4) {
+        const uint4 r = philox4x32_10(make_uint4((uint32_t)grow, (uint32_t)(grow >> 32), (uint32_t)f, 0u), key);
+        // Box-Muller on two uniform pairs
+        const float r0 = sqrtf(-2.0f * __logf(u01(r.x)));
+        const float r1 = sqrtf(-2.0f * __logf(u01(r.z)));
+        float s0, c0, s1, c1;
+        __sincosf(6.28318530717958647692f * u01(r.y), &s0, &c0);
+        __sincosf(6.28318530717958647692f * u01(r.w), &s1, &c1);
+        v = make_float4(r0 * c0, r0 * s0, r1 * c1, r1 * s1);
+        const int c = f * 4;
+        if (c + 1 >= C) v.y = 0.f;
+        if (c + 2 >= C) v.z = 0.f;
+        if (c + 3 >= C) v.w = 0.f;
+        if (round16) {
+          v.x = round_through_fp16(v.x); v.y = round_through_fp16(v.y);
+          v.z = round_through_fp16(v.z); v.w = round_through_fp16(v.w);
+        }
+        dot = fmaf(v.x, wt[c], dot);
+        if (c + 1 < C) dot = fmaf(v.y, wt[c + 1], dot);
+        if (c + 2 < C) dot = fmaf(v.z, wt[c + 2], dot);
+        if (c + 3 < C) dot = fmaf(v.w, wt[c + 3], dot);
+      }
+      out[f] = v;
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, m);
+    if (lane == 0) rec[lr * ld + C] = round16 ? round_through_fp16(dot) : dot;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Data-parallel bucketing: from the GLOBAL permutation keep, per step, the rows this
+// rank owns (batch order preserved), as local row numbers + per-step offsets.
+// Pass 1 counts per step, the host does not take part: an exclusive scan kernel builds offsets,
+// pass 2 writes.  One CTA per step and a block-wide stable compaction keep the batch order.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sgd_bucket_count_kernel(const int32_t* __restrict__ perm,
+                                                               int64_t B, int32_t nb,
+                                                               int64_t row_begin, int64_t row_end,
+                                                               int64_t* __restrict__ counts) {
+  __shared__ int red[8];
+  for (int s = blockIdx.x; s < nb; s += gridDim.x) {
+    const int32_t* p = perm + (int64_t)s * B;
+    int c = 0;
+    for (int64_t i = threadIdx.x; i < B; i += blockDim.x) {
+      const int64_t r = p[i];
+      c += (r >= row_begin && r < row_end) ? 1 : 0;
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) c += __shfl_xor_sync(0xffffffffu, c, m);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int t = 0;
+      for (int i = 0; i < 8; ++i) t += red[i];
+      counts[s] = t;
+    }
+    __syncthreads();
+  }
+}
+
+// single-block exclusive scan of counts[0..nb) into offs[0..nb]
+__global__ void __launch_bounds__(1024) sgd_scan_kernel(const int64_t* __restrict__ counts,
+                                                        int32_t nb, int64_t* __restrict__ offs) {
+  __shared__ int64_t warp_tot[32];
+  __shared__ int64_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < nb; base += 1024) {
+    const int i = base + threadIdx.x;
+    int64_t v = (i < nb) ? counts[i] : 0;
+    int64_t incl = v;
+#pragma unroll
+    for (int m = 1; m < 32; m <<= 1) {
+      const int64_t t = __shfl_up_sync(0xffffffffu, incl, m);
+      if ((threadIdx.x & 31) >= m) incl += t;
+    }
+    if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    int64_t wbase = 0;
+    for (int wq = 0; wq < (int)(threadIdx.x >> 5); ++wq) wbase += warp_tot[wq];
+    const int64_t c0 = carry;
+    if (i < nb) offs[i] = c0 + wbase + incl - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = c0 + wbase + incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) offs[nb] = carry;
+}
+
+__global__ void __launch_bounds__(256) sgd_bucket_write_kernel(const int32_t* __restrict__ perm,
+                                                               int64_t B, int32_t nb,
+                                                               int64_t row_begin, int64_t row_end,
+                                                               const int64_t* __restrict__ offs,
+                                                               int32_t* __restrict__ local_perm) {
+  __shared__ int warp_cnt[8];
+  __shared__ int64_t running;
+  for (int s = blockIdx.x; s < nb; s += gridDim.x) {
+    const int32_t* p = perm + (int64_t)s * B;
+    if (threadIdx.x == 0) running = offs[s];
+    __syncthreads();
+    for (int64_t base = 0; base < B; base += blockDim.x) {
+      const int64_t i = base + threadIdx.x;
+      int64_t r = -1;
+      bool mine = false;
+      if (i < B) {
+        r = p[i];
+        mine = (r >= row_begin && r < row_end);
+      }
+      const unsigned ballot = __ballot_sync(0xffffffffu, mine);
+      const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
+      if (lane == 0) warp_cnt[wq] = __popc(ballot);
+      __syncthreads();
+      int before = 0;
+      for (int k = 0; k < wq; ++k) before += warp_cnt[k];
+      int total = 0;
+      for (int k = 0; k < 8; ++k) total += warp_cnt[k];
+      const int pos = before + __popc(ballot & ((1u << lane) - 1u));
+      const int64_t run = running;
+      if (mine) local_perm[run + pos] = (int32_t)(r - row_begin);
+      __syncthreads();
+      if (threadIdx.x == 0) running = run + total;
+      __syncthreads();
+    }
+  }
+}
+
+}  // namespace b200sgd

@@ -1,0 +1,257 @@
+"""Parity of the CUDA path (libb200sgd.so, through the C-ABI) with the CPU oracle.  Needs a B200.
+
+Bars (BASELINE.json north_star): permutation indices bit-exact; weights rel-L2 <= 1e-4 and MAE
+within 1e-4 relative of the oracle (fp32 arithmetic, different summation order)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import cuda_sgd_sese_project_b200 as pkg
+from cuda_sgd_sese_project_b200 import _lib
+from oracle import loader as orc
+from tests.helpers import make_regression, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+W_TOL = 1e-4     # relative L2 on the weights (north_star)
+MAE_TOL = 1e-4   # relative on the mean absolute error
+
+
+def oracle_epochs(X, y, B_arg, lr, epochs, seed=1):
+    """Oracle run that also returns the permutation of every epoch."""
+    R, C = X.shape
+    B, _ = orc.num_batches(R, B_arg)
+    g = orc.Rand(seed)
+    ind = np.arange(R, dtype=np.int32)
+    w = orc.init_weights(C)
+    perms = []
+    for e in range(1, epochs + 1):
+        g.shuffle(ind)
+        perms.append(ind.copy())
+        orc.epoch(X, y, B, ind, w, lr, e)
+    return w, perms, orc.mean_abs_error(X, y, w)
+
+
+def check_run(X, y, B_arg, lr, epochs, **kw):
+    R, C = X.shape
+    w_o, perms, mae_o = oracle_epochs(X, y, B_arg, lr, epochs)
+    with pkg.SGDEngine(R, C, B_arg, lr, data=X, labels=y, **kw) as eng:
+        for e in range(1, epochs + 1):
+            eng.iteration(e)                       # one cuda_iteration / cublas_iteration
+            assert np.array_equal(eng.permutation(), perms[e - 1]), f"permutation differs in epoch {e}"
+        w = eng.weights
+        mae = eng.calculate_mean_abs_error()
+    assert np.all(np.isfinite(w))
+    assert rel_l2(w, w_o) <= W_TOL, (rel_l2(w, w_o), kw)
+    # relative to the oracle's MAE, with a floor at fp32 resolution of the labels (a converged,
+    # noise-free fit has an MAE that is pure rounding noise)
+    assert abs(mae - mae_o) <= MAE_TOL * abs(mae_o) + 1e-6 * float(np.mean(np.abs(y))), (mae, mae_o)
+    return w, mae
+
+
+# ------------------------------------------------------------------ the reference's own fixtures
+def test_fixture_abs_error(fixtures):
+    # testing.cu:15-55 "Mean absolute error (8.0 expected)"
+    X, y = fixtures["gemv_test_X"], fixtures["gemv_test_y"]
+    with pkg.SGDEngine(5, 4, 0, 0.0, data=X, labels=y) as eng:
+        eng.weights = np.ones(4, np.float32)
+        assert eng.calculate_mean_abs_error() == 8.0
+
+
+def test_fixture_gemv_residuals_and_gradient(fixtures):
+    # testing.cu:225-275: loss derivative with w = 1 -> [0,4,8,12,16]; then the scaled column sums
+    X, y = fixtures["gemv_test_X"], fixtures["gemv_test_y"]
+    with pkg.SGDEngine(5, 4, 0, 0.0, data=X, labels=y, keep_residuals=True) as eng:
+        eng.weights = np.ones(4, np.float32)
+        eng.set_permutation(np.arange(5))
+        eng.epoch(1)
+        r = eng.residuals()
+        assert r.tolist() == [0.0, 4.0, 8.0, 12.0, 16.0]
+        g = eng.last_gradient()
+        assert np.allclose(g, orc.gradient(X, r, 5.0), rtol=1e-6)
+        assert np.array_equal(eng.weights, np.ones(4, np.float32))   # lr = 0: a = -0
+
+
+def test_fixture_permutation(fixtures):
+    # testing.cu:57-105 with the order vector of testing.cu:80-84: the gather follows `order`
+    X, y = fixtures["permutation_test_X"], fixtures["permutation_test_y"]
+    with pkg.SGDEngine(5, 4, 0, 0.0, data=X, labels=y, keep_residuals=True) as eng:
+        eng.weights = np.zeros(4, np.float32)
+        eng.set_permutation([4, 2, 0, 1, 3])
+        assert eng.permutation().tolist() == [4, 2, 0, 1, 3]
+        eng.epoch(1)
+        assert (-eng.residuals()).tolist() == [5.0, 3.0, 1.0, 2.0, 4.0]   # permuted labels
+        eng.weights = np.array([1, 0, 0, 0], np.float32)
+        eng.epoch(1)
+        assert eng.residuals().tolist() == [0.0] * 5                        # permuted rows match labels
+
+
+def test_fixture_col_sums_and_matrix_scale(fixtures):
+    # testing.cu:107-188 (column sums [5,10,15,20], scaled by 2 -> [2.5,5,7.5,10]) and :190-223
+    # (rows scaled by 2..6): g = X^T r / B with chosen r reproduces both expectations
+    X = fixtures["col_sum_test_X"]
+    # labels = -1 and w = 0 give r = +1 for every row -> g = column sums / B
+    with pkg.SGDEngine(5, 4, 0, 0.0, data=X, labels=-np.ones(5, np.float32)) as eng:
+        eng.weights = np.zeros(4, np.float32)
+        eng.set_permutation(np.arange(5))
+        eng.epoch(1)
+        assert (eng.last_gradient() * 5).tolist() == [5.0, 10.0, 15.0, 20.0]
+    Xs, v = fixtures["matrix_scale_test_X"], fixtures["matrix_scale_test_y"]
+    with pkg.SGDEngine(5, 4, 0, 0.0, data=Xs, labels=-v) as eng:   # r_i = v_i = 2..6
+        eng.weights = np.zeros(4, np.float32)
+        eng.set_permutation(np.arange(5))
+        eng.epoch(1)
+        assert (eng.last_gradient() * 5).tolist() == [20.0] * 4      # sum of the scaled rows
+
+
+@pytest.mark.parametrize("name,C,B,lr,epochs", [
+    ("xy5", 1, 0, 1e-5, 10),                 # main.cu:311 docstring example
+    ("correct_prediction", 3, 100, 0.1, 10),
+    ("correct_prediction", 3, 7, 0.05, 3),   # ragged tail (1000 = 142*7 + 6)
+    ("enb2012", 8, 64, 1e-6, 4),
+])
+def test_end_to_end_fixtures(fixtures, name, C, B, lr, epochs):
+    check_run(fixtures[name + "_X"], fixtures[name + "_y"], B, lr, epochs)
+
+
+# ------------------------------------------------------------------ BASELINE config 1
+def test_config_c1():
+    X, y, w_true = make_regression(10000, 100, seed=42, fp16_round=True)
+    w, mae = check_run(X, y, 1000, 0.1, 20)
+    assert rel_l2(w, w_true) < 5e-4
+
+
+def test_config_c1_run_pipeline_equals_iteration_loop():
+    X, y, _ = make_regression(10000, 100, seed=42, fp16_round=True)
+    w_o, perms, mae_o = oracle_epochs(X, y, 1000, 0.01, 10)
+    with pkg.SGDEngine(10000, 100, 1000, 0.01, data=X, labels=y) as eng:
+        t = eng.run(1, 10)                                   # overlapped shuffle pipeline
+        assert t["steps"] == 100 and t["samples"] == 100000 and t["launches"] == 10
+        assert np.array_equal(eng.permutation(), perms[-1])
+        assert rel_l2(eng.weights, w_o) <= W_TOL
+        assert abs(eng.calculate_mean_abs_error() - mae_o) <= MAE_TOL * mae_o
+
+
+# ------------------------------------------------------------------ shapes and edge cases
+@pytest.mark.parametrize("C", [1, 2, 3, 4, 5, 31, 32, 33, 100, 127, 128, 129, 255, 256, 300, 512, 513, 1000, 1024, 2048])
+def test_feature_counts(C):
+    R = 1500 if C <= 512 else 600
+    X, y, _ = make_regression(R, C, seed=C)
+    check_run(X, y, 250, 0.02, 2)
+
+
+@pytest.mark.parametrize("R,B", [(1, 0), (2, 1), (7, 7), (1000, 1), (1000, 3), (1000, 999), (1000, 1000),
+                                 (1000, 0), (4097, 64), (5000, 4096), (300, 301 - 1)])
+def test_batch_shapes(R, B):
+    X, y, _ = make_regression(R, 17, seed=R + B)
+    check_run(X, y, B, 0.01, 2)
+
+
+def test_batch_larger_than_rows_is_rejected():
+    X, y, _ = make_regression(10, 3)
+    with pytest.raises(pkg.SgdError) as ei:
+        pkg.SGDEngine(10, 3, 11, 0.1, data=X, labels=y)
+    assert ei.value.code == _lib.SGD_ERR_ARG
+
+
+@pytest.mark.parametrize("reduce", [_lib.SGD_REDUCE_ALLGATHER, _lib.SGD_REDUCE_SCATTER])
+@pytest.mark.parametrize("grid", [1, 2, 7, 37, 148])
+def test_reduction_modes_and_grids(reduce, grid):
+    X, y, _ = make_regression(6000, 100, seed=9)
+    check_run(X, y, 500, 0.05, 2, reduce=reduce, grid=grid)
+
+
+@pytest.mark.parametrize("C,B", [(100, 1000), (512, 256), (2048, 96)])
+def test_graph_engine(C, B):
+    X, y, _ = make_regression(3000, C, seed=C + 1)
+    w_p, _ = check_run(X, y, B, 0.02, 2, engine=_lib.SGD_ENGINE_PERSISTENT)
+    w_g, _ = check_run(X, y, B, 0.02, 2, engine=_lib.SGD_ENGINE_GRAPH)
+    assert np.array_equal(w_p, w_g)     # same kernel, same order of operations
+
+
+def test_graph_engine_many_steps_reuses_graph():
+    X, y, _ = make_regression(9000, 20, seed=4)
+    check_run(X, y, 10, 0.005, 2, engine=_lib.SGD_ENGINE_GRAPH)   # 900 steps > one graph chunk
+
+
+def test_results_are_bit_reproducible():
+    X, y, _ = make_regression(20000, 100, seed=11)
+    runs = []
+    for _ in range(2):
+        with pkg.SGDEngine(20000, 100, 1000, 0.1, data=X, labels=y) as eng:
+            eng.run(1, 3)
+            runs.append(eng.weights)
+    assert np.array_equal(runs[0], runs[1])
+
+
+def test_linearity_of_the_gradient():
+    # size-independent property: g(X, y1 + y2, w=0) = g(X, y1, 0) + g(X, y2, 0)
+    X, y1, _ = make_regression(4096, 64, seed=1)
+    _, y2, _ = make_regression(4096, 64, seed=2)
+    gs = []
+    for yy in (y1, y2, y1 + y2):
+        with pkg.SGDEngine(4096, 64, 0, 0.0, data=X, labels=yy) as eng:
+            eng.weights = np.zeros(64, np.float32)
+            eng.set_permutation(np.arange(4096))
+            eng.epoch(1)
+            gs.append(eng.last_gradient().astype(np.float64))
+    assert rel_l2(gs[0] + gs[1], gs[2]) < 1e-5
+
+
+# ------------------------------------------------------------------ synthetic generator
+def test_synthetic_generator_properties_and_parity():
+    R, C = 50000, 100
+    with pkg.SGDEngine(R, C, 1000, 0.1) as eng:
+        eng.load_synthetic(seed=42)
+        X, y = eng.get_rows(0, R)
+        wt = eng.true_weights()
+        assert abs(X.mean()) < 0.01 and abs(X.std() - 1.0) < 0.01
+        assert wt.min() >= 0 and wt.max() <= 100 and 30 < wt.mean() < 70
+        assert rel_l2(y, X.astype(np.float64) @ wt.astype(np.float64)) < 1e-5
+        w_o, perms, mae_o = oracle_epochs(X, y, 1000, 0.1, 3)
+        eng.run(1, 3)
+        assert np.array_equal(eng.permutation(), perms[-1])
+        assert rel_l2(eng.weights, w_o) <= W_TOL
+        assert abs(eng.calculate_mean_abs_error() - mae_o) <= MAE_TOL * mae_o + 1e-6 * float(np.mean(np.abs(y)))
+    # a shard of a 4-rank layout generates the same rows (values do not depend on the rank count)
+    with pkg.SGDEngine(R, C, 1000, 0.1, rank=2, nranks=4) as sh:
+        sh.load_synthetic(seed=42)
+        assert sh.local_row_begin == 25000 and sh.local_rows == 12500
+        Xs, ys = sh.get_rows(25000, 12500)
+        assert np.array_equal(Xs, X[25000:37500]) and np.array_equal(ys, y[25000:37500])
+
+
+def test_synthetic_fp16_rounding_matches_generate_data():
+    with pkg.SGDEngine(4000, 10, 100, 0.1) as eng:
+        eng.load_synthetic(seed=7, round_fp16=True)     # generate_data.py:37
+        X, y = eng.get_rows(0, 4000)
+        assert np.array_equal(X, X.astype(np.float16).astype(np.float32))
+        assert np.array_equal(y, y.astype(np.float16).astype(np.float32))
+
+
+# ------------------------------------------------------------------ BASELINE config 2 at full size
+@pytest.mark.slow
+def test_config_c2_full_size_properties(kat):
+    """4M x 100, B=1000 (BASELINE configs[1]): golden permutation checksum, convergence to the
+    generating weights, and full-size parity with the OpenMP oracle on the same device-generated data."""
+    R, C, B = 4000000, 100, 1000
+    with pkg.SGDEngine(R, C, B, 0.1) as eng:
+        eng.load_synthetic(seed=42)
+        t = eng.run(1, 2)
+        assert t["steps"] == 8000
+        perm = eng.permutation()
+        rec = [r for r in kat["shuffle_kat"] if r["R"] == R and r["epoch"] == 2][0]
+        i = np.arange(1, R + 1, dtype=np.uint64)
+        assert perm[:4].tolist() == rec["head"] and int(perm[-1]) == rec["last"]
+        assert int((i * perm.astype(np.uint64)).sum(dtype=np.uint64)) == rec["checksum"]
+        w = eng.weights
+        mae = eng.calculate_mean_abs_error()
+        assert rel_l2(w, eng.true_weights()) < 1e-3
+        X, y = eng.get_rows(0, R)
+    mae_o, w_o, ind_o = orc.run(X, y, B, 0.1, 2, threads=orc.max_threads())
+    assert np.array_equal(perm, ind_o)
+    assert rel_l2(w, w_o) <= W_TOL
+    # the fit has converged to fp32 resolution of the labels (|y| ~ 450): the MAE is rounding noise
+    assert abs(mae - mae_o) <= MAE_TOL * mae_o + 1e-6 * float(np.mean(np.abs(y)))

@@ -1,0 +1,127 @@
+"""Host-side logic of the product (libb200sgd.so through the Python mirror), checked against the
+third-party known answers, the oracle and golden byte strings.  CPU only."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import cuda_sgd_sese_project_b200 as pkg
+from oracle import loader as orc
+
+
+def _checksum(ind):
+    i = np.arange(1, ind.shape[0] + 1, dtype=np.uint64)
+    return int((i * ind.astype(np.uint64)).sum(dtype=np.uint64))
+
+
+@pytest.mark.parametrize("n", [1, 2, 5, 10, 33])
+def test_host_shuffle_small_exact(kat, n):
+    ind = np.arange(n, dtype=np.int32)
+    for e, rec in enumerate(kat["shuffle_full"][str(n)]):
+        pkg.host_shuffle(ind, seed=1, skip_epochs=e, epochs=1)  # permutation indices are bit-exact
+        assert ind.tolist() == rec["head"]
+
+
+@pytest.mark.parametrize("n", [1000, 10000, 4000000])
+def test_host_shuffle_kat(kat, n):
+    recs = [r for r in kat["shuffle_kat"] if r["R"] == n]
+    ind = np.arange(n, dtype=np.int32)
+    for e, rec in enumerate(recs):
+        pkg.host_shuffle(ind, seed=1, skip_epochs=e, epochs=1)
+        assert ind[:4].tolist() == rec["head"] and int(ind[-1]) == rec["last"]
+        assert _checksum(ind) == rec["checksum"]
+
+
+@pytest.mark.slow
+@pytest.mark.parametrize("n", [16777216])
+def test_host_shuffle_kat_large(kat, n):
+    recs = [r for r in kat["shuffle_kat"] if r["R"] == n]
+    ind = np.arange(n, dtype=np.int32)
+    pkg.host_shuffle(ind, seed=1, epochs=2)
+    assert ind[:4].tolist() == recs[1]["head"] and _checksum(ind) == recs[1]["checksum"]
+
+
+def test_host_shuffle_equals_oracle_for_other_seeds_and_sizes():
+    for seed, n in [(1, 1025), (7, 31), (12345, 2049), (99, 100003)]:
+        a = np.arange(n, dtype=np.int32)
+        pkg.host_shuffle(a, seed=seed, epochs=3)
+        g = orc.Rand(seed)
+        b = np.arange(n, dtype=np.int32)
+        for _ in range(3):
+            g.shuffle(b)
+        assert np.array_equal(a, b), (seed, n)
+
+
+def test_init_weights(kat):
+    want = np.array([int(h, 16) for h in kat["weights_hex"]], dtype=np.uint32)
+    for C in (1, 100, 2048):
+        assert np.array_equal(pkg.init_weights(C).view(np.uint32), want[:C])
+
+
+def test_batch_geometry_matches_oracle():
+    for R, B in [(40, 0), (10000, 1000), (10001, 1000), (999, 999), (4000000, 1000), (67108864, 65536), (16777217, 4096), (1000, 7)]:
+        assert pkg.batch_geometry(R, B) == orc.num_batches(R, B)
+
+
+def test_read_csv(tmp_path, fixtures):
+    p = tmp_path / "t.csv"
+    p.write_text("1,2,3,0.1\n4,5,6,0.2\n7,8,9,0.3")
+    ok, X, y = pkg.read_csv(str(p), 3, 3)
+    assert ok and np.array_equal(X, fixtures["example_X"]) and np.array_equal(y, fixtures["example_y"])
+    p.write_text("-0.53906,-6.0791e-1, .8374 ,-142.38\r\n1e3,+2,3.5,-0\n")
+    ok, X, y = pkg.read_csv(str(p), 2, 3)
+    rc, Xo, yo = orc.read_csv(str(p), 2, 3)
+    assert ok and rc == 0 and np.array_equal(X, Xo) and np.array_equal(y, yo)
+    ok, _, _ = pkg.read_csv(str(tmp_path / "missing.csv"), 2, 3)
+    assert not ok  # reference: read_csv returns false
+    p.write_text("1,2\n3,4\n5,6\n")
+    with pytest.raises(pkg.SgdError) as ei:
+        pkg.read_csv(str(p), 2, 1)
+    assert ei.value.code == pkg._lib.SGD_ERR_PARSE
+    p.write_text("1,2,3\n")
+    with pytest.raises(pkg.SgdError):
+        pkg.read_csv(str(p), 1, 1)   # more columns than announced
+    p.write_text("1,,3\n")
+    with pytest.raises(pkg.SgdError):
+        pkg.read_csv(str(p), 1, 2)   # std::stof("") throws in the reference
+
+
+def test_read_csv_large_parallel_equals_oracle(tmp_path):
+    rng = np.random.default_rng(0)
+    R, C = 60000, 12   # > 4 MB of text -> exercises the multi-threaded chunking
+    a = rng.standard_normal((R, C + 1)).astype(np.float32)
+    p = tmp_path / "big.csv"
+    with open(p, "w") as f:
+        for row in a:
+            f.write(",".join("%.9g" % v for v in row) + "\n")
+    assert os.path.getsize(p) > (4 << 20)
+    ok, X, y = pkg.read_csv(str(p), R, C)
+    rc, Xo, yo = orc.read_csv(str(p), R, C)
+    assert ok and rc == 0
+    assert np.array_equal(X, Xo) and np.array_equal(y, yo)
+    assert np.array_equal(X, a[:, :C]) and np.array_equal(y, a[:, C])
+
+
+def test_get_filename_from_path():
+    # sgd_io.cuh docstring example: "/path/to/file.csv" -> "file"
+    assert pkg.get_filename_from_path("/path/to/file.csv") == "file"
+    assert pkg.get_filename_from_path("data/5xy.csv") == "5xy"
+    assert pkg.get_filename_from_path("plain") == "plain"
+    assert pkg.get_filename_from_path("a/b.c/test_number_of_features-1000.csv") == "test_number_of_features-1000"
+
+
+def test_experiment_json_is_byte_compatible_with_jsoncpp(tmp_path):
+    # bytes of experiments/results/100b-1200b-cublas/test_number_of_samples_scalable-1000-cublas.json
+    golden = ('{\n   "error" : 0.016775146126747131,\n   "gpu_time" : 102.58531188964844,\n'
+              '   "shuffle_time" : 421.97488403320312,\n   "total_gradient_time" : 292.31671142578125,\n'
+              '   "transfer_time" : 795.40350341796875\n}\n')
+    vals = json.loads(golden)
+    p = tmp_path / "x-cublas.json"
+    pkg.write_experiment_output(str(p), np.float32(vals["shuffle_time"]), np.float32(vals["total_gradient_time"]),
+                                np.float32(vals["gpu_time"]), np.float32(vals["transfer_time"]), np.float32(vals["error"]))
+    assert p.read_text() == golden
+    assert sorted(json.loads(p.read_text())) == ["error", "gpu_time", "shuffle_time", "total_gradient_time", "transfer_time"]
+    pkg.write_experiment_output(str(p), 0.0, 8.0, float("nan"), float("inf"), -1.5)
+    assert p.read_text() == ('{\n   "error" : -1.5,\n   "gpu_time" : null,\n   "shuffle_time" : 0,\n'
+                             '   "total_gradient_time" : 8,\n   "transfer_time" : 1e+9999\n}\n')
