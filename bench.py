@@ -212,7 +212,7 @@ def main() -> int:
     ap.add_argument("--batch", type=int, default=0, help="override batch per GPU")
     ap.add_argument("--engine", default="persistent", choices=["persistent", "graph"])
     ap.add_argument("--grid", type=int, default=0)
-    ap.add_argument("--reduce", default="auto", choices=["auto", "allgather", "scatter"])
+    ap.add_argument("--reduce", default="auto", choices=["auto", "allgather", "scatter", "dataflow", "dataflow1"])
     ap.add_argument("--ref-rows", type=int, default=100_000)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
@@ -251,7 +251,7 @@ def main() -> int:
     K, W = args.steps, max(args.warmup, 3)
     eng = pkg.SGDEngine(R, cols, B, lr, device=local_rank, rank=rank, nranks=N,
                         engine=_lib.SGD_ENGINE_GRAPH if args.engine == "graph" else _lib.SGD_ENGINE_PERSISTENT,
-                        reduce={"auto": 0, "allgather": 1, "scatter": 2}[args.reduce], grid=args.grid)
+                        reduce={"auto": 0, "allgather": 1, "scatter": 2, "dataflow": 3, "dataflow1": 4}[args.reduce], grid=args.grid)
     eng.load_synthetic(seed=42)
     if N > 1:
         from cuda_sgd_sese_project_b200.dist import connect_peers
@@ -301,7 +301,7 @@ def main() -> int:
             t0 = time.perf_counter()
             e2 = pkg.SGDEngine(R, cols, B, lr, device=local_rank,
                                engine=_lib.SGD_ENGINE_GRAPH if args.engine == "graph" else _lib.SGD_ENGINE_PERSISTENT,
-                               reduce={"auto": 0, "allgather": 1, "scatter": 2}[args.reduce], grid=args.grid)
+                               reduce={"auto": 0, "allgather": 1, "scatter": 2, "dataflow": 3, "dataflow1": 4}[args.reduce], grid=args.grid)
             e2.load_rows_ptr(0, R, Xh.data_ptr(), yh.data_ptr())     # H2D from pinned memory
             te = e2.run(1, K)                                         # H2D of every permutation inside
             w_e2e = e2.weights                                        # D2H
@@ -340,7 +340,7 @@ def main() -> int:
                                    f"{rows_pg} rows per GPU), batch {B}, lr {lr}, {steps_epoch} steps per epoch; "
                                    "one bench step = one SGD epoch incl. its bit-exact permutation",
                        "l2": "inputs larger than L2 (per-GPU data %.1f GB vs 126 MB)" % (4 * rows_pg * (cols + 1) / 1e9),
-                       "engine": args.engine, "grid": eng.grid, "reduce": {1: "allgather", 2: "scatter"}[eng.reduce],
+                       "engine": args.engine, "grid": eng.grid, "reduce": {1: "allgather", 2: "scatter", 3: "dataflow-2hop", 4: "dataflow-1hop"}[eng.reduce],
                        "kernel": "sgd_epoch_kernel<KC=%d,U=%d,NW=%d>" % eng.kernel_shape,
                        "ring_slots": eng.nslots, "smem_bytes": eng.smem_bytes,
                        "parallelism": f"dp{N} row-sharded, fused NVLink gradient exchange" if N > 1 else "single GPU"},

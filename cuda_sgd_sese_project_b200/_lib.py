@@ -16,7 +16,7 @@ SGD_ERR_ARG, SGD_ERR_IO, SGD_ERR_PARSE, SGD_ERR_CUDA, SGD_ERR_STATE, SGD_ERR_NOM
     -1, -2, -3, -4, -5, -6, -7)
 SGD_PATH_CUBLAS, SGD_PATH_PLAIN_CUDA, SGD_PATH_LVL1 = 0, 1, 2
 SGD_ENGINE_AUTO, SGD_ENGINE_PERSISTENT, SGD_ENGINE_GRAPH = 0, 1, 2
-SGD_REDUCE_AUTO, SGD_REDUCE_ALLGATHER, SGD_REDUCE_SCATTER = 0, 1, 2
+SGD_REDUCE_AUTO, SGD_REDUCE_ALLGATHER, SGD_REDUCE_SCATTER, SGD_REDUCE_DATAFLOW, SGD_REDUCE_DATAFLOW_1HOP = 0, 1, 2, 3, 4
 SGD_FLAG_HOST_SHUFFLE, SGD_FLAG_RESIDUALS = 0x1, 0x2
 SGD_PEER_HANDLE_BYTES = 128
 
@@ -28,7 +28,8 @@ EXPORTS = [
     "sgd_load_synthetic", "sgd_get_rows", "sgd_get_true_weights", "sgd_get_weights",
     "sgd_set_weights", "sgd_get_config", "sgd_local_rows", "sgd_local_row_begin", "sgd_shuffle",
     "sgd_set_permutation", "sgd_get_permutation", "sgd_epoch", "sgd_iteration", "sgd_run",
-    "sgd_get_residuals", "sgd_get_last_gradient", "sgd_mean_abs_error", "sgd_peer_export",
+    "sgd_get_residuals", "sgd_get_last_gradient", "sgd_mean_abs_error", "sgd_debug_phase_cycles",
+    "sgd_peer_export",
     "sgd_peer_import", "sgd_peer_ready",
 ]
 
@@ -103,6 +104,7 @@ def load() -> C.CDLL:
         "sgd_get_residuals": ([vp, vp, i64], C.c_int),
         "sgd_get_last_gradient": ([vp, vp], C.c_int),
         "sgd_mean_abs_error": ([vp, C.POINTER(f32), C.POINTER(C.c_double)], C.c_int),
+        "sgd_debug_phase_cycles": ([vp, vp, i32], C.c_int),
         "sgd_peer_export": ([vp, vp], C.c_int),
         "sgd_peer_import": ([vp, i32, vp], C.c_int),
         "sgd_peer_ready": ([vp], C.c_int),

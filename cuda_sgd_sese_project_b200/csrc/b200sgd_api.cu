@@ -17,6 +17,7 @@
 #include <cmath>
 #include <cstddef>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -70,13 +71,30 @@ KernelChoice make_choice() {
   return k;
 }
 
-bool choose_kernel(int C4, KernelChoice* out) {
-  if (C4 <= 32) *out = make_choice<1, 4, 16>();
-  else if (C4 <= 64) *out = make_choice<2, 4, 16>();
-  else if (C4 <= 128) *out = make_choice<4, 2, 16>();
-  else if (C4 <= 256) *out = make_choice<8, 2, 8>();
-  else if (C4 <= 512) *out = make_choice<16, 1, 8>();
-  else return false;
+// Kernel variant by row width (KC) and by how many rows one CTA handles per step: few rows ->
+// fewer consumer warps and no row unrolling, so the latency-critical step tail is not slowed down
+// by warps that only execute control code (the tail is issue-bound).
+bool choose_kernel(int C4, int64_t rows_per_cta, KernelChoice* out) {
+  if (C4 <= 32) {
+    if (rows_per_cta <= 8) *out = make_choice<1, 1, 8>();
+    else if (rows_per_cta <= 16) *out = make_choice<1, 2, 8>();
+    else if (rows_per_cta <= 32) *out = make_choice<1, 2, 16>();
+    else *out = make_choice<1, 4, 16>();
+  } else if (C4 <= 64) {
+    if (rows_per_cta <= 8) *out = make_choice<2, 1, 8>();
+    else if (rows_per_cta <= 32) *out = make_choice<2, 2, 16>();
+    else *out = make_choice<2, 4, 16>();
+  } else if (C4 <= 128) {
+    if (rows_per_cta <= 8) *out = make_choice<4, 1, 8>();
+    else *out = make_choice<4, 2, 16>();
+  } else if (C4 <= 256) {
+    if (rows_per_cta <= 8) *out = make_choice<8, 1, 8>();
+    else *out = make_choice<8, 2, 8>();
+  } else if (C4 <= 512) {
+    *out = make_choice<16, 1, 8>();
+  } else {
+    return false;
+  }
   return true;
 }
 
@@ -105,11 +123,16 @@ struct sgd_ctx {
   int64_t* d_counts = nullptr;
   float4* d_partials = nullptr;
   float4* d_wstage = nullptr;
+  uint4* d_ll_part = nullptr;  // DATAFLOW reduction: tagged partials [grid][C4][2]
+  uint4* d_ll_w = nullptr;     //                     tagged new weights [w_copies][C4][2]
+  int w_copies = 1;
+  uint32_t step_tag = 0;       // tags handed out so far (persistent engine)
   float* d_glast = nullptr;
   float* d_rout = nullptr;
   int64_t rout_len = 0;
   unsigned int* d_bar = nullptr;  // [0] barrier counter, [1] watchdog error word
   b200sgd::StepCtl* d_ctl = nullptr;
+  unsigned long long* d_dbg = nullptr;  // phase profile, only with B200SGD_PHASE_PROFILE=1
   double* d_mae = nullptr;
   int mae_blocks = 0;
 
@@ -129,12 +152,11 @@ struct sgd_ctx {
   int graph_nodes = 0;
 
   // multi-GPU
-  void* d_xchg_block = nullptr;  // [xchg float4 2*nranks*C4][flags 2*nranks*grid]
-  size_t xchg_bytes = 0, flag_off = 0;
+  void* d_xchg_block = nullptr;  // inbox of tagged slice sums [2][nranks][C4][2] uint4
+  size_t xchg_bytes = 0;
   void* peer_block[8] = {nullptr};
   bool peer_open[8] = {false};
   bool peers_ready = false;
-  uint32_t epoch_tag = 0;
 };
 
 namespace {
@@ -166,6 +188,7 @@ void free_all(sgd_ctx* c) {
   cudaFree(c->d_perm[0]); cudaFree(c->d_perm[1]); cudaFree(c->d_perm_local);
   cudaFree(c->d_step_off); cudaFree(c->d_counts); cudaFree(c->d_partials); cudaFree(c->d_wstage);
   cudaFree(c->d_glast); cudaFree(c->d_rout); cudaFree(c->d_bar); cudaFree(c->d_ctl);
+  cudaFree(c->d_ll_part); cudaFree(c->d_ll_w); cudaFree(c->d_dbg);
   cudaFree(c->d_mae); cudaFree(c->d_xchg_block);
   if (c->h_stage[0]) cudaFreeHost(c->h_stage[0]);
   if (c->h_stage[1]) cudaFreeHost(c->h_stage[1]);
@@ -178,8 +201,18 @@ void free_all(sgd_ctx* c) {
 
 // Decide grid size, reduction mode and ring depth for this shape (DESIGN.md "launch geometry").
 int configure_launch(sgd_ctx* c) {
-  if (!choose_kernel(c->C4, &c->kc))
-    return fail(SGD_ERR_ARG, "cols > 2048 is not supported by this build of the step kernel");
+  if (c->C4 > 512) return fail(SGD_ERR_ARG, "cols > 2048 is not supported by this build of the step kernel");
+  // rows this rank sees per step
+  const int64_t rows_step = std::max<int64_t>(1, (int64_t)c->B / std::max(1, c->cfg.nranks));
+  int grid = c->cfg.grid;
+  if (grid <= 0) {
+    // one CTA per SM once every CTA gets a few rows per step; fewer CTAs for tiny batches keep
+    // the partial-gradient gather cheap
+    grid = (int)std::min<int64_t>(c->num_sms, std::max<int64_t>(1, rows_step / 2));
+  }
+  grid = std::max(1, std::min(grid, c->num_sms));
+  if (!choose_kernel(c->C4, (rows_step + grid - 1) / grid, &c->kc))
+    return fail(SGD_ERR_ARG, "unsupported row width");
   const size_t slot_bytes = (size_t)c->ld * 4;
   if (c->kc.fixed_smem + 2 * slot_bytes > kMaxDynSmem)
     return fail(SGD_ERR_ARG, "row too wide for the shared-memory ring");
@@ -196,20 +229,10 @@ int configure_launch(sgd_ctx* c) {
   int occ = 0;
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, c->kc.fn, 32 * (c->kc.NW + 1), c->smem_bytes));
   if (occ < 1) return fail(SGD_ERR_CUDA, "step kernel does not fit on an SM");
-  // rows this rank sees per step
-  const int64_t rows_step = std::max<int64_t>(1, (int64_t)c->B / std::max(1, c->cfg.nranks));
-  int grid = c->cfg.grid;
-  if (grid <= 0) {
-    // one CTA per SM once every CTA gets a few rows per step; fewer CTAs for tiny batches keep
-    // the grid barrier and the partial-gradient reduction cheap
-    grid = (int)std::min<int64_t>(c->num_sms, std::max<int64_t>(1, rows_step / 2));
-  }
-  grid = std::max(1, std::min(grid, c->num_sms * occ));
   c->grid = grid;
   int mode = c->cfg.reduce;
-  if (c->cfg.nranks > 1) mode = SGD_REDUCE_SCATTER;
-  if (mode != SGD_REDUCE_ALLGATHER && mode != SGD_REDUCE_SCATTER)
-    mode = ((int64_t)grid * c->C4 <= 1024) ? SGD_REDUCE_ALLGATHER : SGD_REDUCE_SCATTER;
+  if (c->cfg.nranks > 1) mode = SGD_REDUCE_DATAFLOW;  // the fused NVLink exchange lives there
+  if (mode < SGD_REDUCE_ALLGATHER || mode > SGD_REDUCE_DATAFLOW_1HOP) mode = SGD_REDUCE_DATAFLOW;
   c->reduce_mode = mode;
   c->engine = (c->cfg.engine == SGD_ENGINE_GRAPH) ? SGD_ENGINE_GRAPH : SGD_ENGINE_PERSISTENT;
   if (c->engine == SGD_ENGINE_GRAPH && c->cfg.nranks > 1)
@@ -241,9 +264,14 @@ void fill_params(sgd_ctx* c, b200sgd::EpochParams* p, int32_t epoch, int buf) {
   p->nslots = c->nslots;
   p->slot_log2 = c->slot_log2;
   p->slot_bytes = (uint32_t)(c->ld * 4);
+  p->ll_part = c->d_ll_part;
+  p->ll_w = c->d_ll_w;
+  p->w_copies = c->w_copies;
+  p->tag_base = c->step_tag;
   p->rank = c->cfg.rank;
   p->nranks = c->cfg.nranks;
   p->ctl = nullptr;
+  p->dbg = c->d_dbg;
 }
 
 int upload_perm(sgd_ctx* c, int buf) {
@@ -304,14 +332,8 @@ int launch_epoch(sgd_ctx* c, int32_t epoch, int buf, int* launches) {
   fill_params(c, &p, epoch, buf);
   if (c->cfg.nranks > 1) {
     if (!c->peers_ready) return fail(SGD_ERR_STATE, "nranks > 1 but sgd_peer_ready was not called");
-    p.xchg_local = (float4*)c->d_xchg_block;
-    p.flag_local = (unsigned int*)((char*)c->d_xchg_block + c->flag_off);
-    for (int r = 0; r < c->cfg.nranks; ++r) {
-      p.xchg_peer[r] = (float4*)c->peer_block[r];
-      p.flag_peer[r] = (unsigned int*)((char*)c->peer_block[r] + c->flag_off);
-    }
-    p.epoch_tag = c->epoch_tag;
-    c->epoch_tag += (uint32_t)c->nb;
+    p.ll_inbox_local = (uint4*)c->d_xchg_block;
+    for (int r = 0; r < c->cfg.nranks; ++r) p.ll_inbox_peer[r] = (uint4*)c->peer_block[r];
   }
   if (c->engine == SGD_ENGINE_GRAPH) {
     SGD_TRY(build_graph(c));
@@ -328,6 +350,7 @@ int launch_epoch(sgd_ctx* c, int32_t epoch, int buf, int* launches) {
     return SGD_OK;
   }
   CUDA_TRY(cudaMemsetAsync(c->d_bar, 0, sizeof(unsigned int), c->stream));
+  c->step_tag += (uint32_t)c->nb;  // every rank advances identically: tags agree across GPUs
   void* args[] = {&p};
   CUDA_TRY(cudaLaunchCooperativeKernel(c->kc.fn, dim3(c->grid), dim3(32 * (c->kc.NW + 1)), args,
                                        c->smem_bytes, c->stream));
@@ -340,8 +363,8 @@ int check_watchdog(sgd_ctx* c) {
   CUDA_TRY(cudaMemcpy(&err, c->d_bar + 1, sizeof(err), cudaMemcpyDeviceToHost));
   if (err != 0) {
     cudaMemset(c->d_bar + 1, 0, sizeof(unsigned int));
-    return fail(err == 2 ? SGD_ERR_COMM : SGD_ERR_CUDA,
-                err == 2 ? "peer gradient exchange timed out (a rank did not arrive)"
+    return fail(c->cfg.nranks > 1 ? SGD_ERR_COMM : SGD_ERR_CUDA,
+                err == 3 ? "dataflow reduction timed out (a CTA or a peer rank did not publish)"
                          : "grid barrier timed out (CTAs not co-resident?)");
   }
   return SGD_OK;
@@ -472,7 +495,7 @@ int sgd_create(const sgd_config* cfg, const float* X, const float* y, sgd_ctx** 
   c->R = cfg->rows;
   c->C = cfg->cols;
   batch_geometry(c->R, cfg->batch, &c->B, &c->nb);
-  c->ld = ((int64_t)c->C + 1 + 7) / 8 * 8;
+  c->ld = ((int64_t)c->C + 1 + 15) / 16 * 16;  // 64-byte records: whole HBM bursts, see DESIGN.md
   c->C4 = (c->C + 3) / 4;
   c->rows_per_rank = (c->R + cfg->nranks - 1) / cfg->nranks;
   c->row_begin = std::min<int64_t>(c->R, c->rows_per_rank * cfg->rank);
@@ -519,10 +542,21 @@ int sgd_create(const sgd_config* cfg, const float* X, const float* y, sgd_ctx** 
     CUDA_TRY(cudaMalloc(&c->d_partials, sizeof(float4) * 2 * (size_t)c->grid * c->C4));
     CUDA_TRY(cudaMemset(c->d_partials, 0, sizeof(float4) * 2 * (size_t)c->grid * c->C4));
     CUDA_TRY(cudaMalloc(&c->d_wstage, sizeof(float4) * c->C4));
+    CUDA_TRY(cudaMalloc(&c->d_ll_part, sizeof(uint4) * 2 * 2 * (size_t)c->grid * c->C4));
+    CUDA_TRY(cudaMemset(c->d_ll_part, 0, sizeof(uint4) * 2 * 2 * (size_t)c->grid * c->C4));
+    // private weight mailboxes per CTA while they stay small (latency-bound shapes); one shared
+    // copy for wide rows, where steps are long and the extra L2 traffic would not pay
+    c->w_copies = ((size_t)c->grid * c->C4 * 32 <= (512u << 10)) ? c->grid : 1;
+    CUDA_TRY(cudaMalloc(&c->d_ll_w, sizeof(uint4) * 2 * (size_t)c->w_copies * c->C4));
+    CUDA_TRY(cudaMemset(c->d_ll_w, 0, sizeof(uint4) * 2 * (size_t)c->w_copies * c->C4));
     CUDA_TRY(cudaMalloc(&c->d_glast, sizeof(float4) * c->C4));
     CUDA_TRY(cudaMemset(c->d_glast, 0, sizeof(float4) * c->C4));
     CUDA_TRY(cudaMalloc(&c->d_bar, sizeof(unsigned int) * 2));
     CUDA_TRY(cudaMemset(c->d_bar, 0, sizeof(unsigned int) * 2));
+    if (const char* e = std::getenv("B200SGD_PHASE_PROFILE"); e && e[0] == '1') {
+      CUDA_TRY(cudaMalloc(&c->d_dbg, sizeof(unsigned long long) * 8 * (size_t)c->grid));
+      CUDA_TRY(cudaMemset(c->d_dbg, 0, sizeof(unsigned long long) * 8 * (size_t)c->grid));
+    }
     CUDA_TRY(cudaMalloc(&c->d_ctl, sizeof(b200sgd::StepCtl)));
     CUDA_TRY(cudaMemset(c->d_ctl, 0, sizeof(b200sgd::StepCtl)));
     if (c->cfg.flags & SGD_FLAG_RESIDUALS) {
@@ -533,9 +567,7 @@ int sgd_create(const sgd_config* cfg, const float* X, const float* y, sgd_ctx** 
     c->mae_blocks = c->num_sms * 8;
     CUDA_TRY(cudaMalloc(&c->d_mae, sizeof(double) * c->mae_blocks));
     if (c->cfg.nranks > 1) {
-      const size_t xb = sizeof(float4) * 2 * (size_t)c->cfg.nranks * c->C4;
-      c->flag_off = (xb + 255) / 256 * 256;
-      c->xchg_bytes = c->flag_off + sizeof(unsigned int) * 2 * (size_t)c->cfg.nranks * c->grid;
+      c->xchg_bytes = sizeof(uint4) * 2 * 2 * (size_t)c->cfg.nranks * c->C4;
       CUDA_TRY(cudaMalloc(&c->d_xchg_block, c->xchg_bytes));
       CUDA_TRY(cudaMemset(c->d_xchg_block, 0, c->xchg_bytes));
       c->peer_block[c->cfg.rank] = c->d_xchg_block;
@@ -886,6 +918,17 @@ int sgd_mean_abs_error(sgd_ctx* c, float* mae_out, double* sum_out) {
   // sgd_thrust.cu:134: return error_sum / R
   if (mae_out) *mae_out = (float)(total / (double)(c->cfg.nranks > 1 ? std::max<int64_t>(1, c->local_rows) : c->R));
   return SGD_OK;
+}
+
+int sgd_debug_phase_cycles(sgd_ctx* c, uint64_t* out, int32_t max_ctas) {
+  SGD_TRY(check_ctx(c));
+  if (!out || max_ctas < 0) return fail(SGD_ERR_ARG, "bad output");
+  if (!c->d_dbg) return fail(SGD_ERR_STATE, "set B200SGD_PHASE_PROFILE=1 before sgd_create");
+  SGD_TRY(bind(c));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  const int n = std::min<int>(max_ctas, c->grid);
+  CUDA_TRY(cudaMemcpy(out, c->d_dbg, sizeof(uint64_t) * 8 * (size_t)n, cudaMemcpyDeviceToHost));
+  return n;
 }
 
 // ---- peers --------------------------------------------------------------------------------------

@@ -20,7 +20,7 @@
 //                   and reruns are bit-identical.
 //
 // Record layout in HBM: row i = [x_0 .. x_{C-1}, y_i, 0-pad] with a leading dimension of
-// ld = roundup(C+1, 8) floats, so a row is one 32-byte-sector-aligned block that carries its label.
+// ld = roundup(C+1, 16) floats, so a row is a whole number of 64-byte HBM bursts and carries its label.
 #pragma once
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -39,11 +39,12 @@ struct StepCtl {
   int32_t step;         // next step to execute
   int32_t nb_total;     // steps per epoch; launches beyond it exit at once
   uint32_t bar_base;    // value of the grid-barrier counter when the next launch starts
+  uint32_t tag_base;    // dataflow tags handed out so far (see ll_store_f4)
 };
 
 struct EpochParams {
   const float* rec;         // records, ld floats each
-  int64_t ld;               // floats per record (multiple of 8)
+  int64_t ld;               // floats per record (multiple of 16)
   int32_t C;                // features
   int32_t C4;               // float4 groups covering the features: ceil(C/4)
   const int32_t* perm;      // LOCAL row numbers of this rank's rows, grouped by step
@@ -63,14 +64,17 @@ struct EpochParams {
   int32_t nslots;           // ring slots (power of two)
   int32_t slot_log2;
   uint32_t slot_bytes;      // ld * 4
+  // DATAFLOW reduction (reduce_mode 3): tagged 8-byte words instead of barriers, see ll_store_f4
+  uint4* ll_part;           // [grid][C4][2]  per-CTA partial gradients
+  uint4* ll_w;              // [w_copies][C4][2] new weights, published by the column owners
+  int32_t w_copies;         // grid: one private mailbox per CTA (no polling hot spot); 1: shared
+  uint32_t tag_base;        // tags used so far; step s of this launch uses tag_base + s + 1
   // multi-GPU exchange (nranks > 1): see sgd_peer_* in b200sgd.h
   int32_t rank, nranks;
-  float4* xchg_local;       // [2][nranks][C4] inbox of this rank (peers write into it)
-  float4* xchg_peer[8];     // same buffer of every rank, mapped into this process
-  unsigned int* flag_local; // [2][nranks][grid-slices] arrival flags of this rank's inbox
-  unsigned int* flag_peer[8];
-  uint32_t epoch_tag;       // value flags must reach: monotone across launches
+  uint4* ll_inbox_local;    // [2][nranks][C4][2] slice sums of every rank, written by the peers
+  uint4* ll_inbox_peer[8];  // the same buffer of every rank, mapped into this process (NVLink)
   StepCtl* ctl;             // GRAPH engine only (nullptr for the persistent engine)
+  unsigned long long* dbg;  // optional [grid][8] per-phase cycle sums (sgd_debug_phase_cycles)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -102,6 +106,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
+  }
+}
+// Same, for the producer: lets the hardware park the thread for up to ~hint ns per try instead of
+// re-issuing the probe back to back (the producer shares an SM sub-partition with consumer warps).
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(2000u)
+        : "memory");
   }
 }
 // one row: global -> shared through the TMA unit, completion counted in bytes on `bar`
@@ -147,6 +165,31 @@ __device__ __forceinline__ float4 ld_volatile_f4(const float4* p) {
                : "memory");
   return v;
 }
+// "LL" words: every float travels in an 8-byte word {value, tag}.  An aligned 8-byte store is
+// delivered whole, so a reader that sees the expected tag also sees the value -- no fence, no
+// flag, no barrier between producer and consumer (the idea of NCCL's LL protocol).  A float4 is two
+// 16-byte stores {x,tag,y,tag} {z,tag,w,tag}; works the same to local HBM and to a peer over NVLink.
+__device__ __forceinline__ void ll_store_f4(uint4* dst, float4 v, uint32_t tag) {
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "r"(__float_as_uint(v.x)),
+               "r"(tag), "r"(__float_as_uint(v.y)), "r"(tag)
+               : "memory");
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(dst + 1), "r"(__float_as_uint(v.z)),
+               "r"(tag), "r"(__float_as_uint(v.w)), "r"(tag)
+               : "memory");
+}
+__device__ __forceinline__ uint4 ld_volatile_u4(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ bool ll_unpack(uint4 a, uint4 b, uint32_t tag, float4* out) {
+  *out = make_float4(__uint_as_float(a.x), __uint_as_float(a.z), __uint_as_float(b.x), __uint_as_float(b.z));
+  return a.y == tag && a.w == tag && b.y == tag && b.w == tag;
+}
+
 __device__ __forceinline__ float4 f4_add(float4 a, float4 b) {
   return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
 }
@@ -182,6 +225,76 @@ struct SpinGuard {
     return false;
   }
 };
+// Blocks until the float4 at `src` carries `tag`.
+__device__ __forceinline__ float4 ll_wait_f4(const uint4* src, uint32_t tag, unsigned int* err) {
+  float4 v;
+  SpinGuard guard;
+  while (!ll_unpack(ld_volatile_u4(src), ld_volatile_u4(src + 1), tag, &v)) {
+    if (guard.expired(err, 3u)) break;
+  }
+  return v;
+}
+
+// Dataflow twin of tree_sum_sources: sums the tagged float4 `f` of sources 0..nsrc-1 (source i at
+// base + (i*stride + f)*2); each load is retried until its tag shows up.  Q threads (a power of
+// two, possibly several warps) share one column group: thread q adds sources q, q+Q, ... in order,
+// a xor-butterfly combines the lanes of a warp and, for Q > 32, the warps' sums go through
+// `xred` and are added in warp order.  The order is fixed, so every CTA (and every rerun) gets the
+// same bits.  Returns the total in EVERY thread of the group.  Must be called by all consumer
+// threads of the CTA with the same Q.
+template <int kThreads>
+__device__ __forceinline__ float4 ll_gather(const uint4* base, int64_t stride, int f, int nsrc, int q, int Q,
+                                            bool active, uint32_t tag, unsigned int* err, float4* xred,
+                                            int ctid) {
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (active) {
+    int i = q;
+    for (; i + 3 * Q < nsrc; i += 4 * Q) {  // 8 loads in flight, then consume in order
+      const uint4* s0 = base + ((int64_t)i * stride + f) * 2;
+      const uint4* s1 = base + ((int64_t)(i + Q) * stride + f) * 2;
+      const uint4* s2 = base + ((int64_t)(i + 2 * Q) * stride + f) * 2;
+      const uint4* s3 = base + ((int64_t)(i + 3 * Q) * stride + f) * 2;
+      const uint4 a0 = ld_volatile_u4(s0), b0 = ld_volatile_u4(s0 + 1);
+      const uint4 a1 = ld_volatile_u4(s1), b1 = ld_volatile_u4(s1 + 1);
+      const uint4 a2 = ld_volatile_u4(s2), b2 = ld_volatile_u4(s2 + 1);
+      const uint4 a3 = ld_volatile_u4(s3), b3 = ld_volatile_u4(s3 + 1);
+      float4 v0, v1, v2, v3;
+      if (!ll_unpack(a0, b0, tag, &v0)) v0 = ll_wait_f4(s0, tag, err);
+      if (!ll_unpack(a1, b1, tag, &v1)) v1 = ll_wait_f4(s1, tag, err);
+      if (!ll_unpack(a2, b2, tag, &v2)) v2 = ll_wait_f4(s2, tag, err);
+      if (!ll_unpack(a3, b3, tag, &v3)) v3 = ll_wait_f4(s3, tag, err);
+      acc = f4_add(acc, v0);
+      acc = f4_add(acc, v1);
+      acc = f4_add(acc, v2);
+      acc = f4_add(acc, v3);
+    }
+    if (i + Q < nsrc) {  // two sources left: both loads in flight
+      const uint4* s0 = base + ((int64_t)i * stride + f) * 2;
+      const uint4* s1 = base + ((int64_t)(i + Q) * stride + f) * 2;
+      const uint4 a0 = ld_volatile_u4(s0), b0 = ld_volatile_u4(s0 + 1);
+      const uint4 a1 = ld_volatile_u4(s1), b1 = ld_volatile_u4(s1 + 1);
+      float4 v0, v1;
+      if (!ll_unpack(a0, b0, tag, &v0)) v0 = ll_wait_f4(s0, tag, err);
+      if (!ll_unpack(a1, b1, tag, &v1)) v1 = ll_wait_f4(s1, tag, err);
+      acc = f4_add(acc, v0);
+      acc = f4_add(acc, v1);
+      i += 2 * Q;
+    }
+    for (; i < nsrc; i += Q) acc = f4_add(acc, ll_wait_f4(base + ((int64_t)i * stride + f) * 2, tag, err));
+  }
+  const int ql = Q < 32 ? Q : 32;
+  for (int m = 1; m < ql; m <<= 1) acc = f4_add(acc, f4_shfl_xor(acc, m));
+  if (Q > 32) {  // uniform over the CTA
+    if ((ctid & 31) == 0) xred[ctid >> 5] = acc;
+    consumer_bar<kThreads>();
+    const int w0 = (ctid / Q) * (Q >> 5);
+    acc = xred[w0];
+    for (int k = 1; k < (Q >> 5); ++k) acc = f4_add(acc, xred[w0 + k]);
+    consumer_bar<kThreads>();
+  }
+  return acc;
+}
+
 template <int kThreads>
 __device__ __forceinline__ void grid_barrier(unsigned int* ctr, unsigned int target, int ctid,
                                              unsigned int* err) {
@@ -264,6 +377,7 @@ __global__ void __launch_bounds__(32 * (NW + 1), 1) sgd_epoch_kernel(const Epoch
   float4* w_s = reinterpret_cast<float4*>(smem_raw + EpochSmem<KC, NW>::kBarBytes);
   float4* gred = w_s + 32 * KC;
   unsigned char* ring = smem_raw + EpochSmem<KC, NW>::kFixed;
+  __shared__ float4 xred[NW];  // cross-warp scratch of ll_gather
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -281,12 +395,14 @@ __global__ void __launch_bounds__(32 * (NW + 1), 1) sgd_epoch_kernel(const Epoch
   float a_step = p.a;
   const int32_t* perm = p.perm;
   unsigned int bar_base = 0;
+  uint32_t tag_base = p.tag_base;
   if (p.ctl != nullptr) {
     first_step = p.ctl->step;
     if (first_step >= p.ctl->nb_total) return;  // surplus node of the last graph replay
     a_step = p.ctl->a;
     perm = p.ctl->perm;
     bar_base = p.ctl->bar_base;
+    tag_base = p.ctl->tag_base;
   }
 
   if (tid == 0) {
@@ -310,8 +426,10 @@ __global__ void __launch_bounds__(32 * (NW + 1), 1) sgd_epoch_kernel(const Epoch
     return p.step_off ? (p.step_off[sa + 1] - p.step_off[sa]) : p.B;
   };
 
-  if (warp == NW) {
+  if (warp == 0) {
     // ===================================== PRODUCER =====================================
+    // (hardware warp 0: lowest issue priority and a different SM sub-partition than consumer
+    // warp 0, which carries the serial part of the step tail)
     // Row sequence of this CTA: for every step its contiguous slice of the batch, numbered
     // q = 0,1,2,... across steps; row q lives in slot q % nslots.  One round = up to 32 rows,
     // one per lane; the indices of round k+1 are loaded before round k is issued.
@@ -358,7 +476,7 @@ __global__ void __launch_bounds__(32 * (NW + 1), 1) sgd_epoch_kernel(const Epoch
         const uint64_t q = cur_q0 + (uint64_t)lane;
         const uint32_t slot = (uint32_t)q & slot_mask;
         const uint32_t use = (uint32_t)(q >> p.slot_log2);
-        mbar_wait(empty0 + 8u * slot, (use & 1u) ^ 1u);  // passes at once on the first use
+        mbar_wait_relaxed(empty0 + 8u * slot, (use & 1u) ^ 1u);  // passes at once on the first use
         const uint32_t fb = full0 + 8u * slot;
         mbar_arrive_expect_tx(fb, p.slot_bytes);
         bulk_g2s(ring0 + slot * p.slot_bytes, p.rec + (int64_t)cur_idx * p.ld, p.slot_bytes, fb);
@@ -369,7 +487,8 @@ __global__ void __launch_bounds__(32 * (NW + 1), 1) sgd_epoch_kernel(const Epoch
   }
 
   // ======================================= CONSUMERS =======================================
-  const int ctid = tid;  // consumer warps are warps 0..NW-1
+  const int ctid = tid - 32;  // consumer threads: hardware warps 1..NW
+  const int cw = warp - 1;    // consumer warp index 0..NW-1
   const float Bf = (float)p.B;
   const float a = a_step;
   const int C4 = p.C4;
@@ -378,8 +497,7 @@ __global__ void __launch_bounds__(32 * (NW + 1), 1) sgd_epoch_kernel(const Epoch
   float4 g[KC];
 
   // w = a * (g / B) + w for one float4 column group (sgd_thrust.cu:269, main.cu:147-150 / :287-290)
-  auto updated = [&](int f, float4 tot, float4* g_scaled) -> float4 {
-    float4 wv = w_s[f];
+  auto updated = [&](int f, float4 wv, float4 tot, float4* g_scaled) -> float4 {
     const float4 gs = make_float4(tot.x / Bf, tot.y / Bf, tot.z / Bf, tot.w / Bf);
     wv.x = fmaf(a, gs.x, wv.x);
     wv.y = fmaf(a, gs.y, wv.y);
@@ -394,16 +512,59 @@ __global__ void __launch_bounds__(32 * (NW + 1), 1) sgd_epoch_kernel(const Epoch
     return wv;
   };
 
+  // geometry of the step tail, invariant over the launch.  CTA k owns the float4 columns
+  // [f0, f0+nf) in the SCATTER and 2-hop DATAFLOW reductions; the 1-hop DATAFLOW and ALLGATHER
+  // reductions treat every column in every CTA.  Q threads (power of two) share one column.
+  const int f0 = (int)slice_lo(C4, cta, G);
+  const int nf = (int)slice_lo(C4, cta + 1, G) - f0;
+  const bool all_cols = (p.reduce_mode == 4 || p.reduce_mode == 1);
+  const int ncol = all_cols ? C4 : nf;
+  const int col0 = all_cols ? 0 : f0;
+  int gcap = 1;  // no point in more threads per column than there are sources
+  while (gcap < G) gcap <<= 1;
+  int Q = 1;
+  {
+    const int qmax = (p.reduce_mode >= 3) ? kCT : 32;  // the barrier modes reduce inside a warp
+    while (Q < qmax && Q < gcap && (int64_t)(ncol > 0 ? ncol : 1) * (Q * 2) <= kCT) Q <<= 1;
+  }
+  const int cols_per_pass = kCT / Q;
+  const int my_col = ctid / Q;  // column (within a pass) and lane (within the column) of this thread
+  const int my_q = ctid % Q;
+
+  // uniform batches (single GPU): the CTA's slice of a batch is the same every step
+  const int64_t lo_uni = slice_lo(p.B, cta, G);
+  const int64_t n_uni = slice_lo(p.B, cta + 1, G) - lo_uni;
+
+  // optional phase profile: consumer thread 0 of every CTA sums the cycles between these marks
+  unsigned long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long t_prev = 0;
+  const bool prof = (p.dbg != nullptr) && ctid == 0;
+  auto mark = [&](int i) {
+    if (prof) {
+      const long long t = clock64();
+      ph[i] += (unsigned long long)(t - t_prev);
+      t_prev = t;
+    }
+  };
+  if (prof) t_prev = clock64();
+
   for (int s = 0; s < p.nb; ++s) {
-    const int64_t rows = step_rows(s);
-    const int64_t off = step_begin(s);
-    const int64_t lo = slice_lo(rows, cta, G);
-    const int64_t n = slice_lo(rows, cta + 1, G) - lo;
+    int64_t off, lo, n;
+    if (p.step_off == nullptr) {
+      off = ((int64_t)first_step + s) * p.B;
+      lo = lo_uni;
+      n = n_uni;
+    } else {
+      const int64_t rows = step_rows(s);
+      off = step_begin(s);
+      lo = slice_lo(rows, cta, G);
+      n = slice_lo(rows, cta + 1, G) - lo;
+    }
 #pragma unroll
     for (int k = 0; k < KC; ++k) g[k] = make_float4(0.f, 0.f, 0.f, 0.f);
 
     // ---- rows of this step: warp `warp` takes rows warp, warp+NW, ... ; U at a time ----
-    for (int64_t j = warp; j < n; j += (int64_t)NW * U) {
+    for (int64_t j = cw; j < n; j += (int64_t)NW * U) {
       float4 x[U][KC];
       float dot[U], y[U];
 #pragma unroll
@@ -465,113 +626,132 @@ __global__ void __launch_bounds__(32 * (NW + 1), 1) sgd_epoch_kernel(const Epoch
       }
     }
     qbase += (uint64_t)n;
+    mark(0);  // rows of this step done (this warp)
 
     // ---- CTA partial: fixed-order sum over the warps ----
 #pragma unroll
-    for (int k = 0; k < KC; ++k) gred[(warp * KC + k) * 32 + lane] = g[k];
+    for (int k = 0; k < KC; ++k) gred[(cw * KC + k) * 32 + lane] = g[k];
     consumer_bar<kCT>();
+    mark(1);  // all warps of the CTA done
     const int par = (first_step + s) & 1;
-    float4* my_part = p.partials + ((int64_t)par * G + cta) * C4;
-    for (int f = ctid; f < C4; f += kCT) {
+    auto cta_partial = [&](int f) -> float4 {
       const int k = f >> 5, l = f & 31;
       float4 acc = gred[(0 * KC + k) * 32 + l];
 #pragma unroll
       for (int wq = 1; wq < NW; ++wq) acc = f4_add(acc, gred[(wq * KC + k) * 32 + l]);
-      st_cg_f4(my_part + f, acc);
+      return acc;
+    };
+    if (p.reduce_mode >= 3) {
+      // ================= DATAFLOW: no barrier, no atomics, tagged words =================
+      const uint32_t tag = tag_base + (uint32_t)s + 1u;
+      // every CTA publishes its partial gradient (double-buffered by step parity)
+      uint4* my_part = p.ll_part + ((int64_t)par * G + cta) * C4 * 2;
+      for (int f = ctid; f < C4; f += kCT) ll_store_f4(my_part + (int64_t)f * 2, cta_partial(f), tag);
+      const uint4* parts = p.ll_part + (int64_t)par * G * C4 * 2;
+      mark(2);  // partial published
+
+      if (p.reduce_mode == 4) {
+        // ---- ONE hop (latency-bound shapes, small grids): every CTA gathers all G partials
+        // itself, in the same fixed order, and updates its own copy of the weights.
+        for (int base = 0; base < C4; base += cols_per_pass) {
+          const int fi = base + my_col;
+          const bool active = fi < C4;
+          const float4 tot = ll_gather<kCT>(parts, C4, active ? fi : 0, G, my_q, Q, active, tag, p.err, xred, ctid);
+          if (active && my_q == 0) {
+            float4 gs;
+            w_s[fi] = updated(fi, w_s[fi], tot, &gs);
+            if (cta == 0) reinterpret_cast<float4*>(p.g_last)[fi] = gs;
+          }
+        }
+        mark(3);  // gathered + updated
+        consumer_bar<kCT>();
+        mark(6);
+        continue;
+      }
+
+      // ---- TWO hops: the owner of a column group gathers the G partials of that group
+      // (multi-GPU: sends its slice sum to the same slot of every rank's inbox over NVLink and
+      // gathers the ranks' slices in a fixed order -> identical bits on every GPU), applies
+      // w = a*(g/B) + w and publishes the new weights; every CTA polls them into shared memory.
+      for (int base = 0; base < nf; base += cols_per_pass) {
+        const int fi = base + my_col;
+        const bool active = fi < nf;
+        const int f = f0 + (active ? fi : 0);
+        // old weights are read before anything of this step is published (the mailbox poll below
+        // overwrites w_s once the new ones arrive)
+        const float4 w_old = active ? w_s[f] : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 tot = ll_gather<kCT>(parts, C4, f, G, my_q, Q, active, tag, p.err, xred, ctid);
+        if (p.nranks > 1) {  // uniform over the grid
+          const int64_t slot = ((int64_t)par * p.nranks) * C4;
+          if (active) {  // lane q writes the inboxes of ranks q, q+Q, ...: NVLink stores in parallel
+            for (int pr = my_q; pr < p.nranks; pr += Q)
+              ll_store_f4(p.ll_inbox_peer[pr] + (slot + (int64_t)p.rank * C4 + f) * 2, tot, tag);
+          }
+          // the ranks' slices are gathered like the partials: lane q polls rank q, fixed tree
+          tot = ll_gather<kCT>(p.ll_inbox_local + slot * 2, C4, f, p.nranks, my_q, Q, active, tag, p.err, xred, ctid);
+        }
+        // every lane of the group holds `tot`: lane q publishes the new weights into the
+        // mailboxes of CTAs q, q+Q, ... (private copies keep 148 pollers off one line)
+        if (active) {
+          float4 gs;
+          const float4 wv = updated(f, w_old, tot, &gs);
+          for (int dst = my_q; dst < p.w_copies; dst += Q)
+            ll_store_f4(p.ll_w + ((int64_t)dst * C4 + f) * 2, wv, tag);
+          if (my_q == 0) reinterpret_cast<float4*>(p.g_last)[f] = gs;
+        }
+      }
+      mark(4);  // owner work (gather, exchange, publish) done
+      const uint4* my_w = p.ll_w + (p.w_copies > 1 ? (int64_t)cta * C4 * 2 : 0);
+      for (int f = ctid; f < C4; f += kCT) w_s[f] = ll_wait_f4(my_w + (int64_t)f * 2, tag, p.err);
+      mark(5);  // new weights arrived
+      consumer_bar<kCT>();
+      mark(6);
+      continue;
     }
 
-    // ---- grid reduction + fused update ----
+    // ================= barrier-based reductions (kept for A/B measurements) =================
+    float4* my_part = p.partials + ((int64_t)par * G + cta) * C4;
+    for (int f = ctid; f < C4; f += kCT) st_cg_f4(my_part + f, cta_partial(f));
     bar_count += 1;
     grid_barrier<kCT>(p.bar, bar_base + bar_count * (unsigned)G, ctid, p.err);
     const float4* parts = p.partials + (int64_t)par * G * C4;
-    if (p.reduce_mode == 1 && p.nranks == 1) {
-      // ALLGATHER: every CTA sums all G partials itself (same order everywhere -> same bits)
-      int Q = 1;
-      while (Q < 32 && (int64_t)C4 * (Q * 2) <= kCT) Q <<= 1;
-      for (int base = 0; base < C4; base += kCT / Q) {
-        const int fi = base + ctid / Q;
-        const int q = ctid % Q;
-        const bool active = fi < C4;
-        const float4 tot = tree_sum_sources<false>(parts, C4, active ? fi : 0, G, q, Q, active);
-        if (active && q == 0) {
-          float4 gs;
-          const float4 wv = updated(fi, tot, &gs);
-          w_s[fi] = wv;
-          if (cta == 0) reinterpret_cast<float4*>(p.g_last)[fi] = gs;
-        }
-      }
-      consumer_bar<kCT>();
-    } else {
-      // SCATTER: CTA k owns the float4 columns [f0, f0+nf); it sums them over all partials,
-      // (multi-GPU: exchanges the slice sums with the same CTA of every peer over NVLink),
-      // applies the update and publishes the new weights; after a second grid barrier every
-      // CTA reloads them.
-      const int f0 = (int)slice_lo(C4, cta, G);
-      const int nf = (int)slice_lo(C4, cta + 1, G) - f0;
-      int Q = 1;
-      while (Q < 32 && (int64_t)(nf > 0 ? nf : 1) * (Q * 2) <= kCT) Q <<= 1;
-      for (int base = 0; base < nf; base += kCT / Q) {
-        const int fi = base + ctid / Q;
-        const int q = ctid % Q;
-        const bool active = fi < nf;
-        const int f = f0 + (active ? fi : 0);
-        const float4 tot = tree_sum_sources<false>(parts, C4, f, G, q, Q, active);
-        if (active && q == 0) {
-          if (p.nranks == 1) {
-            float4 gs;
-            const float4 wv = updated(f, tot, &gs);
-            st_cg_f4(p.w_stage + f, wv);
-            reinterpret_cast<float4*>(p.g_last)[f] = gs;
-          } else {
-            // fused gradient exchange, part 1: my slice sum into slot [par][rank] of EVERY
-            // rank's inbox -- plain stores to peer-mapped memory, i.e. NVLink writes
-            for (int pr = 0; pr < p.nranks; ++pr)
-              p.xchg_peer[pr][((int64_t)par * p.nranks + p.rank) * C4 + f] = tot;
-            __threadfence_system();
-          }
-        }
-      }
-      if (p.nranks > 1 && nf > 0) {
-        // part 2: publish one flag per destination rank (release at system scope, after the
-        // CTA barrier that orders every thread's slice stores before it), then wait until
-        // every rank's slice for this step has landed in my inbox.
-        consumer_bar<kCT>();
-        const uint32_t tag = p.epoch_tag + (uint32_t)s + 1u;
-        if (ctid < p.nranks) {
-          st_release_sys(p.flag_peer[ctid] + ((int64_t)par * p.nranks + p.rank) * G + cta, tag);
-          const unsigned int* fl = p.flag_local + ((int64_t)par * p.nranks + ctid) * G + cta;
-          SpinGuard guard;
-          while ((int)(ld_acquire_sys(fl) - tag) < 0) {
-            if (guard.expired(p.err, 2u)) break;
-          }
-        }
-        consumer_bar<kCT>();
-        // part 3: add the ranks' slices in rank order (identical bits on every GPU) and update
-        const float4* inbox = p.xchg_local + (int64_t)par * p.nranks * C4;
-        for (int fi = ctid; fi < nf; fi += kCT) {
-          const int f = f0 + fi;
-          float4 tot = ld_volatile_f4(inbox + f);
-          for (int pr = 1; pr < p.nranks; ++pr)
-            tot = f4_add(tot, ld_volatile_f4(inbox + (int64_t)pr * C4 + f));
-          float4 gs;
-          const float4 wv = updated(f, tot, &gs);
+    for (int base = 0; base < ncol; base += cols_per_pass) {
+      const int fi = base + my_col;
+      const bool active = fi < ncol;
+      const int f = col0 + (active ? fi : 0);
+      const float4 tot = tree_sum_sources<false>(parts, C4, f, G, my_q, Q, active);
+      if (active && my_q == 0) {
+        float4 gs;
+        const float4 wv = updated(f, w_s[f], tot, &gs);
+        if (p.reduce_mode == 1) {
+          // ALLGATHER: every CTA summed all G partials itself (same order -> same bits)
+          w_s[f] = wv;
+          if (cta == 0) reinterpret_cast<float4*>(p.g_last)[f] = gs;
+        } else {
+          // SCATTER: the owner stages the new weights of its columns
           st_cg_f4(p.w_stage + f, wv);
           reinterpret_cast<float4*>(p.g_last)[f] = gs;
         }
       }
+    }
+    if (p.reduce_mode != 1) {  // SCATTER: second grid barrier, then everybody reloads the weights
       bar_count += 1;
       grid_barrier<kCT>(p.bar, bar_base + bar_count * (unsigned)G, ctid, p.err);
       for (int f = ctid; f < C4; f += kCT) w_s[f] = ld_cg_f4(p.w_stage + f);
-      consumer_bar<kCT>();
     }
+    consumer_bar<kCT>();
   }
 
+  if (prof) {
+    for (int i = 0; i < 8; ++i) p.dbg[(int64_t)cta * 8 + i] = ph[i];
+  }
   // final weights back to global (every CTA holds the same bits; CTA 0 writes)
   if (cta == 0) {
     for (int c = ctid; c < p.C; c += kCT) p.w[c] = reinterpret_cast<float*>(w_s)[c];
     if (p.ctl != nullptr && ctid == 0) {  // every CTA has read ctl before its first grid barrier
       p.ctl->step = first_step + p.nb;
       p.ctl->bar_base = bar_base + bar_count * (unsigned)G;
+      p.ctl->tag_base = tag_base + (uint32_t)p.nb;
     }
   }
 }

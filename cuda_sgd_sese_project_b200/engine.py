@@ -236,6 +236,14 @@ class SGDEngine:
         L.check(L.load().sgd_mean_abs_error(self._h, None, C.byref(s)))
         return float(s.value)
 
+    def debug_phase_cycles(self) -> np.ndarray:
+        """[grid, 8] cycle sums per phase of the last launch (needs B200SGD_PHASE_PROFILE=1)."""
+        out = np.zeros((self.grid, 8), dtype=np.uint64)
+        n = L.load().sgd_debug_phase_cycles(self._h, _ptr(out), self.grid)
+        if n < 0:
+            L.check(n)
+        return out[:n]
+
     # -- peers (multi-GPU)
     def peer_export(self) -> bytes:
         buf = C.create_string_buffer(L.SGD_PEER_HANDLE_BYTES)

@@ -53,7 +53,9 @@ typedef enum {
 typedef enum {
   SGD_REDUCE_AUTO = 0,
   SGD_REDUCE_ALLGATHER = 1, /* every CTA sums all partials itself: 1 grid barrier, G^2*C traffic */
-  SGD_REDUCE_SCATTER = 2    /* column-sliced reduce + broadcast: 2 grid barriers, 2*G*C traffic  */
+  SGD_REDUCE_SCATTER = 2,   /* column-sliced reduce + broadcast: 2 grid barriers, 2*G*C traffic  */
+  SGD_REDUCE_DATAFLOW = 3,  /* column-sliced, tagged words instead of barriers: 2 one-way hops   */
+  SGD_REDUCE_DATAFLOW_1HOP = 4 /* every CTA gathers all tagged partials itself: 1 hop, small grids */
 } sgd_reduce;
 
 typedef struct sgd_config {
@@ -170,6 +172,12 @@ int sgd_get_last_gradient(sgd_ctx* ctx, float* g);
  * With nranks > 1 it returns this rank's SUM of absolute errors in *sum_out (the caller adds the
  * ranks and divides by R); mae_out is sum/R_local... for nranks == 1 it is the reference's value */
 int sgd_mean_abs_error(sgd_ctx* ctx, float* mae_out, double* sum_out);
+
+/* diagnostics: when the context was created with B200SGD_PHASE_PROFILE=1 in the environment, the
+ * epoch kernel sums, per CTA, the SM cycles of the phases of a step (rows | CTA reduce | publish
+ * partial | gather+update (1-hop) | owner work (2-hop) | wait for weights | CTA barrier | -) of
+ * the LAST launch.  out gets 8 values per CTA; returns the number of CTAs written or < 0. */
+int sgd_debug_phase_cycles(sgd_ctx* ctx, uint64_t* out, int32_t max_ctas);
 
 /* ---- multi-GPU (new functionality, BASELINE.json north_star; one process per GPU) -----------
  * The d-float gradient exchange runs inside the step kernel over NVLink peer memory.  Each rank

@@ -156,7 +156,7 @@ def test_batch_larger_than_rows_is_rejected():
     assert ei.value.code == _lib.SGD_ERR_ARG
 
 
-@pytest.mark.parametrize("reduce", [_lib.SGD_REDUCE_ALLGATHER, _lib.SGD_REDUCE_SCATTER])
+@pytest.mark.parametrize("reduce", [_lib.SGD_REDUCE_ALLGATHER, _lib.SGD_REDUCE_SCATTER, _lib.SGD_REDUCE_DATAFLOW, _lib.SGD_REDUCE_DATAFLOW_1HOP])
 @pytest.mark.parametrize("grid", [1, 2, 7, 37, 148])
 def test_reduction_modes_and_grids(reduce, grid):
     X, y, _ = make_regression(6000, 100, seed=9)
