@@ -25,6 +25,7 @@
 #include "host_io.hpp"
 #include "host_rng.hpp"
 #include "sgd_kernels.cuh"
+#include "shuffle_kernels.cuh"
 
 namespace {
 
@@ -75,21 +76,20 @@ KernelChoice make_choice() {
 // fewer consumer warps and no row unrolling, so the latency-critical step tail is not slowed down
 // by warps that only execute control code (the tail is issue-bound).
 bool choose_kernel(int C4, int64_t rows_per_cta, KernelChoice* out) {
+  // a ring tile holds NW*U <= 32 rows (one producer round)
   if (C4 <= 32) {
     if (rows_per_cta <= 8) *out = make_choice<1, 1, 8>();
     else if (rows_per_cta <= 16) *out = make_choice<1, 2, 8>();
-    else if (rows_per_cta <= 32) *out = make_choice<1, 2, 16>();
-    else *out = make_choice<1, 4, 16>();
+    else *out = make_choice<1, 2, 16>();
   } else if (C4 <= 64) {
     if (rows_per_cta <= 8) *out = make_choice<2, 1, 8>();
-    else if (rows_per_cta <= 32) *out = make_choice<2, 2, 16>();
-    else *out = make_choice<2, 4, 16>();
+    else if (rows_per_cta <= 16) *out = make_choice<2, 2, 8>();
+    else *out = make_choice<2, 2, 16>();
   } else if (C4 <= 128) {
     if (rows_per_cta <= 8) *out = make_choice<4, 1, 8>();
-    else *out = make_choice<4, 2, 16>();
+    else *out = make_choice<4, 1, 16>();
   } else if (C4 <= 256) {
-    if (rows_per_cta <= 8) *out = make_choice<8, 1, 8>();
-    else *out = make_choice<8, 2, 8>();
+    *out = make_choice<8, 1, 8>();
   } else if (C4 <= 512) {
     *out = make_choice<16, 1, 8>();
   } else {
@@ -111,7 +111,7 @@ struct sgd_ctx {
   cudaStream_t stream = nullptr, copy_stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t ev_perm[2] = {nullptr, nullptr};  // upload of d_perm[i] finished
-  cudaEvent_t ev_done[2] = {nullptr, nullptr};  // last kernel reading d_perm[i] finished
+  cudaEvent_t ev_done[3] = {nullptr, nullptr, nullptr};  // last reader of d_perm[i] done; [2]: shuffle scratch free
 
   // device state
   float* d_rec = nullptr;
@@ -136,6 +136,13 @@ struct sgd_ctx {
   double* d_mae = nullptr;
   int mae_blocks = 0;
 
+  // device shuffle (shuffle_kernels.cuh): raw stream / targets, hit lists in CSR form
+  bool device_shuffle = false;
+  uint32_t* d_tgt = nullptr;
+  int32_t *d_cnt = nullptr, *d_start = nullptr, *d_hits = nullptr, *d_first = nullptr, *d_tilesum = nullptr;
+  int32_t scan_tiles = 0;
+  bool host_ind_stale = false;  // h_ind lags behind the device permutation
+
   // host permutation state
   std::vector<int32_t> h_ind;                // the reference's ind_vector (main.cu:421-424)
   int32_t* h_stage[2] = {nullptr, nullptr};  // pinned upload staging
@@ -143,10 +150,12 @@ struct sgd_ctx {
   int cur = 0;  // which d_perm / h_stage holds the active permutation
   bool perm_valid = false, data_loaded = false, have_true_w = false;
   float last_shuffle_ms = 0.f;
+  int last_shuffle_launches = 0;
 
   // kernel configuration
   KernelChoice kc{};
-  int grid = 0, reduce_mode = 0, nslots = 0, slot_log2 = 0, engine = SGD_ENGINE_PERSISTENT;
+  int grid = 0, reduce_mode = 0, ntiles = 0, tile_log2 = 0, engine = SGD_ENGINE_PERSISTENT;
+  int nprod = 1;  // producer warps
   size_t smem_bytes = 0;
   cudaGraphExec_t graph_exec = nullptr;
   int graph_nodes = 0;
@@ -189,10 +198,12 @@ void free_all(sgd_ctx* c) {
   cudaFree(c->d_step_off); cudaFree(c->d_counts); cudaFree(c->d_partials); cudaFree(c->d_wstage);
   cudaFree(c->d_glast); cudaFree(c->d_rout); cudaFree(c->d_bar); cudaFree(c->d_ctl);
   cudaFree(c->d_ll_part); cudaFree(c->d_ll_w); cudaFree(c->d_dbg);
+  cudaFree(c->d_tgt); cudaFree(c->d_cnt); cudaFree(c->d_start); cudaFree(c->d_hits); cudaFree(c->d_first);
+  cudaFree(c->d_tilesum);
   cudaFree(c->d_mae); cudaFree(c->d_xchg_block);
   if (c->h_stage[0]) cudaFreeHost(c->h_stage[0]);
   if (c->h_stage[1]) cudaFreeHost(c->h_stage[1]);
-  cudaEvent_t evs[] = {c->ev0, c->ev1, c->ev_perm[0], c->ev_perm[1], c->ev_done[0], c->ev_done[1]};
+  cudaEvent_t evs[] = {c->ev0, c->ev1, c->ev_perm[0], c->ev_perm[1], c->ev_done[0], c->ev_done[1], c->ev_done[2]};
   for (cudaEvent_t e : evs)
     if (e) cudaEventDestroy(e);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -206,28 +217,48 @@ int configure_launch(sgd_ctx* c) {
   const int64_t rows_step = std::max<int64_t>(1, (int64_t)c->B / std::max(1, c->cfg.nranks));
   int grid = c->cfg.grid;
   if (grid <= 0) {
-    // one CTA per SM once every CTA gets a few rows per step; fewer CTAs for tiny batches keep
-    // the partial-gradient gather cheap
-    grid = (int)std::min<int64_t>(c->num_sms, std::max<int64_t>(1, rows_step / 2));
+    // Small steps are bound by the step tail (publish -> gather -> publish -> poll, ~1.7 us at 32
+    // CTAs, ~2.7 us at 148, measured), which grows with the number of CTAs, so they get
+    // ~24 rows per CTA; once a step moves a few MB the row stream dominates and every SM is used.
+    const int64_t step_bytes = rows_step * c->ld * 4;
+    if (step_bytes < (2ll << 20)) {
+      // power of two: measured 3.3 us/step at 32 or 64 CTAs vs 4.8-5.8 us at 41, 48 or 100 on
+      // the same shape (some owners' polling then runs 2.5x late; cause not pinned down)
+      grid = 1;
+      while (grid * 2 <= 64 && (int64_t)grid * 2 * 24 <= rows_step) grid *= 2;
+    } else {
+      grid = c->num_sms;
+    }
   }
   grid = std::max(1, std::min(grid, c->num_sms));
   if (!choose_kernel(c->C4, (rows_step + grid - 1) / grid, &c->kc))
     return fail(SGD_ERR_ARG, "unsupported row width");
   const size_t slot_bytes = (size_t)c->ld * 4;
-  if (c->kc.fixed_smem + 2 * slot_bytes > kMaxDynSmem)
+  // producer warps: one TMA bulk copy per row is issued lane by lane (~30-40 cycles each), so
+  // short rows need several issuing warps to keep up with HBM; long rows and tiny batches do not
+  {
+    const int64_t rows_cta = (rows_step + grid - 1) / grid;
+    int np = 1;
+    if (slot_bytes <= 1024) np = rows_cta >= 64 ? 4 : 2;
+    else if (slot_bytes <= 4096) np = rows_cta >= 32 ? 2 : 1;
+    if (const char* e = std::getenv("B200SGD_PRODUCER_WARPS")) np = std::atoi(e);
+    c->nprod = std::max(1, std::min(np, b200sgd::kMaxProducerWarps));
+  }
+  const size_t tile_bytes = (size_t)c->kc.NW * c->kc.U * slot_bytes;
+  if (c->kc.fixed_smem + 2 * tile_bytes > kMaxDynSmem)
     return fail(SGD_ERR_ARG, "row too wide for the shared-memory ring");
-  int nslots = 2, lg = 1;
-  while (nslots * 2 <= b200sgd::kMaxSlots &&
-         c->kc.fixed_smem + (size_t)(nslots * 2) * slot_bytes <= kMaxDynSmem) {
-    nslots *= 2;
+  int ntiles = 2, lg = 1;
+  while (ntiles * 2 <= b200sgd::kMaxTiles &&
+         c->kc.fixed_smem + (size_t)(ntiles * 2) * tile_bytes <= kMaxDynSmem) {
+    ntiles *= 2;
     ++lg;
   }
-  c->nslots = nslots;
-  c->slot_log2 = lg;
-  c->smem_bytes = c->kc.fixed_smem + (size_t)nslots * slot_bytes;
+  c->ntiles = ntiles;
+  c->tile_log2 = lg;
+  c->smem_bytes = c->kc.fixed_smem + (size_t)ntiles * tile_bytes;
   CUDA_TRY(cudaFuncSetAttribute(c->kc.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
   int occ = 0;
-  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, c->kc.fn, 32 * (c->kc.NW + 1), c->smem_bytes));
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, c->kc.fn, 32 * (c->kc.NW + c->nprod), c->smem_bytes));
   if (occ < 1) return fail(SGD_ERR_CUDA, "step kernel does not fit on an SM");
   c->grid = grid;
   int mode = c->cfg.reduce;
@@ -261,9 +292,10 @@ void fill_params(sgd_ctx* c, b200sgd::EpochParams* p, int32_t epoch, int buf) {
   p->bar = c->d_bar;
   p->err = c->d_bar + 1;
   p->reduce_mode = c->reduce_mode;
-  p->nslots = c->nslots;
-  p->slot_log2 = c->slot_log2;
+  p->ntiles = c->ntiles;
+  p->tile_log2 = c->tile_log2;
   p->slot_bytes = (uint32_t)(c->ld * 4);
+  p->nprod = c->nprod;
   p->ll_part = c->d_ll_part;
   p->ll_w = c->d_ll_w;
   p->w_copies = c->w_copies;
@@ -311,7 +343,7 @@ int build_graph(sgd_ctx* c) {
   CUDA_TRY(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
   cudaError_t e = cudaSuccess;
   for (int i = 0; i < nodes && e == cudaSuccess; ++i)
-    e = cudaLaunchKernel(c->kc.fn, dim3(c->grid), dim3(32 * (c->kc.NW + 1)), args, c->smem_bytes, c->stream);
+    e = cudaLaunchKernel(c->kc.fn, dim3(c->grid), dim3(32 * (c->kc.NW + c->nprod)), args, c->smem_bytes, c->stream);
   cudaError_t e2 = cudaStreamEndCapture(c->stream, &graph);
   if (e != cudaSuccess || e2 != cudaSuccess) {
     if (graph) cudaGraphDestroy(graph);
@@ -352,9 +384,53 @@ int launch_epoch(sgd_ctx* c, int32_t epoch, int buf, int* launches) {
   CUDA_TRY(cudaMemsetAsync(c->d_bar, 0, sizeof(unsigned int), c->stream));
   c->step_tag += (uint32_t)c->nb;  // every rank advances identically: tags agree across GPUs
   void* args[] = {&p};
-  CUDA_TRY(cudaLaunchCooperativeKernel(c->kc.fn, dim3(c->grid), dim3(32 * (c->kc.NW + 1)), args,
+  CUDA_TRY(cudaLaunchCooperativeKernel(c->kc.fn, dim3(c->grid), dim3(32 * (c->kc.NW + c->nprod)), args,
                                        c->smem_bytes, c->stream));
   *launches += 1;
+  return SGD_OK;
+}
+
+// Host part of one device shuffle: draw the n-1 raw values of the rand() stream this epoch
+// consumes (main.cu:90 / :207 consume exactly n-1 per std::random_shuffle) into pinned staging.
+void draw_raw_stream(sgd_ctx* c, int buf) {
+  uint32_t* stage = reinterpret_cast<uint32_t*>(c->h_stage[buf]);
+  stage[0] = 0;
+  if (c->R > 1) c->rng.raw(stage + 1, (size_t)(c->R - 1));
+}
+
+// Device part: upload the raw stream (copy stream), then K1..K5 on the compute stream turn
+// d_perm[src] into d_perm[dst].  No host sync.
+int enqueue_device_shuffle(sgd_ctx* c, int stage_buf, int src, int dst, int* launches) {
+  const int64_t n = c->R;
+  CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->ev_done[2], 0));  // previous shuffle done with d_tgt
+  CUDA_TRY(cudaMemcpyAsync(c->d_tgt, c->h_stage[stage_buf], sizeof(uint32_t) * (size_t)n, cudaMemcpyHostToDevice,
+                           c->copy_stream));
+  CUDA_TRY(cudaEventRecord(c->ev_perm[stage_buf], c->copy_stream));
+  CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_perm[stage_buf], 0));
+  const int blocks = (int)std::min<int64_t>((n + 255) / 256, (int64_t)c->num_sms * 16);
+  CUDA_TRY(cudaMemsetAsync(c->d_cnt, 0, sizeof(int32_t) * ((size_t)n + 1), c->stream));
+  b200sgd::shuf_targets_kernel<<<blocks, 256, 0, c->stream>>>(c->d_tgt, n, c->d_cnt);
+  b200sgd::scan_tile_sums_kernel<<<c->scan_tiles, b200sgd::kScanBlock, 0, c->stream>>>(c->d_cnt, n, c->d_tilesum);
+  b200sgd::scan_tile_offsets_kernel<<<1, b200sgd::kScanBlock, 0, c->stream>>>(c->d_tilesum, c->scan_tiles,
+                                                                             c->d_tilesum + c->scan_tiles);
+  b200sgd::scan_apply_kernel<<<c->scan_tiles, b200sgd::kScanBlock, 0, c->stream>>>(
+      c->d_cnt, n, c->d_tilesum, c->d_tilesum + c->scan_tiles, c->d_start);
+  CUDA_TRY(cudaMemsetAsync(c->d_cnt, 0, sizeof(int32_t) * ((size_t)n + 1), c->stream));
+  b200sgd::shuf_fill_kernel<<<blocks, 256, 0, c->stream>>>(c->d_tgt, n, c->d_start, c->d_cnt, c->d_hits);
+  b200sgd::shuf_order_kernel<<<blocks, 256, 0, c->stream>>>(n, c->d_start, c->d_hits, c->d_first);
+  b200sgd::shuf_resolve_kernel<<<blocks, 256, 0, c->stream>>>(c->d_tgt, n, c->d_start, c->d_hits, c->d_first,
+                                                            c->d_perm[src], c->d_perm[dst]);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaEventRecord(c->ev_done[2], c->stream));
+  *launches += 7;
+  return SGD_OK;
+}
+
+int sync_host_ind(sgd_ctx* c) {  // bring h_ind up to date after device shuffles
+  if (!c->host_ind_stale) return SGD_OK;
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(cudaMemcpy(c->h_ind.data(), c->d_perm[c->cur], sizeof(int32_t) * (size_t)c->R, cudaMemcpyDeviceToHost));
+  c->host_ind_stale = false;
   return SGD_OK;
 }
 
@@ -522,6 +598,7 @@ int sgd_create(const sgd_config* cfg, const float* X, const float* y, sgd_ctx** 
       CUDA_TRY(cudaEventCreateWithFlags(&c->ev_perm[i], cudaEventDisableTiming));
       CUDA_TRY(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
     }
+    CUDA_TRY(cudaEventCreateWithFlags(&c->ev_done[2], cudaEventDisableTiming));
     SGD_TRY(configure_launch(c));
     const size_t rec_bytes = sizeof(float) * (size_t)std::max<int64_t>(1, c->local_rows) * (size_t)c->ld;
     if (cudaMalloc(&c->d_rec, rec_bytes) != cudaSuccess) {
@@ -542,13 +619,14 @@ int sgd_create(const sgd_config* cfg, const float* X, const float* y, sgd_ctx** 
     CUDA_TRY(cudaMalloc(&c->d_partials, sizeof(float4) * 2 * (size_t)c->grid * c->C4));
     CUDA_TRY(cudaMemset(c->d_partials, 0, sizeof(float4) * 2 * (size_t)c->grid * c->C4));
     CUDA_TRY(cudaMalloc(&c->d_wstage, sizeof(float4) * c->C4));
-    CUDA_TRY(cudaMalloc(&c->d_ll_part, sizeof(uint4) * 2 * 2 * (size_t)c->grid * c->C4));
-    CUDA_TRY(cudaMemset(c->d_ll_part, 0, sizeof(uint4) * 2 * 2 * (size_t)c->grid * c->C4));
+    const size_t Gp = ((size_t)c->grid + 3) & ~(size_t)3, C4p = ((size_t)c->C4 + 3) & ~(size_t)3;
+    CUDA_TRY(cudaMalloc(&c->d_ll_part, sizeof(uint4) * 2 * 2 * Gp * c->C4));
+    CUDA_TRY(cudaMemset(c->d_ll_part, 0, sizeof(uint4) * 2 * 2 * Gp * c->C4));
     // private weight mailboxes per CTA while they stay small (latency-bound shapes); one shared
     // copy for wide rows, where steps are long and the extra L2 traffic would not pay
     c->w_copies = ((size_t)c->grid * c->C4 * 32 <= (512u << 10)) ? c->grid : 1;
-    CUDA_TRY(cudaMalloc(&c->d_ll_w, sizeof(uint4) * 2 * (size_t)c->w_copies * c->C4));
-    CUDA_TRY(cudaMemset(c->d_ll_w, 0, sizeof(uint4) * 2 * (size_t)c->w_copies * c->C4));
+    CUDA_TRY(cudaMalloc(&c->d_ll_w, sizeof(uint4) * 2 * (size_t)c->w_copies * C4p));
+    CUDA_TRY(cudaMemset(c->d_ll_w, 0, sizeof(uint4) * 2 * (size_t)c->w_copies * C4p));
     CUDA_TRY(cudaMalloc(&c->d_glast, sizeof(float4) * c->C4));
     CUDA_TRY(cudaMemset(c->d_glast, 0, sizeof(float4) * c->C4));
     CUDA_TRY(cudaMalloc(&c->d_bar, sizeof(unsigned int) * 2));
@@ -564,10 +642,22 @@ int sgd_create(const sgd_config* cfg, const float* X, const float* y, sgd_ctx** 
       CUDA_TRY(cudaMalloc(&c->d_rout, sizeof(float) * (size_t)std::max<int64_t>(1, c->rout_len)));
       CUDA_TRY(cudaMemset(c->d_rout, 0, sizeof(float) * (size_t)std::max<int64_t>(1, c->rout_len)));
     }
+    // bit-exact permutation on the device for anything but tiny data sets
+    c->device_shuffle = !(c->cfg.flags & SGD_FLAG_HOST_SHUFFLE) && c->R >= 32768;
+    if (c->device_shuffle) {
+      const size_t n = (size_t)c->R;
+      c->scan_tiles = (int32_t)((n + b200sgd::kScanTile - 1) / b200sgd::kScanTile);
+      CUDA_TRY(cudaMalloc(&c->d_tgt, sizeof(uint32_t) * n));
+      CUDA_TRY(cudaMalloc(&c->d_cnt, sizeof(int32_t) * (n + 1)));
+      CUDA_TRY(cudaMalloc(&c->d_start, sizeof(int32_t) * (n + 1)));
+      CUDA_TRY(cudaMalloc(&c->d_hits, sizeof(int32_t) * n));
+      CUDA_TRY(cudaMalloc(&c->d_first, sizeof(int32_t) * n));
+      CUDA_TRY(cudaMalloc(&c->d_tilesum, sizeof(int32_t) * ((size_t)c->scan_tiles + 1)));
+    }
     c->mae_blocks = c->num_sms * 8;
     CUDA_TRY(cudaMalloc(&c->d_mae, sizeof(double) * c->mae_blocks));
     if (c->cfg.nranks > 1) {
-      c->xchg_bytes = sizeof(uint4) * 2 * 2 * (size_t)c->cfg.nranks * c->C4;
+      c->xchg_bytes = sizeof(uint4) * 2 * 2 * (size_t)c->cfg.nranks * (((size_t)c->C4 + 3) & ~(size_t)3);
       CUDA_TRY(cudaMalloc(&c->d_xchg_block, c->xchg_bytes));
       CUDA_TRY(cudaMemset(c->d_xchg_block, 0, c->xchg_bytes));
       c->peer_block[c->cfg.rank] = c->d_xchg_block;
@@ -579,6 +669,7 @@ int sgd_create(const sgd_config* cfg, const float* X, const float* y, sgd_ctx** 
     // main.cu:421-426: identity index vector, on host and device
     c->h_ind.resize((size_t)c->R);
     for (int64_t i = 0; i < c->R; ++i) c->h_ind[(size_t)i] = (int32_t)i;
+    CUDA_TRY(cudaMemcpy(c->d_perm[0], c->h_ind.data(), sizeof(int32_t) * (size_t)c->R, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaDeviceSynchronize());
     return SGD_OK;
   };
@@ -723,7 +814,7 @@ int sgd_get_config(const sgd_ctx* c, sgd_config* out) {
   out->engine = c->engine;
   out->batch = c->B;
   out->reserved[0] = c->nb;
-  out->reserved[1] = c->nslots;
+  out->reserved[1] = c->ntiles * c->kc.NW * c->kc.U;
   out->reserved[2] = (int32_t)c->smem_bytes;
   out->reserved[3] = c->kc.KC;
   out->reserved[4] = c->kc.U;
@@ -740,6 +831,22 @@ int sgd_shuffle(sgd_ctx* c) {
   SGD_TRY(check_ctx(c));
   SGD_TRY(bind(c));
   const auto t0 = clk::now();
+  if (c->device_shuffle) {
+    const int buf = c->cur ^ 1;
+    int launches = 0;
+    CUDA_TRY(cudaEventSynchronize(c->ev_perm[buf]));
+    draw_raw_stream(c, buf);
+    CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_done[buf], 0));
+    SGD_TRY(enqueue_device_shuffle(c, buf, c->cur, buf, &launches));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->cur = buf;
+    c->perm_valid = true;
+    c->host_ind_stale = true;
+    c->last_shuffle_ms = (float)ms_since(t0);
+    c->last_shuffle_launches = launches;
+    return SGD_OK;
+  }
+  SGD_TRY(sync_host_ind(c));
   // main.cu:90 / :207: std::random_shuffle(ind_vector.begin(), ind_vector.end()), cumulative
   b200sgd::exact_shuffle(c->rng, c->h_ind.data(), c->R);
   const int buf = c->cur ^ 1;
@@ -760,6 +867,7 @@ int sgd_set_permutation(sgd_ctx* c, const int32_t* perm) {
     if (perm[i] < 0 || perm[i] >= c->R) return fail(SGD_ERR_ARG, "permutation entry out of range");
   SGD_TRY(bind(c));
   std::memcpy(c->h_ind.data(), perm, sizeof(int32_t) * (size_t)c->R);
+  c->host_ind_stale = false;
   const int buf = c->cur ^ 1;
   CUDA_TRY(cudaEventSynchronize(c->ev_perm[buf]));
   std::memcpy(c->h_stage[buf], perm, sizeof(int32_t) * (size_t)c->R);
@@ -803,8 +911,9 @@ int sgd_epoch(sgd_ctx* c, int32_t epoch, sgd_timings* out) {
   SGD_TRY(check_watchdog(c));
   float ms = 0.f;
   CUDA_TRY(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
-  fill_timings(c, out, c->last_shuffle_ms, ms, launches, 1);
+  fill_timings(c, out, c->last_shuffle_ms, ms, launches + c->last_shuffle_launches, 1);
   c->last_shuffle_ms = 0.f;
+  c->last_shuffle_launches = 0;
   return SGD_OK;
 }
 
@@ -835,7 +944,19 @@ int sgd_run(sgd_ctx* c, int32_t first_epoch, int32_t num_epochs, sgd_timings* to
     }
   int launches = 0;
   int rc = SGD_OK;
-  auto stage_next = [&]() -> int {  // shuffle on this thread while the GPU runs the previous epoch
+  auto stage_next = [&]() -> int {  // host part of the shuffle runs while the GPU runs the previous epoch
+    if (c->device_shuffle) {
+      const int buf = c->cur ^ 1;
+      CUDA_TRY(cudaEventSynchronize(c->ev_perm[buf]));  // staging buffer free again
+      draw_raw_stream(c, buf);
+      // d_perm[buf] was last read by the epoch before the one in flight: stream order covers it
+      SGD_TRY(enqueue_device_shuffle(c, buf, c->cur, buf, &launches));
+      c->cur = buf;
+      c->perm_valid = true;
+      c->host_ind_stale = true;
+      return SGD_OK;
+    }
+    SGD_TRY(sync_host_ind(c));
     b200sgd::exact_shuffle(c->rng, c->h_ind.data(), c->R);
     const int buf = c->cur ^ 1;
     CUDA_TRY(cudaEventSynchronize(c->ev_perm[buf]));

@@ -28,7 +28,8 @@
 
 namespace b200sgd {
 
-constexpr int kMaxSlots = 256;  // ring slots (rows in flight per CTA), power of two
+constexpr int kMaxTiles = 64;  // ring tiles per CTA (power of two); a tile holds NW*U row slots
+constexpr int kMaxProducerWarps = 4;
 
 // Device-resident control block of the GRAPH engine: the captured step kernels carry no per-step
 // arguments; they read the step index, the step size and the permutation from here and the last
@@ -61,9 +62,10 @@ struct EpochParams {
   unsigned int* bar;        // grid barrier counter, zeroed by the host before the launch
   unsigned int* err;        // watchdog error word (0 = fine), see SpinGuard
   int32_t reduce_mode;      // 1 = ALLGATHER, 2 = SCATTER
-  int32_t nslots;           // ring slots (power of two)
-  int32_t slot_log2;
+  int32_t ntiles;           // ring tiles (power of two), each NW*U row slots
+  int32_t tile_log2;
   uint32_t slot_bytes;      // ld * 4
+  int32_t nprod;            // producer warps (1..kMaxProducerWarps); block = 32 * (NW + nprod)
   // DATAFLOW reduction (reduce_mode 3): tagged 8-byte words instead of barriers, see ll_store_f4
   uint4* ll_part;           // [grid][C4][2]  per-CTA partial gradients
   uint4* ll_w;              // [w_copies][C4][2] new weights, published by the column owners
@@ -235,17 +237,20 @@ __device__ __forceinline__ float4 ll_wait_f4(const uint4* src, uint32_t tag, uns
   return v;
 }
 
-// Dataflow twin of tree_sum_sources: sums the tagged float4 `f` of sources 0..nsrc-1 (source i at
-// base + (i*stride + f)*2); each load is retried until its tag shows up.  Q threads (a power of
+// Dataflow twin of tree_sum_sources: sums the tagged float4 `f` of sources 0..nsrc-1; each load
+// is retried until its tag shows up.  Q threads (a power of
 // two, possibly several warps) share one column group: thread q adds sources q, q+Q, ... in order,
 // a xor-butterfly combines the lanes of a warp and, for Q > 32, the warps' sums go through
 // `xred` and are added in warp order.  The order is fixed, so every CTA (and every rerun) gets the
 // same bits.  Returns the total in EVERY thread of the group.  Must be called by all consumer
 // threads of the CTA with the same Q.
 template <int kThreads>
-__device__ __forceinline__ float4 ll_gather(const uint4* base, int64_t stride, int f, int nsrc, int q, int Q,
-                                            bool active, uint32_t tag, unsigned int* err, float4* xred,
-                                            int ctid) {
+__device__ __forceinline__ float4 ll_gather(const uint4* base0, int64_t stride, int64_t col_stride, int f, int nsrc,
+                                            int q, int Q, bool active, uint32_t tag, unsigned int* err,
+                                            float4* xred, int ctid) {
+  // source i of column f sits at base0 + (i*stride + f*col_stride) * 2
+  const uint4* base = base0 + (int64_t)f * col_stride * 2;
+  f = 0;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   if (active) {
     int i = q;
@@ -361,19 +366,19 @@ __device__ __forceinline__ float4 tree_sum_sources(const float4* src, int64_t st
 // ------------------------------------------------------------------------------------------------
 template <int KC, int NW>
 struct EpochSmem {
-  static constexpr size_t kBarBytes = 2 * kMaxSlots * sizeof(uint64_t);
+  static constexpr size_t kBarBytes = 2 * kMaxTiles * sizeof(uint64_t);
   static constexpr size_t kWBytes = 32 * KC * sizeof(float4);
   static constexpr size_t kGredBytes = (size_t)NW * 32 * KC * sizeof(float4);
   static constexpr size_t kFixed = kBarBytes + kWBytes + kGredBytes;
 };
 
 template <int KC, int U, int NW>
-__global__ void __launch_bounds__(32 * (NW + 1), 1) sgd_epoch_kernel(const EpochParams p) {
-  constexpr int kThreads = 32 * (NW + 1);
+__global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1) sgd_epoch_kernel(const EpochParams p) {
+  const int kThreads = blockDim.x;  // 32 * (NW + p.nprod)
   constexpr int kCT = 32 * NW;  // consumer threads
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw);
-  uint64_t* empty_bar = full_bar + kMaxSlots;
+  uint64_t* empty_bar = full_bar + kMaxTiles;
   float4* w_s = reinterpret_cast<float4*>(smem_raw + EpochSmem<KC, NW>::kBarBytes);
   float4* gred = w_s + 32 * KC;
   unsigned char* ring = smem_raw + EpochSmem<KC, NW>::kFixed;
@@ -384,8 +389,11 @@ __global__ void __launch_bounds__(32 * (NW + 1), 1) sgd_epoch_kernel(const Epoch
   const int lane = tid & 31;
   const int cta = blockIdx.x;
   const int G = gridDim.x;
-  const int nslots = p.nslots;
-  const uint32_t slot_mask = (uint32_t)nslots - 1u;
+  constexpr int TR = NW * U;  // rows per ring tile = rows of one producer round
+  static_assert(TR <= 32, "a producer round is one warp instruction: at most 32 rows per tile");
+  const int ntiles = p.ntiles;
+  const uint32_t tile_mask = (uint32_t)ntiles - 1u;
+  const uint32_t tile_bytes = (uint32_t)TR * p.slot_bytes;
   const uint32_t full0 = smem_u32(full_bar);
   const uint32_t empty0 = smem_u32(empty_bar);
   const uint32_t ring0 = smem_u32(ring);
@@ -406,9 +414,9 @@ __global__ void __launch_bounds__(32 * (NW + 1), 1) sgd_epoch_kernel(const Epoch
   }
 
   if (tid == 0) {
-    for (int i = 0; i < nslots; ++i) {
-      mbar_init(full0 + 8u * i, 1);
-      mbar_init(empty0 + 8u * i, 1);
+    for (int i = 0; i < ntiles; ++i) {
+      mbar_init(full0 + 8u * i, 1);    // the producer's arrive.expect_tx; the rows complete the bytes
+      mbar_init(empty0 + 8u * i, NW);  // every consumer warp releases every tile once
     }
     fence_barrier_init();
   }
@@ -426,74 +434,102 @@ __global__ void __launch_bounds__(32 * (NW + 1), 1) sgd_epoch_kernel(const Epoch
     return p.step_off ? (p.step_off[sa + 1] - p.step_off[sa]) : p.B;
   };
 
-  if (warp == 0) {
-    // ===================================== PRODUCER =====================================
-    // (hardware warp 0: lowest issue priority and a different SM sub-partition than consumer
-    // warp 0, which carries the serial part of the step tail)
-    // Row sequence of this CTA: for every step its contiguous slice of the batch, numbered
-    // q = 0,1,2,... across steps; row q lives in slot q % nslots.  One round = up to 32 rows,
-    // one per lane; the indices of round k+1 are loaded before round k is issued.
-    const int per_round = nslots < 32 ? nslots : 32;
+  // uniform batches (single GPU): the CTA's slice of a batch is the same every step
+  const int64_t lo_uni = slice_lo(p.B, cta, G);
+  const int64_t n_uni = slice_lo(p.B, cta + 1, G) - lo_uni;
+  const int NP = p.nprod;  // producer warps: hardware warps 0..NP-1
+
+  if (warp < NP) {
+    // ===================================== PRODUCERS =====================================
+    // (lowest hardware warp ids: lowest issue priority; consumer warp 0, which carries the serial
+    // part of the step tail, sits on another SM sub-partition when NP == 1)
+    // The CTA's rows form a sequence of rounds: every step's contiguous slice of the batch cut
+    // into pieces of at most TR rows.  Round t fills ring tile t % ntiles, one row per lane, one
+    // TMA bulk copy per row, all completing on the tile's `full` barrier.  Flow control is per
+    // TILE (one wait / one expect_tx per round), not per row: the SM's mbarrier unit is shared
+    // with the consumers and per-row polling from 32 lanes starves them.  Producer warp w issues
+    // rounds w, w+NP, ...; the permutation indices of its next round are in flight while it
+    // issues the current one, so NP rounds of index loads overlap per CTA.
+    const int per_round = TR;
     int s = 0;
-    int64_t lo = 0, n = 0, j0 = 0;  // current step slice [lo, lo+n), next unissued row j0
+    int64_t lo = 0, n = 0, j0 = 0;  // current step slice [lo, lo+n), first row of the round j0
     int64_t off = 0;
-    uint64_t q0 = 0;                // sequence number of row j0
-    auto enter_step = [&](int ss) {
+    uint32_t tq = 0;  // sequence number of the current round
+    auto load_step = [&]() {
       n = 0;
-      if (ss < p.nb) {
-        const int64_t rows = step_rows(ss);
-        off = step_begin(ss);
-        lo = slice_lo(rows, cta, G);
-        n = slice_lo(rows, cta + 1, G) - lo;
+      if (s < p.nb) {
+        if (p.step_off == nullptr) {
+          off = ((int64_t)first_step + s) * p.B;
+          lo = lo_uni;
+          n = n_uni;
+        } else {
+          const int64_t rows = step_rows(s);
+          off = step_begin(s);
+          lo = slice_lo(rows, cta, G);
+          n = slice_lo(rows, cta + 1, G) - lo;
+        }
       }
     };
-    enter_step(0);
-    while (s < p.nb && n == 0) enter_step(++s);
-    int cnt = 0;
+    auto settle = [&]() {  // skip steps in which this CTA has no rows
+      while (s < p.nb && n == 0) {
+        ++s;
+        load_step();
+      }
+    };
+    auto round_cnt = [&]() -> int {
+      if (s >= p.nb) return 0;
+      return (int)((n - j0) < per_round ? (n - j0) : per_round);
+    };
+    auto advance = [&]() {  // to the next round of the CTA's sequence
+      const int c = round_cnt();
+      j0 += c;
+      tq += (c > 0) ? 1u : 0u;
+      if (s < p.nb && j0 >= n) {
+        j0 = 0;
+        ++s;
+        load_step();
+        settle();
+      }
+    };
+    load_step();
+    settle();
+    for (int k = 0; k < warp; ++k) advance();  // my first round
+    int cnt = round_cnt();
     int32_t idx = 0;
-    if (s < p.nb) {
-      cnt = (int)((n - j0) < per_round ? (n - j0) : per_round);
-      if (lane < cnt) idx = __ldg(perm + off + lo + j0 + lane);
-    }
+    if (lane < cnt) idx = __ldg(perm + off + lo + j0 + lane);
     while (cnt > 0) {
       const int cur_cnt = cnt;
       const int32_t cur_idx = idx;
-      const uint64_t cur_q0 = q0;
-      // advance the iterator and prefetch the next round's indices
-      j0 += cur_cnt;
-      q0 += (uint64_t)cur_cnt;
-      if (j0 >= n) {
-        j0 = 0;
-        do { enter_step(++s); } while (s < p.nb && n == 0);
+      const uint32_t cur_tq = tq;
+      // move to my next round and get its indices in flight
+      for (int k = 0; k < NP; ++k) advance();
+      cnt = round_cnt();
+      if (lane < cnt) idx = __ldg(perm + off + lo + j0 + lane);
+      // issue the current round: wait for the tile, arm its barrier, one TMA bulk copy per row
+      const uint32_t tile = cur_tq & tile_mask;
+      const uint32_t use = cur_tq >> p.tile_log2;
+      const uint32_t fb = full0 + 8u * tile;
+      if (lane == 0) {
+        mbar_wait_relaxed(empty0 + 8u * tile, (use & 1u) ^ 1u);  // passes at once on the first use
+        mbar_arrive_expect_tx(fb, (uint32_t)cur_cnt * p.slot_bytes);
       }
-      cnt = 0;
-      if (s < p.nb) {
-        cnt = (int)((n - j0) < per_round ? (n - j0) : per_round);
-        if (lane < cnt) idx = __ldg(perm + off + lo + j0 + lane);
-      }
-      // issue the current round: one TMA bulk copy per row
-      if (lane < cur_cnt) {
-        const uint64_t q = cur_q0 + (uint64_t)lane;
-        const uint32_t slot = (uint32_t)q & slot_mask;
-        const uint32_t use = (uint32_t)(q >> p.slot_log2);
-        mbar_wait_relaxed(empty0 + 8u * slot, (use & 1u) ^ 1u);  // passes at once on the first use
-        const uint32_t fb = full0 + 8u * slot;
-        mbar_arrive_expect_tx(fb, p.slot_bytes);
-        bulk_g2s(ring0 + slot * p.slot_bytes, p.rec + (int64_t)cur_idx * p.ld, p.slot_bytes, fb);
-      }
+      __syncwarp();
+      if (lane < cur_cnt)
+        bulk_g2s(ring0 + tile * tile_bytes + (uint32_t)lane * p.slot_bytes, p.rec + (int64_t)cur_idx * p.ld,
+                 p.slot_bytes, fb);
       __syncwarp();
     }
     return;
   }
 
   // ======================================= CONSUMERS =======================================
-  const int ctid = tid - 32;  // consumer threads: hardware warps 1..NW
-  const int cw = warp - 1;    // consumer warp index 0..NW-1
+  const int ctid = tid - 32 * NP;  // consumer threads: hardware warps NP..NP+NW-1
+  const int cw = warp - NP;        // consumer warp index 0..NW-1
   const float Bf = (float)p.B;
   const float a = a_step;
   const int C4 = p.C4;
   unsigned int bar_count = 0;  // grid barriers passed so far
-  uint64_t qbase = 0;          // sequence number of the first row of the current step
+  uint32_t tqbase = 0;         // sequence number of the first round of the current step
   float4 g[KC];
 
   // w = a * (g / B) + w for one float4 column group (sgd_thrust.cu:269, main.cu:147-150 / :287-290)
@@ -528,12 +564,10 @@ __global__ void __launch_bounds__(32 * (NW + 1), 1) sgd_epoch_kernel(const Epoch
     while (Q < qmax && Q < gcap && (int64_t)(ncol > 0 ? ncol : 1) * (Q * 2) <= kCT) Q <<= 1;
   }
   const int cols_per_pass = kCT / Q;
+  const int Gp = (G + 3) & ~3;     // strides of the tagged-word arrays, padded to 128-byte lines
+  const int C4p = (C4 + 3) & ~3;
   const int my_col = ctid / Q;  // column (within a pass) and lane (within the column) of this thread
   const int my_q = ctid % Q;
-
-  // uniform batches (single GPU): the CTA's slice of a batch is the same every step
-  const int64_t lo_uni = slice_lo(p.B, cta, G);
-  const int64_t n_uni = slice_lo(p.B, cta + 1, G) - lo_uni;
 
   // optional phase profile: consumer thread 0 of every CTA sums the cycles between these marks
   unsigned long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -563,34 +597,38 @@ __global__ void __launch_bounds__(32 * (NW + 1), 1) sgd_epoch_kernel(const Epoch
 #pragma unroll
     for (int k = 0; k < KC; ++k) g[k] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-    // ---- rows of this step: warp `warp` takes rows warp, warp+NW, ... ; U at a time ----
-    for (int64_t j = cw; j < n; j += (int64_t)NW * U) {
+    // ---- rows of this step, one ring tile (= producer round) at a time: consumer warp cw
+    // takes rows cw, cw+NW, ... of the tile, all U of them concurrently ----
+    const int nt = (int)((n + TR - 1) / TR);
+    for (int ti = 0; ti < nt; ++ti) {
+      const uint32_t tq = tqbase + (uint32_t)ti;
+      const uint32_t tile = tq & tile_mask;
+      const uint32_t use = tq >> p.tile_log2;
+      const int cnt = (int)((n - (int64_t)ti * TR) < TR ? (n - (int64_t)ti * TR) : TR);
+      const unsigned char* tbase = ring + (size_t)tile * tile_bytes;
       float4 x[U][KC];
       float dot[U], y[U];
+      mbar_wait(full0 + 8u * tile, use & 1u);  // all rows of the tile have landed
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const int64_t ju = j + (int64_t)u * NW;
+        const int r = cw + u * NW;
         dot[u] = 0.f;
         y[u] = 0.f;
-        if (ju < n) {  // warp-uniform
-          const uint64_t q = qbase + (uint64_t)ju;
-          const uint32_t slot = (uint32_t)q & slot_mask;
-          const uint32_t use = (uint32_t)(q >> p.slot_log2);
-          mbar_wait(full0 + 8u * slot, use & 1u);
-          const float4* row = reinterpret_cast<const float4*>(ring + (size_t)slot * p.slot_bytes);
+        if (r < cnt) {  // warp-uniform
+          const float4* row = reinterpret_cast<const float4*>(tbase + (size_t)r * p.slot_bytes);
 #pragma unroll
           for (int k = 0; k < KC; ++k) {
             const int f = k * 32 + lane;
             x[u][k] = (f < C4) ? row[f] : make_float4(0.f, 0.f, 0.f, 0.f);
           }
           y[u] = reinterpret_cast<const float*>(row)[p.C];  // label rides in the record
-          __syncwarp();
-          if (lane == 0) mbar_arrive(empty0 + 8u * slot);  // row is in registers: free the slot
         } else {
 #pragma unroll
           for (int k = 0; k < KC; ++k) x[u][k] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty0 + 8u * tile);  // my rows are in registers
 #pragma unroll
       for (int k = 0; k < KC; ++k) {
         const float4 wv = w_s[k * 32 + lane];
@@ -610,7 +648,7 @@ __global__ void __launch_bounds__(32 * (NW + 1), 1) sgd_epoch_kernel(const Epoch
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         // r = x.w - y   (sgd_thrust.cu:43-48; Sgemv with beta = -1, sgd_thrust.cu:352-364);
-        // rows beyond the slice have x = 0, y = 0 -> r = 0 and contribute nothing
+        // rows beyond the tile have x = 0, y = 0 -> r = 0 and contribute nothing
         const float r = dot[u] - y[u];
 #pragma unroll
         for (int k = 0; k < KC; ++k) {
@@ -620,12 +658,12 @@ __global__ void __launch_bounds__(32 * (NW + 1), 1) sgd_epoch_kernel(const Epoch
           g[k].w = fmaf(r, x[u][k].w, g[k].w);
         }
         if (p.r_out != nullptr && lane == 0) {
-          const int64_t ju = j + (int64_t)u * NW;
-          if (ju < n) p.r_out[off + lo + ju] = r;
+          const int rr = cw + u * NW;
+          if (rr < cnt) p.r_out[off + lo + (int64_t)ti * TR + rr] = r;
         }
       }
     }
-    qbase += (uint64_t)n;
+    tqbase += (uint32_t)nt;
     mark(0);  // rows of this step done (this warp)
 
     // ---- CTA partial: fixed-order sum over the warps ----
@@ -641,13 +679,27 @@ __global__ void __launch_bounds__(32 * (NW + 1), 1) sgd_epoch_kernel(const Epoch
       for (int wq = 1; wq < NW; ++wq) acc = f4_add(acc, gred[(wq * KC + k) * 32 + l]);
       return acc;
     };
+    if (G == 1 && p.nranks == 1) {
+      // single CTA (tiny batches): the CTA partial is the gradient; nothing leaves the SM
+      for (int f = ctid; f < C4; f += kCT) {
+        float4 gs;
+        w_s[f] = updated(f, w_s[f], cta_partial(f), &gs);
+        reinterpret_cast<float4*>(p.g_last)[f] = gs;
+      }
+      consumer_bar<kCT>();
+      continue;
+    }
     if (p.reduce_mode >= 3) {
       // ================= DATAFLOW: no barrier, no atomics, tagged words =================
       const uint32_t tag = tag_base + (uint32_t)s + 1u;
-      // every CTA publishes its partial gradient (double-buffered by step parity)
-      uint4* my_part = p.ll_part + ((int64_t)par * G + cta) * C4 * 2;
-      for (int f = ctid; f < C4; f += kCT) ll_store_f4(my_part + (int64_t)f * 2, cta_partial(f), tag);
-      const uint4* parts = p.ll_part + (int64_t)par * G * C4 * 2;
+      // every CTA publishes its partial gradient (double-buffered by step parity).  Layout
+      // [parity][column][cta]: the G words a column owner gathers are contiguous, so its polling
+      // loads coalesce into whole lines spread evenly over the L2 slices (with the CTA-major layout
+      // some columns' words all hashed to the same slice and those owners ran ~2x late).
+      // Column blocks and mailboxes are padded to whole 128-byte lines (Gp, C4p): two owners never
+      // poll the same line (grids like 41 or 48 ran 1.5x slower than 32 or 64 without it).
+      uint4* parts = p.ll_part + (int64_t)par * Gp * C4 * 2;
+      for (int f = ctid; f < C4; f += kCT) ll_store_f4(parts + ((int64_t)f * Gp + cta) * 2, cta_partial(f), tag);
       mark(2);  // partial published
 
       if (p.reduce_mode == 4) {
@@ -656,7 +708,7 @@ __global__ void __launch_bounds__(32 * (NW + 1), 1) sgd_epoch_kernel(const Epoch
         for (int base = 0; base < C4; base += cols_per_pass) {
           const int fi = base + my_col;
           const bool active = fi < C4;
-          const float4 tot = ll_gather<kCT>(parts, C4, active ? fi : 0, G, my_q, Q, active, tag, p.err, xred, ctid);
+          const float4 tot = ll_gather<kCT>(parts, 1, Gp, active ? fi : 0, G, my_q, Q, active, tag, p.err, xred, ctid);
           if (active && my_q == 0) {
             float4 gs;
             w_s[fi] = updated(fi, w_s[fi], tot, &gs);
@@ -680,15 +732,16 @@ __global__ void __launch_bounds__(32 * (NW + 1), 1) sgd_epoch_kernel(const Epoch
         // old weights are read before anything of this step is published (the mailbox poll below
         // overwrites w_s once the new ones arrive)
         const float4 w_old = active ? w_s[f] : make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 tot = ll_gather<kCT>(parts, C4, f, G, my_q, Q, active, tag, p.err, xred, ctid);
+        float4 tot = ll_gather<kCT>(parts, 1, Gp, f, G, my_q, Q, active, tag, p.err, xred, ctid);
+        mark(3);  // (owners) partials gathered
         if (p.nranks > 1) {  // uniform over the grid
-          const int64_t slot = ((int64_t)par * p.nranks) * C4;
+          const int64_t slot = ((int64_t)par * p.nranks) * C4p;
           if (active) {  // lane q writes the inboxes of ranks q, q+Q, ...: NVLink stores in parallel
             for (int pr = my_q; pr < p.nranks; pr += Q)
-              ll_store_f4(p.ll_inbox_peer[pr] + (slot + (int64_t)p.rank * C4 + f) * 2, tot, tag);
+              ll_store_f4(p.ll_inbox_peer[pr] + (slot + (int64_t)p.rank * C4p + f) * 2, tot, tag);
           }
           // the ranks' slices are gathered like the partials: lane q polls rank q, fixed tree
-          tot = ll_gather<kCT>(p.ll_inbox_local + slot * 2, C4, f, p.nranks, my_q, Q, active, tag, p.err, xred, ctid);
+          tot = ll_gather<kCT>(p.ll_inbox_local + slot * 2, C4p, 1, f, p.nranks, my_q, Q, active, tag, p.err, xred, ctid);
         }
         // every lane of the group holds `tot`: lane q publishes the new weights into the
         // mailboxes of CTAs q, q+Q, ... (private copies keep 148 pollers off one line)
@@ -696,12 +749,12 @@ __global__ void __launch_bounds__(32 * (NW + 1), 1) sgd_epoch_kernel(const Epoch
           float4 gs;
           const float4 wv = updated(f, w_old, tot, &gs);
           for (int dst = my_q; dst < p.w_copies; dst += Q)
-            ll_store_f4(p.ll_w + ((int64_t)dst * C4 + f) * 2, wv, tag);
+            ll_store_f4(p.ll_w + ((int64_t)dst * C4p + f) * 2, wv, tag);
           if (my_q == 0) reinterpret_cast<float4*>(p.g_last)[f] = gs;
         }
       }
       mark(4);  // owner work (gather, exchange, publish) done
-      const uint4* my_w = p.ll_w + (p.w_copies > 1 ? (int64_t)cta * C4 * 2 : 0);
+      const uint4* my_w = p.ll_w + (p.w_copies > 1 ? (int64_t)cta * C4p * 2 : 0);
       for (int f = ctid; f < C4; f += kCT) w_s[f] = ll_wait_f4(my_w + (int64_t)f * 2, tag, p.err);
       mark(5);  // new weights arrived
       consumer_bar<kCT>();

@@ -1,0 +1,194 @@
+// shuffle_kernels.cuh -- the reference's per-epoch permutation, bit-exact, on the device.
+//
+// The reference shuffles its index vector on the HOST with std::random_shuffle driven by glibc
+// rand() (main.cu:90, :207): for i = 1..n-1: j = rand() % (i+1); if (i != j) swap(v[i], v[j]).
+// That loop is sequential and is the true epoch bottleneck at scale (23 ms at
+// 4M rows on this box's host vs a few ms of step loop).  The SAME permutation is produced here in
+// parallel.  Only the random stream is still drawn on the host (a linear recurrence, ~1 ns per
+// value, see host_rng.hpp) and uploaded; everything else is five small kernels:
+//
+//   Look at the values instead of the loop.  Position i is untouched until step i, so the value
+//   in[i] sits at i until time i, when it moves to j_i (and whatever was at j_i moves to i).  A
+//   value sitting at position p is thrown out the next time p is some later step's target ("hit"):
+//   a hit of p at step h moves it to position h, where it again waits for the first hit of h ...
+//   So with   hits(p) = { i > p : j_i = p }   sorted ascending, the trajectory of in[i] is
+//       i --(time i)--> j_i --(successor of i in hits(j_i))--> h --> first(hits(h)) --> ...
+//   until a position without a later hit is reached: its final place.  (A self swap j_i = i is a
+//   no-op, exactly as the `if (i != j)` of libstdc++.)  Chains are short: first(hits(p)) is about
+//   2p in expectation.
+//
+//   K1 targets : j_i from the raw stream, count hits per position
+//   K2 scan    : exclusive prefix sum of the counts  -> CSR offsets
+//   K3 fill    : scatter i into its target's list (atomic cursor, arbitrary order)
+//   K4 order   : sort every (tiny) list ascending, record first(hits(p))
+//   K5 resolve : one thread per value follows its trajectory and writes out[final] = in[i]
+//
+// tests/test_gpu_shuffle.py checks it against the host loop and the golden vectors of
+// tests/golden/thirdparty_kat.json (real glibc + libstdc++ outputs).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200sgd {
+
+// tgt holds the raw 32-bit stream values on entry (raw[i-1] for step i, i >= 1; slot 0 unused)
+// and the swap targets j_i on exit.  cnt must be zero on entry.
+__global__ void __launch_bounds__(256) shuf_targets_kernel(uint32_t* __restrict__ tgt, int64_t n,
+                                                           int32_t* __restrict__ cnt) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t j = 0;
+    if (i >= 1) {
+      j = (tgt[i] >> 1) % (uint32_t)(i + 1);  // rand() % ((i - first) + 1), stl_algo.h
+      if ((int64_t)j != i) atomicAdd(cnt + j, 1);
+    }
+    tgt[i] = j;
+  }
+}
+
+constexpr int kScanBlock = 1024;
+constexpr int kScanPerThread = 4;
+constexpr int kScanTile = kScanBlock * kScanPerThread;
+
+__device__ __forceinline__ int32_t block_exclusive_scan(int32_t v, int32_t* warp_tot, int32_t* total) {
+  // exclusive scan of one value per thread over a 1024-thread block
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int32_t incl = v;
+#pragma unroll
+  for (int m = 1; m < 32; m <<= 1) {
+    const int32_t t = __shfl_up_sync(0xffffffffu, incl, m);
+    if (lane >= m) incl += t;
+  }
+  if (lane == 31) warp_tot[w] = incl;
+  __syncthreads();
+  if (w == 0) {
+    int32_t t = warp_tot[lane];
+    int32_t ti = t;
+#pragma unroll
+    for (int m = 1; m < 32; m <<= 1) {
+      const int32_t u = __shfl_up_sync(0xffffffffu, ti, m);
+      if (lane >= m) ti += u;
+    }
+    warp_tot[lane] = ti - t;  // exclusive over warps
+    if (lane == 31) *total = ti;
+  }
+  __syncthreads();
+  const int32_t r = warp_tot[w] + incl - v;
+  __syncthreads();
+  return r;
+}
+
+// phase 1: per-tile totals
+__global__ void __launch_bounds__(kScanBlock) scan_tile_sums_kernel(const int32_t* __restrict__ in, int64_t n,
+                                                                    int32_t* __restrict__ tile_sum) {
+  __shared__ int32_t warp_tot[32];
+  __shared__ int32_t total;
+  const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanPerThread;
+  int32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < kScanPerThread; ++k)
+    if (base + k < n) s += in[base + k];
+  block_exclusive_scan(s, warp_tot, &total);
+  if (threadIdx.x == 0) tile_sum[blockIdx.x] = total;
+}
+
+// phase 2: exclusive scan of the tile totals (single block, loops); also writes the grand total
+__global__ void __launch_bounds__(kScanBlock) scan_tile_offsets_kernel(int32_t* __restrict__ tile_sum, int32_t ntiles,
+                                                                       int32_t* __restrict__ grand_total) {
+  __shared__ int32_t warp_tot[32];
+  __shared__ int32_t total;
+  int32_t carry = 0;
+  for (int base = 0; base < ntiles; base += kScanBlock) {
+    const int i = base + threadIdx.x;
+    const int32_t v = i < ntiles ? tile_sum[i] : 0;
+    const int32_t ex = block_exclusive_scan(v, warp_tot, &total);
+    if (i < ntiles) tile_sum[i] = carry + ex;
+    carry += total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *grand_total = carry;
+}
+
+// phase 3: exclusive scan inside every tile plus the tile offset; out has n+1 entries
+__global__ void __launch_bounds__(kScanBlock) scan_apply_kernel(const int32_t* __restrict__ in, int64_t n,
+                                                                const int32_t* __restrict__ tile_off,
+                                                                const int32_t* __restrict__ grand_total,
+                                                                int32_t* __restrict__ out) {
+  __shared__ int32_t warp_tot[32];
+  __shared__ int32_t total;
+  const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanPerThread;
+  int32_t v[kScanPerThread];
+  int32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < kScanPerThread; ++k) {
+    v[k] = (base + k < n) ? in[base + k] : 0;
+    s += v[k];
+  }
+  int32_t ex = block_exclusive_scan(s, warp_tot, &total) + tile_off[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < kScanPerThread; ++k) {
+    if (base + k < n) out[base + k] = ex;
+    ex += v[k];
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = *grand_total;
+}
+
+// cursor must be zero on entry
+__global__ void __launch_bounds__(256) shuf_fill_kernel(const uint32_t* __restrict__ tgt, int64_t n,
+                                                        const int32_t* __restrict__ start,
+                                                        int32_t* __restrict__ cursor, int32_t* __restrict__ hits) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x + 1; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t j = tgt[i];
+    if ((int64_t)j != i) hits[start[j] + atomicAdd(cursor + j, 1)] = (int32_t)i;
+  }
+}
+
+__global__ void __launch_bounds__(256) shuf_order_kernel(int64_t n, const int32_t* __restrict__ start,
+                                                         int32_t* __restrict__ hits, int32_t* __restrict__ first) {
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n;
+       p += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t lo = start[p], hi = start[p + 1];
+    for (int32_t a = lo + 1; a < hi; ++a) {  // insertion sort: lists have ~1 entry on average
+      const int32_t key = hits[a];
+      int32_t b = a - 1;
+      while (b >= lo && hits[b] > key) {
+        hits[b + 1] = hits[b];
+        --b;
+      }
+      hits[b + 1] = key;
+    }
+    first[p] = hi > lo ? hits[lo] : -1;
+  }
+}
+
+__global__ void __launch_bounds__(256) shuf_resolve_kernel(const uint32_t* __restrict__ tgt, int64_t n,
+                                                           const int32_t* __restrict__ start,
+                                                           const int32_t* __restrict__ hits,
+                                                           const int32_t* __restrict__ first,
+                                                           const int32_t* __restrict__ in, int32_t* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int32_t pos = (int32_t)i;
+    bool settled = false;
+    const uint32_t j = tgt[i];
+    if (i >= 1 && (int64_t)j != i) {
+      // moved to j at time i; thrown out again by the next hit of j after time i, if any
+      const int32_t lo = start[j], hi = start[j + 1];
+      int32_t nxt = -1;
+      for (int32_t a = lo; a < hi; ++a) {
+        const int32_t h = hits[a];
+        if (h > (int32_t)i) { nxt = h; break; }
+      }
+      if (nxt < 0) { pos = (int32_t)j; settled = true; }
+      else pos = nxt;
+    }
+    if (!settled) {
+      int32_t nx;
+      while ((nx = first[pos]) >= 0) pos = nx;
+    }
+    out[pos] = in[i];
+  }
+}
+
+}  // namespace b200sgd

@@ -1,0 +1,71 @@
+"""The device permutation (csrc/shuffle_kernels.cuh) must equal the reference's host loop
+(std::random_shuffle + glibc rand(), main.cu:90 / :207) bit for bit, cumulatively over epochs."""
+import numpy as np
+import pytest
+
+import cuda_sgd_sese_project_b200 as pkg
+from cuda_sgd_sese_project_b200 import _lib
+from oracle import loader as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _checksum(ind):
+    i = np.arange(1, ind.shape[0] + 1, dtype=np.uint64)
+    return int((i * ind.astype(np.uint64)).sum(dtype=np.uint64))
+
+
+@pytest.mark.parametrize("R", [32768, 32769, 40000, 65536, 100003, 1 << 20])
+def test_device_shuffle_equals_oracle_over_epochs(R):
+    g = orc.Rand()
+    ind = np.arange(R, dtype=np.int32)
+    with pkg.SGDEngine(R, 3, 1000, 0.1) as eng:
+        eng.load_synthetic(seed=1)
+        for epoch in range(3):
+            g.shuffle(ind)                  # cumulative, never reset (main.cu:421-424)
+            eng.shuffle()
+            got = eng.permutation()
+            assert np.array_equal(got, ind), f"epoch {epoch + 1}: first mismatch at {np.nonzero(got != ind)[0][:5]}"
+
+
+def test_device_and_host_paths_agree_and_interleave():
+    R = 50000
+    with pkg.SGDEngine(R, 2, 500, 0.1) as dev, pkg.SGDEngine(R, 2, 500, 0.1, ) as dev2:
+        dev.load_synthetic(seed=1)
+        dev2.load_synthetic(seed=1)
+        # same engine type twice must give identical streams
+        for _ in range(2):
+            dev.shuffle(); dev2.shuffle()
+            assert np.array_equal(dev.permutation(), dev2.permutation())
+    ref = np.arange(R, dtype=np.int32)
+    pkg.host_shuffle(ref, epochs=2)
+    with pkg.SGDEngine(R, 2, 500, 0.1) as dev:
+        dev.load_synthetic(seed=1)
+        dev.shuffle(); dev.shuffle()
+        assert np.array_equal(dev.permutation(), ref)
+
+
+@pytest.mark.parametrize("R", [4000000, 16777216])
+def test_device_shuffle_golden_kat(kat, R):
+    # golden values from the REAL glibc / libstdc++ (tests/golden/thirdparty_kat.json)
+    recs = [r for r in kat["shuffle_kat"] if r["R"] == R]
+    with pkg.SGDEngine(R, 1, 1000, 0.1) as eng:
+        eng.load_synthetic(seed=1)
+        for rec in recs:
+            eng.shuffle()
+            p = eng.permutation()
+            assert p[:4].tolist() == rec["head"] and int(p[-1]) == rec["last"]
+            assert _checksum(p) == rec["checksum"]
+
+
+def test_set_permutation_then_device_shuffle_continues_from_it():
+    R = 40000
+    start = np.arange(R, dtype=np.int32)[::-1].copy()
+    g = orc.Rand()
+    want = start.copy()
+    g.shuffle(want)
+    with pkg.SGDEngine(R, 2, 500, 0.1) as eng:
+        eng.load_synthetic(seed=1)
+        eng.set_permutation(start)
+        eng.shuffle()
+        assert np.array_equal(eng.permutation(), want)

@@ -173,6 +173,32 @@ __global__ void fan2_kernel(uint4* part, uint4* mbox, int owners, int sentinel, 
   if (cta == 0 && t == 0) *cycles = clock64() - t0;
 }
 
+// push all-gather: ONE hop.  Every CTA pushes `words` tagged 16-byte words to the private inbox of
+// every CTA (inbox[dst][src][w]); every CTA then polls its own inbox (G*words words).
+__global__ void push_kernel(uint4* inbox, int words, int iters, long long* cycles) {
+  const int G = gridDim.x, cta = blockIdx.x, t = threadIdx.x, T = blockDim.x;
+  long long t0 = clock64();
+  const int total = G * words;
+  for (int it = 1; it <= iters; ++it) {
+    const unsigned tag = (unsigned)it;
+    uint4* buf = inbox + (size_t)(it & 1) * 64 * 64 * 64;  // double-buffered: nobody is 2 iterations ahead
+    for (int i = t; i < total; i += T) {  // i = dst * words + w
+      const int dst = i / words, w = i - dst * words;
+      st_u4(buf + ((size_t)dst * G + cta) * words + w, make_uint4(cta, tag, w, tag));
+    }
+    unsigned acc = 0;
+    for (int i = t; i < total; i += T) {  // i = src * words + w
+      uint4 v;
+      const uint4* src = buf + (size_t)cta * G * words + i;
+      do { v = ld_u4(src); } while (v.y != tag || v.w != tag);
+      acc += v.x;
+    }
+    if (acc == 0xffffffffu) cycles[1] = acc;
+    __syncthreads();
+  }
+  if (cta == 0 && t == 0) *cycles = clock64() - t0;
+}
+
 // ---- dependent-load latency and load overlap: one thread, lines written long ago by another SM
 template <int MODE>  // 0: ld.volatile  1: ld.global.cg (weak)  2: ld.relaxed.gpu
 __device__ __forceinline__ uint4 ld_mode(const uint4* p) {
@@ -229,7 +255,7 @@ int main() {
   unsigned* flags;
   long long* cyc;
   CK(cudaMalloc(&flags, 1 << 20));
-  CK(cudaMallocManaged(&cyc, sizeof(long long)));
+  CK(cudaMallocManaged(&cyc, 2 * sizeof(long long)));
   const int iters = 20000;
 
   auto coop = [&](const void* fn, int grid, int block, void** args) {
@@ -264,6 +290,21 @@ int main() {
         coop((const void*)fan_kernel, G, 32, args);
         std::printf("{\"test\": \"fan\", \"G\": %d, \"private_mailboxes\": %d, \"poll_sleep_ns\": %d, \"cycles_per_iter\": %.1f}\n", G, priv,
                     sleep_ns, (double)*cyc / iters);
+      }
+    }
+  }
+  // push all-gather (one hop)
+  {
+    uint4* ib;
+    CK(cudaMalloc(&ib, (size_t)2 * 64 * 64 * 64 * 16));
+    for (int G : {2, 8, 16, 32, 48, 64}) {
+      for (int words : {1, 50}) {
+        CK(cudaMemset(ib, 0, (size_t)2 * 64 * 64 * 64 * 16));
+        int it = 5000;
+        void* args[] = {&ib, &words, &it, &cyc};
+        coop((const void*)push_kernel, G, 512, args);
+        std::printf("{\"test\": \"push_allgather\", \"G\": %d, \"words16B_per_cta\": %d, \"cycles_per_iter\": %.1f}\n", G, words,
+                    (double)*cyc / it);
       }
     }
   }

@@ -42,8 +42,14 @@ def run(R, C, B, lr=0.01, epochs=3, warm=1, shuffle=True, **kw):
         phases = None
         if os.environ.get("B200SGD_PHASE_PROFILE") == "1":
             d = eng.debug_phase_cycles().astype(np.float64) / max(1, best["steps"])
-            names = ["rows", "cta_reduce", "publish", "gather1hop", "owner", "wait_w", "bar2", "-"]
+            names = ["rows", "cta_reduce", "publish", "gather", "owner_publish", "wait_w", "bar2", "-"]
+            own = d[:, 3] > 50   # CTAs that own columns (2-hop) / all CTAs (1-hop)
             phases = {n: [round(float(d[:, i].mean())), round(float(d[:, i].max()))] for i, n in enumerate(names) if d[:, i].any()}
+            if own.any():
+                phases["owners_only"] = {n: round(float(d[own, i].mean())) for i, n in enumerate(names) if d[:, i].any()}
+                phases["n_owners"] = int(own.sum())
+                phases["per_owner_gather"] = {int(i): round(float(d[i, 3])) for i in np.nonzero(own)[0]}
+                phases["per_owner_wait_w"] = {int(i): round(float(d[i, 5])) for i in np.nonzero(own)[0]}
         out = {"R": R, "C": C, "B": B, "grid": eng.grid, "reduce": eng.reduce, "engine": eng.engine,
                "kernel": eng.kernel_shape, "slots": eng.nslots, "steps": best["steps"],
                "ms_per_epoch": round(best["steploop_ms"], 4),
