@@ -542,6 +542,38 @@ int sgd_host_shuffle(int32_t* ind, int64_t rows, uint32_t seed, int32_t skip_epo
   return SGD_OK;
 }
 
+int sgd_shard_range(int64_t rows, int32_t rank, int32_t nranks, int64_t* begin, int64_t* end) {
+  if (rows <= 0 || nranks < 1 || rank < 0 || rank >= nranks) return fail(SGD_ERR_ARG, "bad shard arguments");
+  const int64_t per = (rows + nranks - 1) / nranks;
+  const int64_t b = std::min<int64_t>(rows, per * rank);
+  if (begin) *begin = b;
+  if (end) *end = std::min<int64_t>(rows, b + per);
+  return SGD_OK;
+}
+
+int sgd_host_bucket(const int32_t* perm, int64_t rows, int32_t batch_arg, int32_t rank, int32_t nranks,
+                    int32_t* local_perm, int64_t local_cap, int64_t* step_off) {
+  if (!perm || !local_perm || !step_off) return fail(SGD_ERR_ARG, "null argument");
+  int64_t rb = 0, re = 0;
+  SGD_TRY(sgd_shard_range(rows, rank, nranks, &rb, &re));
+  int32_t B, nb;
+  batch_geometry(rows, batch_arg, &B, &nb);
+  int64_t n = 0;
+  for (int32_t s = 0; s < nb; ++s) {
+    step_off[s] = n;
+    const int32_t* p = perm + (int64_t)s * B;
+    for (int32_t i = 0; i < B; ++i) {
+      const int64_t r = p[i];
+      if (r >= rb && r < re) {
+        if (n >= local_cap) return fail(SGD_ERR_ARG, "local_perm too small");
+        local_perm[n++] = (int32_t)(r - rb);
+      }
+    }
+  }
+  step_off[nb] = n;
+  return SGD_OK;
+}
+
 int sgd_create(const sgd_config* cfg, const float* X, const float* y, sgd_ctx** out) {
   if (!cfg || !out) return fail(SGD_ERR_ARG, "sgd_create: null argument");
   *out = nullptr;
@@ -1038,6 +1070,19 @@ int sgd_mean_abs_error(sgd_ctx* c, float* mae_out, double* sum_out) {
   if (sum_out) *sum_out = total;
   // sgd_thrust.cu:134: return error_sum / R
   if (mae_out) *mae_out = (float)(total / (double)(c->cfg.nranks > 1 ? std::max<int64_t>(1, c->local_rows) : c->R));
+  return SGD_OK;
+}
+
+int sgd_get_local_schedule(sgd_ctx* c, int32_t* local_perm, int64_t local_cap, int64_t* step_off) {
+  SGD_TRY(check_ctx(c));
+  if (!local_perm || !step_off) return fail(SGD_ERR_ARG, "null output");
+  if (c->cfg.nranks < 2) return fail(SGD_ERR_STATE, "single-rank contexts have no bucketed schedule");
+  SGD_TRY(bind(c));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(cudaMemcpy(step_off, c->d_step_off, sizeof(int64_t) * ((size_t)c->nb + 1), cudaMemcpyDeviceToHost));
+  const int64_t n = step_off[c->nb];
+  if (n > local_cap) return fail(SGD_ERR_ARG, "local_perm too small");
+  CUDA_TRY(cudaMemcpy(local_perm, c->d_perm_local, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost));
   return SGD_OK;
 }
 

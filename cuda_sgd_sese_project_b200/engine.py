@@ -77,6 +77,25 @@ def host_shuffle(ind: np.ndarray, seed: int = 1, skip_epochs: int = 0, epochs: i
     return ind
 
 
+def shard_range(R: int, rank: int, nranks: int):
+    """Rows [begin, end) owned by `rank` of `nranks`."""
+    b, e = C.c_int64(), C.c_int64()
+    L.check(L.load().sgd_shard_range(R, rank, nranks, C.byref(b), C.byref(e)))
+    return b.value, e.value
+
+
+def host_bucket(perm: np.ndarray, batch_arg: int, rank: int, nranks: int):
+    """Host statement of the per-epoch bucketing: (local_perm, step_off) of `rank`."""
+    perm = np.ascontiguousarray(perm, dtype=np.int32)
+    R = perm.shape[0]
+    _, nb = batch_geometry(R, batch_arg)
+    b, e = shard_range(R, rank, nranks)
+    local = np.empty(max(1, e - b), dtype=np.int32)
+    off = np.empty(nb + 1, dtype=np.int64)
+    L.check(L.load().sgd_host_bucket(_ptr(perm), R, batch_arg, rank, nranks, _ptr(local), local.shape[0], _ptr(off)))
+    return local[: off[nb]].copy(), off
+
+
 def device_count() -> int:
     return int(L.load().sgd_device_count())
 
@@ -235,6 +254,13 @@ class SGDEngine:
         s = C.c_double()
         L.check(L.load().sgd_mean_abs_error(self._h, None, C.byref(s)))
         return float(s.value)
+
+    def local_schedule(self):
+        """nranks > 1: (local_perm, step_off) of the last executed epoch as built on the device."""
+        local = np.empty(max(1, self.local_rows), dtype=np.int32)
+        off = np.empty(self.num_batches + 1, dtype=np.int64)
+        L.check(L.load().sgd_get_local_schedule(self._h, _ptr(local), local.shape[0], _ptr(off)))
+        return local[: off[self.num_batches]].copy(), off
 
     def debug_phase_cycles(self) -> np.ndarray:
         """[grid, 8] cycle sums per phase of the last launch (needs B200SGD_PHASE_PROFILE=1)."""

@@ -120,6 +120,15 @@ int sgd_batch_geometry(int64_t rows, int32_t batch_arg, int32_t* batch_out, int3
 int sgd_host_shuffle(int32_t* ind, int64_t rows, uint32_t seed, int32_t skip_epochs,
                      int32_t epochs);
 
+/* ---- row sharding of the data-parallel path (new functionality, BASELINE.json north_star) ------
+ * rank k owns rows [k*ceil(R/N), min(R, (k+1)*ceil(R/N))). */
+int sgd_shard_range(int64_t rows, int32_t rank, int32_t nranks, int64_t* begin, int64_t* end);
+/* host statement of the per-epoch bucketing the device does (sgd_bucket_* kernels): from the GLOBAL
+ * permutation keep, per step, the rows `rank` owns, batch order preserved, as local row numbers;
+ * step_off gets steps+1 offsets into local_perm. */
+int sgd_host_bucket(const int32_t* perm, int64_t rows, int32_t batch_arg, int32_t rank, int32_t nranks,
+                    int32_t* local_perm, int64_t local_cap, int64_t* step_off);
+
 /* ---- context: replaces the set-up half of main() (main.cu:381-433) --------------------------
  * Allocates device storage for this rank's row shard [rank*ceil(R/nranks), ...), initialises the
  * weights (main.cu:389-395) and the identity index vector (main.cu:421-424).  X/y may be NULL
@@ -172,6 +181,9 @@ int sgd_get_last_gradient(sgd_ctx* ctx, float* g);
  * With nranks > 1 it returns this rank's SUM of absolute errors in *sum_out (the caller adds the
  * ranks and divides by R); mae_out is sum/R_local... for nranks == 1 it is the reference's value */
 int sgd_mean_abs_error(sgd_ctx* ctx, float* mae_out, double* sum_out);
+
+/* nranks > 1: the bucketed schedule of the last executed epoch, as the device built it */
+int sgd_get_local_schedule(sgd_ctx* ctx, int32_t* local_perm, int64_t local_cap, int64_t* step_off);
 
 /* diagnostics: when the context was created with B200SGD_PHASE_PROFILE=1 in the environment, the
  * epoch kernel sums, per CTA, the SM cycles of the phases of a step (rows | CTA reduce | publish
