@@ -139,6 +139,10 @@ struct sgd_ctx {
   // device shuffle (shuffle_kernels.cuh): raw stream / targets, hit lists in CSR form
   bool device_shuffle = false;
   uint32_t* d_tgt = nullptr;
+  uint32_t* d_states = nullptr;            // per-chunk start states of the rand() stream
+  uint32_t* h_states[2] = {nullptr, nullptr};
+  int64_t chunk_len = 0, nchunks = 0;
+  b200sgd::GlibcRand::Poly jump_chunk{};
   int32_t *d_cnt = nullptr, *d_start = nullptr, *d_hits = nullptr, *d_first = nullptr, *d_tilesum = nullptr;
   int32_t scan_tiles = 0;
   bool host_ind_stale = false;  // h_ind lags behind the device permutation
@@ -199,7 +203,9 @@ void free_all(sgd_ctx* c) {
   cudaFree(c->d_glast); cudaFree(c->d_rout); cudaFree(c->d_bar); cudaFree(c->d_ctl);
   cudaFree(c->d_ll_part); cudaFree(c->d_ll_w); cudaFree(c->d_dbg);
   cudaFree(c->d_tgt); cudaFree(c->d_cnt); cudaFree(c->d_start); cudaFree(c->d_hits); cudaFree(c->d_first);
-  cudaFree(c->d_tilesum);
+  cudaFree(c->d_tilesum); cudaFree(c->d_states);
+  if (c->h_states[0]) cudaFreeHost(c->h_states[0]);
+  if (c->h_states[1]) cudaFreeHost(c->h_states[1]);
   cudaFree(c->d_mae); cudaFree(c->d_xchg_block);
   if (c->h_stage[0]) cudaFreeHost(c->h_stage[0]);
   if (c->h_stage[1]) cudaFreeHost(c->h_stage[1]);
@@ -390,26 +396,27 @@ int launch_epoch(sgd_ctx* c, int32_t epoch, int buf, int* launches) {
   return SGD_OK;
 }
 
-// Host part of one device shuffle: draw the n-1 raw values of the rand() stream this epoch
-// consumes (main.cu:90 / :207 consume exactly n-1 per std::random_shuffle) into pinned staging.
-void draw_raw_stream(sgd_ctx* c, int buf) {
-  uint32_t* stage = reinterpret_cast<uint32_t*>(c->h_stage[buf]);
-  stage[0] = 0;
-  if (c->R > 1) c->rng.raw(stage + 1, (size_t)(c->R - 1));
+// Host part of one device shuffle: the start state of every chunk of the n-1 values of the rand()
+// stream this epoch consumes (main.cu:90 / :207 consume exactly n-1 per std::random_shuffle), by
+// jump-ahead; then the host generator is moved past the epoch.  ~1 us per chunk.
+void prepare_stream_states(sgd_ctx* c, int buf) {
+  c->rng.chunk_states(c->jump_chunk, c->nchunks, c->h_states[buf]);
+  c->rng.skip((uint64_t)(c->R - 1));
 }
 
-// Device part: upload the raw stream (copy stream), then K1..K5 on the compute stream turn
+// Device part: upload the chunk states (copy stream), then K1..K5 on the compute stream turn
 // d_perm[src] into d_perm[dst].  No host sync.
 int enqueue_device_shuffle(sgd_ctx* c, int stage_buf, int src, int dst, int* launches) {
   const int64_t n = c->R;
-  CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->ev_done[2], 0));  // previous shuffle done with d_tgt
-  CUDA_TRY(cudaMemcpyAsync(c->d_tgt, c->h_stage[stage_buf], sizeof(uint32_t) * (size_t)n, cudaMemcpyHostToDevice,
-                           c->copy_stream));
+  CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->ev_done[2], 0));  // previous shuffle done with d_states
+  CUDA_TRY(cudaMemcpyAsync(c->d_states, c->h_states[stage_buf], sizeof(uint32_t) * 31 * (size_t)c->nchunks,
+                           cudaMemcpyHostToDevice, c->copy_stream));
   CUDA_TRY(cudaEventRecord(c->ev_perm[stage_buf], c->copy_stream));
   CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_perm[stage_buf], 0));
   const int blocks = (int)std::min<int64_t>((n + 255) / 256, (int64_t)c->num_sms * 16);
   CUDA_TRY(cudaMemsetAsync(c->d_cnt, 0, sizeof(int32_t) * ((size_t)n + 1), c->stream));
-  b200sgd::shuf_targets_kernel<<<blocks, 256, 0, c->stream>>>(c->d_tgt, n, c->d_cnt);
+  b200sgd::shuf_targets_stream_kernel<<<(int)((c->nchunks + 127) / 128), 128, 0, c->stream>>>(
+      c->d_states, c->chunk_len, c->nchunks, n, c->d_tgt, c->d_cnt);
   b200sgd::scan_tile_sums_kernel<<<c->scan_tiles, b200sgd::kScanBlock, 0, c->stream>>>(c->d_cnt, n, c->d_tilesum);
   b200sgd::scan_tile_offsets_kernel<<<1, b200sgd::kScanBlock, 0, c->stream>>>(c->d_tilesum, c->scan_tiles,
                                                                              c->d_tilesum + c->scan_tiles);
@@ -685,6 +692,14 @@ int sgd_create(const sgd_config* cfg, const float* X, const float* y, sgd_ctx** 
       CUDA_TRY(cudaMalloc(&c->d_hits, sizeof(int32_t) * n));
       CUDA_TRY(cudaMalloc(&c->d_first, sizeof(int32_t) * n));
       CUDA_TRY(cudaMalloc(&c->d_tilesum, sizeof(int32_t) * ((size_t)c->scan_tiles + 1)));
+      // the epoch's rand() stream is regenerated on the device from ~1024 chunk start states
+      int64_t L = 1024;
+      while (L * 1024 < c->R) L *= 2;
+      c->chunk_len = L;
+      c->nchunks = (c->R - 1 + L - 1) / L;
+      c->jump_chunk = b200sgd::GlibcRand::poly_z_pow((uint64_t)L);
+      CUDA_TRY(cudaMalloc(&c->d_states, sizeof(uint32_t) * 31 * (size_t)c->nchunks));
+      for (int i = 0; i < 2; ++i) CUDA_TRY(cudaMallocHost(&c->h_states[i], sizeof(uint32_t) * 31 * (size_t)c->nchunks));
     }
     c->mae_blocks = c->num_sms * 8;
     CUDA_TRY(cudaMalloc(&c->d_mae, sizeof(double) * c->mae_blocks));
@@ -867,7 +882,7 @@ int sgd_shuffle(sgd_ctx* c) {
     const int buf = c->cur ^ 1;
     int launches = 0;
     CUDA_TRY(cudaEventSynchronize(c->ev_perm[buf]));
-    draw_raw_stream(c, buf);
+    prepare_stream_states(c, buf);
     CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_done[buf], 0));
     SGD_TRY(enqueue_device_shuffle(c, buf, c->cur, buf, &launches));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -980,7 +995,7 @@ int sgd_run(sgd_ctx* c, int32_t first_epoch, int32_t num_epochs, sgd_timings* to
     if (c->device_shuffle) {
       const int buf = c->cur ^ 1;
       CUDA_TRY(cudaEventSynchronize(c->ev_perm[buf]));  // staging buffer free again
-      draw_raw_stream(c, buf);
+      prepare_stream_states(c, buf);
       // d_perm[buf] was last read by the epoch before the one in flight: stream order covers it
       SGD_TRY(enqueue_device_shuffle(c, buf, c->cur, buf, &launches));
       c->cur = buf;

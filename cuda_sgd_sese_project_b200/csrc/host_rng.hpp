@@ -70,6 +70,66 @@ class GlibcRand {
     return (int32_t)(v >> 1);
   }
 
+  // ---- jump-ahead ------------------------------------------------------------------------------
+  // The stream is a linear recurrence x[k] = x[k-31] + x[k-3] over Z/2^32, characteristic
+  // polynomial p(z) = z^31 - z^28 - 1.  If z^L = sum_j a_j z^j (mod p) then x[m+L] = sum_j a_j
+  // x[m+j] for every m, so the generator can be moved L steps ahead with 31 dot products instead
+  // of L additions.  Used to hand the device one start state per chunk of the stream (the stream
+  // itself is then generated on the GPU, shuffle_kernels.cuh) and to keep this generator in step.
+  struct Poly {
+    uint32_t a[31];
+  };
+  static Poly poly_mul(const Poly& f, const Poly& g) {
+    uint32_t prod[61] = {0};
+    for (int i = 0; i < 31; ++i)
+      for (int j = 0; j < 31; ++j) prod[i + j] += f.a[i] * g.a[j];
+    for (int d = 60; d >= 31; --d) {  // z^d = z^(d-3) + z^(d-31)
+      const uint32_t c = prod[d];
+      prod[d - 3] += c;
+      prod[d - 31] += c;
+    }
+    Poly r;
+    for (int i = 0; i < 31; ++i) r.a[i] = prod[i];
+    return r;
+  }
+  static Poly poly_z_pow(uint64_t n) {  // z^n mod p
+    Poly result{}, base{};
+    result.a[0] = 1;
+    base.a[1] = 1;
+    while (n) {
+      if (n & 1) result = poly_mul(result, base);
+      base = poly_mul(base, base);
+      n >>= 1;
+    }
+    return result;
+  }
+  // state = the last 31 outputs; returns the state `jump` (= the polynomial's exponent) steps later
+  static void apply(const Poly& jump, const uint32_t* state, uint32_t* out) {
+    uint32_t ext[61];
+    for (int i = 0; i < 31; ++i) ext[i] = state[i];
+    for (int i = 31; i < 61; ++i) ext[i] = ext[i - 31] + ext[i - 3];
+    for (int i = 0; i < 31; ++i) {
+      uint32_t acc = 0;
+      for (int j = 0; j < 31; ++j) acc += jump.a[j] * ext[i + j];
+      out[i] = acc;
+    }
+  }
+  void skip(uint64_t count) {
+    if (count == 0) return;
+    const Poly pz = poly_z_pow(count);
+    uint32_t nxt[31];
+    apply(pz, hist_, nxt);
+    std::memcpy(hist_, nxt, sizeof(hist_));
+  }
+  // start states (31 words each) of `nchunks` consecutive chunks of `chunk` values, beginning at the
+  // current position; the generator itself does not move
+  void chunk_states(const Poly& jump_chunk, int64_t nchunks, uint32_t* out) const {
+    if (nchunks <= 0) return;
+    std::memcpy(out, hist_, sizeof(hist_));
+    for (int64_t c = 1; c < nchunks; ++c) apply(jump_chunk, out + (c - 1) * 31, out + c * 31);
+  }
+  const uint32_t* state() const { return hist_; }
+
  private:
   uint32_t hist_[31];
 };

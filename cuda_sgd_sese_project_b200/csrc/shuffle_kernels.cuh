@@ -4,8 +4,9 @@
 // rand() (main.cu:90, :207): for i = 1..n-1: j = rand() % (i+1); if (i != j) swap(v[i], v[j]).
 // That loop is sequential and is the true epoch bottleneck at scale (23 ms at
 // 4M rows on this box's host vs a few ms of step loop).  The SAME permutation is produced here in
-// parallel.  Only the random stream is still drawn on the host (a linear recurrence, ~1 ns per
-// value, see host_rng.hpp) and uploaded; everything else is five small kernels:
+// parallel.  The host only computes ~1000 start states of the rand() stream per epoch by jump-ahead
+// (host_rng.hpp, ~1 ms) and uploads them (tens of KB); the stream itself is regenerated on the
+// device inside K1.  Five small kernels:
 //
 //   Look at the values instead of the loop.  Position i is untouched until step i, so the value
 //   in[i] sits at i until time i, when it moves to j_i (and whatever was at j_i moves to i).  A
@@ -17,7 +18,7 @@
 //   no-op, exactly as the `if (i != j)` of libstdc++.)  Chains are short: first(hits(p)) is about
 //   2p in expectation.
 //
-//   K1 targets : j_i from the raw stream, count hits per position
+//   K1 targets : regenerate the stream chunk by chunk, j_i = rand() % (i+1), count hits per position
 //   K2 scan    : exclusive prefix sum of the counts  -> CSR offsets
 //   K3 fill    : scatter i into its target's list (atomic cursor, arbitrary order)
 //   K4 order   : sort every (tiny) list ascending, record first(hits(p))
@@ -31,18 +32,35 @@
 
 namespace b200sgd {
 
-// tgt holds the raw 32-bit stream values on entry (raw[i-1] for step i, i >= 1; slot 0 unused)
-// and the swap targets j_i on exit.  cnt must be zero on entry.
-__global__ void __launch_bounds__(256) shuf_targets_kernel(uint32_t* __restrict__ tgt, int64_t n,
-                                                           int32_t* __restrict__ cnt) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    uint32_t j = 0;
-    if (i >= 1) {
-      j = (tgt[i] >> 1) % (uint32_t)(i + 1);  // rand() % ((i - first) + 1), stl_algo.h
-      if ((int64_t)j != i) atomicAdd(cnt + j, 1);
+// K1 with the stream generated on the device: thread c regenerates chunk c of this epoch's rand()
+// stream (values k in [c*L, (c+1)*L) of the epoch, consumed by steps i = k+1) from its 31-word
+// start state (host_rng.hpp chunk_states) and turns every value into a swap target at once.
+// x[k] = x[k-31] + x[k-3] (mod 2^32); rand() = x >> 1.  31 values per unrolled block keep the
+// window in registers.  cnt must be zero on entry.
+__global__ void __launch_bounds__(128) shuf_targets_stream_kernel(const uint32_t* __restrict__ states, int64_t L,
+                                                                  int64_t nchunks, int64_t n,
+                                                                  uint32_t* __restrict__ tgt, int32_t* __restrict__ cnt) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0) tgt[0] = 0;
+  if (c >= nchunks) return;
+  uint32_t r[31];
+#pragma unroll
+  for (int i = 0; i < 31; ++i) r[i] = states[c * 31 + i];
+  int64_t k = c * L;                                         // index into the epoch's stream
+  const int64_t kend = (k + L < n - 1) ? (k + L) : (n - 1);  // the epoch consumes n-1 values
+  while (k < kend) {
+#pragma unroll
+    for (int i = 0; i < 31; ++i) {
+      const uint32_t v = r[i] + (i < 3 ? r[28 + i] : r[i - 3]);  // r[i-3] already holds a NEW value
+      r[i] = v;
+      if (k < kend) {
+        const int64_t step = k + 1;
+        const uint32_t j = (v >> 1) % (uint32_t)(step + 1);  // rand() % ((i - first) + 1), stl_algo.h
+        if ((int64_t)j != step) atomicAdd(cnt + j, 1);
+        tgt[step] = j;
+      }
+      ++k;
     }
-    tgt[i] = j;
   }
 }
 
