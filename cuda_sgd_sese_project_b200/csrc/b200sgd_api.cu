@@ -72,6 +72,11 @@ KernelChoice make_choice() {
   return k;
 }
 
+int variant_env() {  // B200SGD_VARIANT: A/B switch for tuning runs
+  const char* e = std::getenv("B200SGD_VARIANT");
+  return e ? std::atoi(e) : 0;
+}
+
 // Kernel variant by row width (KC) and by how many rows one CTA handles per step: few rows ->
 // fewer consumer warps and no row unrolling, so the latency-critical step tail is not slowed down
 // by warps that only execute control code (the tail is issue-bound).
@@ -87,9 +92,11 @@ bool choose_kernel(int C4, int64_t rows_per_cta, KernelChoice* out) {
     else *out = make_choice<2, 2, 16>();
   } else if (C4 <= 128) {
     if (rows_per_cta <= 8) *out = make_choice<4, 1, 8>();
-    else *out = make_choice<4, 1, 16>();
+    else if (variant_env() == 1) *out = make_choice<4, 1, 16>();
+    else *out = make_choice<4, 2, 8>();
   } else if (C4 <= 256) {
-    *out = make_choice<8, 1, 8>();
+    if (rows_per_cta > 8 && variant_env() == 2) *out = make_choice<8, 2, 8>();
+    else *out = make_choice<8, 1, 8>();
   } else if (C4 <= 512) {
     *out = make_choice<16, 1, 8>();
   } else {
@@ -108,7 +115,8 @@ struct sgd_ctx {
   int32_t C4 = 0;
   int64_t rows_per_rank = 0, row_begin = 0, row_end = 0, local_rows = 0;
   int device = 0, num_sms = 0;
-  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  cudaStream_t stream = nullptr, copy_stream = nullptr, shuf_stream = nullptr;
+  cudaEvent_t ev_shuf[2] = {nullptr, nullptr};  // device shuffle into d_perm[i] finished
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t ev_perm[2] = {nullptr, nullptr};  // upload of d_perm[i] finished
   cudaEvent_t ev_done[3] = {nullptr, nullptr, nullptr};  // last reader of d_perm[i] done; [2]: shuffle scratch free
@@ -194,6 +202,7 @@ void free_all(sgd_ctx* c) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+  if (c->shuf_stream) cudaStreamSynchronize(c->shuf_stream);
   for (int i = 0; i < 8; ++i)
     if (c->peer_open[i] && c->peer_block[i]) cudaIpcCloseMemHandle(c->peer_block[i]);
   if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
@@ -212,8 +221,11 @@ void free_all(sgd_ctx* c) {
   cudaEvent_t evs[] = {c->ev0, c->ev1, c->ev_perm[0], c->ev_perm[1], c->ev_done[0], c->ev_done[1], c->ev_done[2]};
   for (cudaEvent_t e : evs)
     if (e) cudaEventDestroy(e);
+  if (c->ev_shuf[0]) cudaEventDestroy(c->ev_shuf[0]);
+  if (c->ev_shuf[1]) cudaEventDestroy(c->ev_shuf[1]);
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  if (c->shuf_stream) cudaStreamDestroy(c->shuf_stream);
 }
 
 // Decide grid size, reduction mode and ring depth for this shape (DESIGN.md "launch geometry").
@@ -404,37 +416,42 @@ void prepare_stream_states(sgd_ctx* c, int buf) {
   c->rng.skip((uint64_t)(c->R - 1));
 }
 
-// Device part: upload the chunk states (copy stream), then K1..K5 on the compute stream turn
-// d_perm[src] into d_perm[dst].  No host sync.
+// Device part: upload the chunk states (copy stream), then K1..K5 on the SHUFFLE stream turn
+// d_perm[src] into d_perm[dst] -- concurrently with the epoch kernel that is still reading
+// d_perm[src] on the compute stream.  No host sync.
 int enqueue_device_shuffle(sgd_ctx* c, int stage_buf, int src, int dst, int* launches) {
   const int64_t n = c->R;
   CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->ev_done[2], 0));  // previous shuffle done with d_states
   CUDA_TRY(cudaMemcpyAsync(c->d_states, c->h_states[stage_buf], sizeof(uint32_t) * 31 * (size_t)c->nchunks,
                            cudaMemcpyHostToDevice, c->copy_stream));
   CUDA_TRY(cudaEventRecord(c->ev_perm[stage_buf], c->copy_stream));
-  CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_perm[stage_buf], 0));
+  CUDA_TRY(cudaStreamWaitEvent(c->shuf_stream, c->ev_perm[stage_buf], 0));
+  CUDA_TRY(cudaStreamWaitEvent(c->shuf_stream, c->ev_done[dst], 0));  // last epoch that read d_perm[dst]
+  CUDA_TRY(cudaStreamWaitEvent(c->shuf_stream, c->ev_perm[src], 0));  // d_perm[src] uploaded (sgd_set_permutation)
   const int blocks = (int)std::min<int64_t>((n + 255) / 256, (int64_t)c->num_sms * 16);
-  CUDA_TRY(cudaMemsetAsync(c->d_cnt, 0, sizeof(int32_t) * ((size_t)n + 1), c->stream));
-  b200sgd::shuf_targets_stream_kernel<<<(int)((c->nchunks + 127) / 128), 128, 0, c->stream>>>(
+  CUDA_TRY(cudaMemsetAsync(c->d_cnt, 0, sizeof(int32_t) * ((size_t)n + 1), c->shuf_stream));
+  b200sgd::shuf_targets_stream_kernel<<<(int)((c->nchunks + 127) / 128), 128, 0, c->shuf_stream>>>(
       c->d_states, c->chunk_len, c->nchunks, n, c->d_tgt, c->d_cnt);
-  b200sgd::scan_tile_sums_kernel<<<c->scan_tiles, b200sgd::kScanBlock, 0, c->stream>>>(c->d_cnt, n, c->d_tilesum);
-  b200sgd::scan_tile_offsets_kernel<<<1, b200sgd::kScanBlock, 0, c->stream>>>(c->d_tilesum, c->scan_tiles,
+  b200sgd::scan_tile_sums_kernel<<<c->scan_tiles, b200sgd::kScanBlock, 0, c->shuf_stream>>>(c->d_cnt, n, c->d_tilesum);
+  b200sgd::scan_tile_offsets_kernel<<<1, b200sgd::kScanBlock, 0, c->shuf_stream>>>(c->d_tilesum, c->scan_tiles,
                                                                              c->d_tilesum + c->scan_tiles);
-  b200sgd::scan_apply_kernel<<<c->scan_tiles, b200sgd::kScanBlock, 0, c->stream>>>(
+  b200sgd::scan_apply_kernel<<<c->scan_tiles, b200sgd::kScanBlock, 0, c->shuf_stream>>>(
       c->d_cnt, n, c->d_tilesum, c->d_tilesum + c->scan_tiles, c->d_start);
-  CUDA_TRY(cudaMemsetAsync(c->d_cnt, 0, sizeof(int32_t) * ((size_t)n + 1), c->stream));
-  b200sgd::shuf_fill_kernel<<<blocks, 256, 0, c->stream>>>(c->d_tgt, n, c->d_start, c->d_cnt, c->d_hits);
-  b200sgd::shuf_order_kernel<<<blocks, 256, 0, c->stream>>>(n, c->d_start, c->d_hits, c->d_first);
-  b200sgd::shuf_resolve_kernel<<<blocks, 256, 0, c->stream>>>(c->d_tgt, n, c->d_start, c->d_hits, c->d_first,
+  CUDA_TRY(cudaMemsetAsync(c->d_cnt, 0, sizeof(int32_t) * ((size_t)n + 1), c->shuf_stream));
+  b200sgd::shuf_fill_kernel<<<blocks, 256, 0, c->shuf_stream>>>(c->d_tgt, n, c->d_start, c->d_cnt, c->d_hits);
+  b200sgd::shuf_order_kernel<<<blocks, 256, 0, c->shuf_stream>>>(n, c->d_start, c->d_hits, c->d_first);
+  b200sgd::shuf_resolve_kernel<<<blocks, 256, 0, c->shuf_stream>>>(c->d_tgt, n, c->d_start, c->d_hits, c->d_first,
                                                             c->d_perm[src], c->d_perm[dst]);
   CUDA_TRY(cudaGetLastError());
-  CUDA_TRY(cudaEventRecord(c->ev_done[2], c->stream));
+  CUDA_TRY(cudaEventRecord(c->ev_done[2], c->shuf_stream));
+  CUDA_TRY(cudaEventRecord(c->ev_shuf[dst], c->shuf_stream));
   *launches += 7;
   return SGD_OK;
 }
 
 int sync_host_ind(sgd_ctx* c) {  // bring h_ind up to date after device shuffles
   if (!c->host_ind_stale) return SGD_OK;
+  CUDA_TRY(cudaStreamSynchronize(c->shuf_stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   CUDA_TRY(cudaMemcpy(c->h_ind.data(), c->d_perm[c->cur], sizeof(int32_t) * (size_t)c->R, cudaMemcpyDeviceToHost));
   c->host_ind_stale = false;
@@ -631,6 +648,9 @@ int sgd_create(const sgd_config* cfg, const float* X, const float* y, sgd_ctx** 
     SGD_TRY(bind(c));
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->shuf_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&c->ev_shuf[0], cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&c->ev_shuf[1], cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreate(&c->ev0));
     CUDA_TRY(cudaEventCreate(&c->ev1));
     for (int i = 0; i < 2; ++i) {
@@ -663,7 +683,7 @@ int sgd_create(const sgd_config* cfg, const float* X, const float* y, sgd_ctx** 
     CUDA_TRY(cudaMemset(c->d_ll_part, 0, sizeof(uint4) * 2 * 2 * Gp * c->C4));
     // private weight mailboxes per CTA while they stay small (latency-bound shapes); one shared
     // copy for wide rows, where steps are long and the extra L2 traffic would not pay
-    c->w_copies = ((size_t)c->grid * c->C4 * 32 <= (512u << 10)) ? c->grid : 1;
+    c->w_copies = ((size_t)c->grid * c->C4 * 32 <= (8u << 20)) ? c->grid : 1;
     CUDA_TRY(cudaMalloc(&c->d_ll_w, sizeof(uint4) * 2 * (size_t)c->w_copies * C4p));
     CUDA_TRY(cudaMemset(c->d_ll_w, 0, sizeof(uint4) * 2 * (size_t)c->w_copies * C4p));
     CUDA_TRY(cudaMalloc(&c->d_glast, sizeof(float4) * c->C4));
@@ -883,9 +903,8 @@ int sgd_shuffle(sgd_ctx* c) {
     int launches = 0;
     CUDA_TRY(cudaEventSynchronize(c->ev_perm[buf]));
     prepare_stream_states(c, buf);
-    CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_done[buf], 0));
     SGD_TRY(enqueue_device_shuffle(c, buf, c->cur, buf, &launches));
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->shuf_stream));
     c->cur = buf;
     c->perm_valid = true;
     c->host_ind_stale = true;
@@ -932,6 +951,7 @@ int sgd_get_permutation(sgd_ctx* c, int32_t* perm) {
   SGD_TRY(bind(c));
   if (c->perm_valid) {
     // read it back from the DEVICE copy the step kernel consumes
+    CUDA_TRY(cudaStreamSynchronize(c->shuf_stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     CUDA_TRY(cudaMemcpy(perm, c->d_perm[c->cur], sizeof(int32_t) * (size_t)c->R, cudaMemcpyDeviceToHost));
   } else {
@@ -949,6 +969,7 @@ int sgd_epoch(sgd_ctx* c, int32_t epoch, sgd_timings* out) {
   SGD_TRY(bind(c));
   int launches = 0;
   CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_perm[c->cur], 0));
+  CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_shuf[c->cur], 0));
   SGD_TRY(bucket_perm(c, c->cur, &launches));
   CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
   SGD_TRY(launch_epoch(c, epoch, c->cur, &launches));
@@ -996,7 +1017,6 @@ int sgd_run(sgd_ctx* c, int32_t first_epoch, int32_t num_epochs, sgd_timings* to
       const int buf = c->cur ^ 1;
       CUDA_TRY(cudaEventSynchronize(c->ev_perm[buf]));  // staging buffer free again
       prepare_stream_states(c, buf);
-      // d_perm[buf] was last read by the epoch before the one in flight: stream order covers it
       SGD_TRY(enqueue_device_shuffle(c, buf, c->cur, buf, &launches));
       c->cur = buf;
       c->perm_valid = true;
@@ -1018,6 +1038,7 @@ int sgd_run(sgd_ctx* c, int32_t first_epoch, int32_t num_epochs, sgd_timings* to
     const int buf = c->cur;
     auto enqueue = [&]() -> int {
       CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_perm[buf], 0));
+      CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_shuf[buf], 0));
       SGD_TRY(bucket_perm(c, buf, &launches));
       CUDA_TRY(cudaEventRecord(evs[2 * e], c->stream));
       SGD_TRY(launch_epoch(c, first_epoch + e, buf, &launches));
@@ -1029,6 +1050,7 @@ int sgd_run(sgd_ctx* c, int32_t first_epoch, int32_t num_epochs, sgd_timings* to
     if (rc == SGD_OK && e + 1 < num_epochs) rc = stage_next();  // overlaps with the kernel above
   }
   cudaError_t se = cudaStreamSynchronize(c->stream);
+  if (se == cudaSuccess) se = cudaStreamSynchronize(c->shuf_stream);
   if (rc == SGD_OK && se != cudaSuccess) rc = fail(SGD_ERR_CUDA, std::string("epoch loop: ") + cudaGetErrorString(se));
   if (rc == SGD_OK) rc = check_watchdog(c);
   float loop_ms = 0.f;

@@ -599,12 +599,13 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1) sgd_epoch_ke
 
     // ---- rows of this step, one ring tile (= producer round) at a time: consumer warp cw
     // takes rows cw, cw+NW, ... of the tile, all U of them concurrently ----
-    const int nt = (int)((n + TR - 1) / TR);
+    const int n32 = (int)n;  // rows of one CTA in one step always fit 32 bits
+    const int nt = (n32 + TR - 1) / TR;
     for (int ti = 0; ti < nt; ++ti) {
       const uint32_t tq = tqbase + (uint32_t)ti;
       const uint32_t tile = tq & tile_mask;
       const uint32_t use = tq >> p.tile_log2;
-      const int cnt = (int)((n - (int64_t)ti * TR) < TR ? (n - (int64_t)ti * TR) : TR);
+      const int cnt = (n32 - ti * TR) < TR ? (n32 - ti * TR) : TR;
       const unsigned char* tbase = ring + (size_t)tile * tile_bytes;
       float4 x[U][KC];
       float dot[U], y[U];

@@ -226,6 +226,28 @@ __global__ void loadlat_kernel(const uint4* buf, int iters, long long* cycles, u
   *sink = acc;
 }
 
+// ---- store issue: NST back-to-back 16-byte stores to different lines by one thread; if a flavour
+// is serialised (each store waits for the previous one's acknowledgement) the time per iteration
+// grows with NST * latency instead of NST * issue cost.
+template <int MODE, int NST>  // 0 st.volatile  1 st.relaxed.gpu  2 st.relaxed.sys  3 st.global.cg  4 st.global
+__global__ void storeissue_kernel(uint4* buf, int iters, long long* cycles) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int k = 0; k < NST; ++k) {
+      uint4* p = buf + (size_t)k * 8 + (it & 1);
+      const unsigned v = (unsigned)it;
+      if (MODE == 0) asm volatile("st.volatile.global.v4.u32 [%0], {%1,%1,%1,%1};" ::"l"(p), "r"(v) : "memory");
+      if (MODE == 1) asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1,%1,%1,%1};" ::"l"(p), "r"(v) : "memory");
+      if (MODE == 2) asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1,%1,%1,%1};" ::"l"(p), "r"(v) : "memory");
+      if (MODE == 3) asm volatile("st.global.cg.v4.u32 [%0], {%1,%1,%1,%1};" ::"l"(p), "r"(v) : "memory");
+      if (MODE == 4) asm volatile("st.global.v4.u32 [%0], {%1,%1,%1,%1};" ::"l"(p), "r"(v) : "memory");
+    }
+  }
+  *cycles = clock64() - t0;
+}
+
 // ---- counter grid barrier --------------------------------------------------------------------
 __global__ void gridbar_kernel(unsigned* ctr, int iters, long long* cycles) {
   const unsigned G = gridDim.x;
@@ -346,6 +368,19 @@ int main() {
     RUN_LL(0, 1) RUN_LL(0, 2) RUN_LL(0, 4) RUN_LL(0, 8)
     RUN_LL(1, 1) RUN_LL(1, 2) RUN_LL(1, 4) RUN_LL(1, 8)
     RUN_LL(2, 1) RUN_LL(2, 2) RUN_LL(2, 4) RUN_LL(2, 8)
+  }
+  // store issue cost by flavour
+  {
+    uint4* sb;
+    CK(cudaMalloc(&sb, 1 << 16));
+    const char* mn[] = {"st.volatile", "st.relaxed.gpu", "st.relaxed.sys", "st.global.cg", "st.global"};
+    int it = 20000;
+#define RUN_ST(MODE, N)                                                                             \
+    storeissue_kernel<MODE, N><<<1, 32>>>(sb, it, cyc);                                             \
+    CK(cudaDeviceSynchronize());                                                                    \
+    std::printf("{\"test\": \"storeissue\", \"flavor\": \"%s\", \"stores_per_iter\": %d, \"cycles_per_iter\": %.1f}\n", mn[MODE], N, (double)*cyc / it);
+    RUN_ST(0, 1) RUN_ST(0, 4) RUN_ST(0, 16) RUN_ST(1, 1) RUN_ST(1, 4) RUN_ST(1, 16) RUN_ST(2, 4) RUN_ST(2, 16)
+    RUN_ST(3, 1) RUN_ST(3, 4) RUN_ST(3, 16) RUN_ST(4, 4) RUN_ST(4, 16)
   }
   // counter barrier
   for (int G : {2, 8, 32, 64, 148}) {
