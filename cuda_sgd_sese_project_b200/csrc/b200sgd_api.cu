@@ -691,8 +691,8 @@ int sgd_create(const sgd_config* cfg, const float* X, const float* y, sgd_ctx** 
     CUDA_TRY(cudaMalloc(&c->d_bar, sizeof(unsigned int) * 2));
     CUDA_TRY(cudaMemset(c->d_bar, 0, sizeof(unsigned int) * 2));
     if (const char* e = std::getenv("B200SGD_PHASE_PROFILE"); e && e[0] == '1') {
-      CUDA_TRY(cudaMalloc(&c->d_dbg, sizeof(unsigned long long) * 8 * (size_t)c->grid));
-      CUDA_TRY(cudaMemset(c->d_dbg, 0, sizeof(unsigned long long) * 8 * (size_t)c->grid));
+      CUDA_TRY(cudaMalloc(&c->d_dbg, sizeof(unsigned long long) * 16 * (size_t)c->grid));
+      CUDA_TRY(cudaMemset(c->d_dbg, 0, sizeof(unsigned long long) * 16 * (size_t)c->grid));
     }
     CUDA_TRY(cudaMalloc(&c->d_ctl, sizeof(b200sgd::StepCtl)));
     CUDA_TRY(cudaMemset(c->d_ctl, 0, sizeof(b200sgd::StepCtl)));
@@ -1129,7 +1129,7 @@ int sgd_debug_phase_cycles(sgd_ctx* c, uint64_t* out, int32_t max_ctas) {
   if (!c->d_dbg) return fail(SGD_ERR_STATE, "set B200SGD_PHASE_PROFILE=1 before sgd_create");
   SGD_TRY(bind(c));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
-  const int n = std::min<int>(max_ctas, c->grid);
+  const int n = std::min<int>(max_ctas, 2 * c->grid);  // [grid..2*grid): wall-clock snapshot of one step
   CUDA_TRY(cudaMemcpy(out, c->d_dbg, sizeof(uint64_t) * 8 * (size_t)n, cudaMemcpyDeviceToHost));
   return n;
 }

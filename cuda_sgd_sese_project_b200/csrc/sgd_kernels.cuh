@@ -227,14 +227,33 @@ struct SpinGuard {
     return false;
   }
 };
-// Blocks until the float4 at `src` carries `tag`.
-__device__ __forceinline__ float4 ll_wait_f4(const uint4* src, uint32_t tag, unsigned int* err) {
-  float4 v;
+// Blocks until the float4 at `src` carries `tag`.  Narrow rows (few column owners) probe both
+// 16-byte words at once: one L2 round trip less on the critical path.  Wide rows (~100 column
+// owners each polling 148 sources, 148 CTAs polling their mailboxes) probe ONE word and fetch the
+// other once it has arrived: the back-to-back double loads crowd the L2 request queues there
+// (C = 512: 9.7 -> 8.8 us per step).  __nanosleep back-off between probes was measured and made
+// every shape slower, so there is none.
+__device__ __forceinline__ float4 ll_wait_f4(const uint4* src, uint32_t tag, unsigned int* err,
+                                             unsigned one_word = 0) {
   SpinGuard guard;
-  while (!ll_unpack(ld_volatile_u4(src), ld_volatile_u4(src + 1), tag, &v)) {
-    if (guard.expired(err, 3u)) break;
+  if (!one_word) {
+    float4 v;
+    while (!ll_unpack(ld_volatile_u4(src), ld_volatile_u4(src + 1), tag, &v)) {
+      if (guard.expired(err, 3u)) break;
+    }
+    return v;
   }
-  return v;
+  uint4 b = ld_volatile_u4(src + 1);
+  while (b.y != tag || b.w != tag) {
+    if (guard.expired(err, 3u)) break;
+    b = ld_volatile_u4(src + 1);
+  }
+  uint4 a = ld_volatile_u4(src);
+  while (a.y != tag || a.w != tag) {
+    if (guard.expired(err, 3u)) break;
+    a = ld_volatile_u4(src);
+  }
+  return make_float4(__uint_as_float(a.x), __uint_as_float(a.z), __uint_as_float(b.x), __uint_as_float(b.z));
 }
 
 // Dataflow twin of tree_sum_sources: sums the tagged float4 `f` of sources 0..nsrc-1; each load
@@ -247,14 +266,14 @@ __device__ __forceinline__ float4 ll_wait_f4(const uint4* src, uint32_t tag, uns
 template <int kThreads>
 __device__ __forceinline__ float4 ll_gather(const uint4* base0, int64_t stride, int64_t col_stride, int f, int nsrc,
                                             int q, int Q, bool active, uint32_t tag, unsigned int* err,
-                                            float4* xred, int ctid) {
+                                            float4* xred, int ctid, unsigned one_word = 0) {
   // source i of column f sits at base0 + (i*stride + f*col_stride) * 2
   const uint4* base = base0 + (int64_t)f * col_stride * 2;
   f = 0;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   if (active) {
     int i = q;
-    for (; i + 3 * Q < nsrc; i += 4 * Q) {  // 8 loads in flight, then consume in order
+    for (; i + 3 * Q < nsrc; i += 4 * Q) {  // 4 sources in flight, consumed in order
       const uint4* s0 = base + ((int64_t)i * stride + f) * 2;
       const uint4* s1 = base + ((int64_t)(i + Q) * stride + f) * 2;
       const uint4* s2 = base + ((int64_t)(i + 2 * Q) * stride + f) * 2;
@@ -264,28 +283,28 @@ __device__ __forceinline__ float4 ll_gather(const uint4* base0, int64_t stride, 
       const uint4 a2 = ld_volatile_u4(s2), b2 = ld_volatile_u4(s2 + 1);
       const uint4 a3 = ld_volatile_u4(s3), b3 = ld_volatile_u4(s3 + 1);
       float4 v0, v1, v2, v3;
-      if (!ll_unpack(a0, b0, tag, &v0)) v0 = ll_wait_f4(s0, tag, err);
-      if (!ll_unpack(a1, b1, tag, &v1)) v1 = ll_wait_f4(s1, tag, err);
-      if (!ll_unpack(a2, b2, tag, &v2)) v2 = ll_wait_f4(s2, tag, err);
-      if (!ll_unpack(a3, b3, tag, &v3)) v3 = ll_wait_f4(s3, tag, err);
+      if (!ll_unpack(a0, b0, tag, &v0)) v0 = ll_wait_f4(s0, tag, err, one_word);
+      if (!ll_unpack(a1, b1, tag, &v1)) v1 = ll_wait_f4(s1, tag, err, one_word);
+      if (!ll_unpack(a2, b2, tag, &v2)) v2 = ll_wait_f4(s2, tag, err, one_word);
+      if (!ll_unpack(a3, b3, tag, &v3)) v3 = ll_wait_f4(s3, tag, err, one_word);
       acc = f4_add(acc, v0);
       acc = f4_add(acc, v1);
       acc = f4_add(acc, v2);
       acc = f4_add(acc, v3);
     }
-    if (i + Q < nsrc) {  // two sources left: both loads in flight
+    if (i + Q < nsrc) {  // two sources left: both in flight
       const uint4* s0 = base + ((int64_t)i * stride + f) * 2;
       const uint4* s1 = base + ((int64_t)(i + Q) * stride + f) * 2;
       const uint4 a0 = ld_volatile_u4(s0), b0 = ld_volatile_u4(s0 + 1);
       const uint4 a1 = ld_volatile_u4(s1), b1 = ld_volatile_u4(s1 + 1);
       float4 v0, v1;
-      if (!ll_unpack(a0, b0, tag, &v0)) v0 = ll_wait_f4(s0, tag, err);
-      if (!ll_unpack(a1, b1, tag, &v1)) v1 = ll_wait_f4(s1, tag, err);
+      if (!ll_unpack(a0, b0, tag, &v0)) v0 = ll_wait_f4(s0, tag, err, one_word);
+      if (!ll_unpack(a1, b1, tag, &v1)) v1 = ll_wait_f4(s1, tag, err, one_word);
       acc = f4_add(acc, v0);
       acc = f4_add(acc, v1);
       i += 2 * Q;
     }
-    for (; i < nsrc; i += Q) acc = f4_add(acc, ll_wait_f4(base + ((int64_t)i * stride + f) * 2, tag, err));
+    for (; i < nsrc; i += Q) acc = f4_add(acc, ll_wait_f4(base + ((int64_t)i * stride + f) * 2, tag, err, one_word));
   }
   const int ql = Q < 32 ? Q : 32;
   for (int m = 1; m < ql; m <<= 1) acc = f4_add(acc, f4_shfl_xor(acc, m));
@@ -564,6 +583,7 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1) sgd_epoch_ke
     while (Q < qmax && Q < gcap && (int64_t)(ncol > 0 ? ncol : 1) * (Q * 2) <= kCT) Q <<= 1;
   }
   const int cols_per_pass = kCT / Q;
+  const unsigned poll_one_word = C4 > 32 ? 1u : 0u;  // see ll_wait_f4
   const int Gp = (G + 3) & ~3;     // strides of the tagged-word arrays, padded to 128-byte lines
   const int C4p = (C4 + 3) & ~3;
   const int my_col = ctid / Q;  // column (within a pass) and lane (within the column) of this thread
@@ -573,16 +593,20 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1) sgd_epoch_ke
   unsigned long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   long long t_prev = 0;
   const bool prof = (p.dbg != nullptr) && ctid == 0;
+  int cur_step = 0;
   auto mark = [&](int i) {
     if (prof) {
       const long long t = clock64();
       ph[i] += (unsigned long long)(t - t_prev);
       t_prev = t;
+      // wall-clock snapshot of one step (the middle one) for cross-CTA timelines
+      if (cur_step == p.nb / 2) p.dbg[((int64_t)G + cta) * 8 + i] = global_timer_ns();
     }
   };
   if (prof) t_prev = clock64();
 
   for (int s = 0; s < p.nb; ++s) {
+    cur_step = s;
     int64_t off, lo, n;
     if (p.step_off == nullptr) {
       off = ((int64_t)first_step + s) * p.B;
@@ -709,7 +733,7 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1) sgd_epoch_ke
         for (int base = 0; base < C4; base += cols_per_pass) {
           const int fi = base + my_col;
           const bool active = fi < C4;
-          const float4 tot = ll_gather<kCT>(parts, 1, Gp, active ? fi : 0, G, my_q, Q, active, tag, p.err, xred, ctid);
+          const float4 tot = ll_gather<kCT>(parts, 1, Gp, active ? fi : 0, G, my_q, Q, active, tag, p.err, xred, ctid, poll_one_word);
           if (active && my_q == 0) {
             float4 gs;
             w_s[fi] = updated(fi, w_s[fi], tot, &gs);
@@ -733,7 +757,7 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1) sgd_epoch_ke
         // old weights are read before anything of this step is published (the mailbox poll below
         // overwrites w_s once the new ones arrive)
         const float4 w_old = active ? w_s[f] : make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 tot = ll_gather<kCT>(parts, 1, Gp, f, G, my_q, Q, active, tag, p.err, xred, ctid);
+        float4 tot = ll_gather<kCT>(parts, 1, Gp, f, G, my_q, Q, active, tag, p.err, xred, ctid, poll_one_word);
         mark(3);  // (owners) partials gathered
         if (p.nranks > 1) {  // uniform over the grid
           const int64_t slot = ((int64_t)par * p.nranks) * C4p;
@@ -742,7 +766,7 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1) sgd_epoch_ke
               ll_store_f4(p.ll_inbox_peer[pr] + (slot + (int64_t)p.rank * C4p + f) * 2, tot, tag);
           }
           // the ranks' slices are gathered like the partials: lane q polls rank q, fixed tree
-          tot = ll_gather<kCT>(p.ll_inbox_local + slot * 2, C4p, 1, f, p.nranks, my_q, Q, active, tag, p.err, xred, ctid);
+          tot = ll_gather<kCT>(p.ll_inbox_local + slot * 2, C4p, 1, f, p.nranks, my_q, Q, active, tag, p.err, xred, ctid, poll_one_word);
         }
         // every lane of the group holds `tot`: lane q publishes the new weights into the
         // mailboxes of CTAs q, q+Q, ... (private copies keep 148 pollers off one line)
@@ -756,7 +780,7 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1) sgd_epoch_ke
       }
       mark(4);  // owner work (gather, exchange, publish) done
       const uint4* my_w = p.ll_w + (p.w_copies > 1 ? (int64_t)cta * C4p * 2 : 0);
-      for (int f = ctid; f < C4; f += kCT) w_s[f] = ll_wait_f4(my_w + (int64_t)f * 2, tag, p.err);
+      for (int f = ctid; f < C4; f += kCT) w_s[f] = ll_wait_f4(my_w + (int64_t)f * 2, tag, p.err, poll_one_word);
       mark(5);  // new weights arrived
       consumer_bar<kCT>();
       mark(6);

@@ -264,11 +264,19 @@ class SGDEngine:
 
     def debug_phase_cycles(self) -> np.ndarray:
         """[grid, 8] cycle sums per phase of the last launch (needs B200SGD_PHASE_PROFILE=1)."""
-        out = np.zeros((self.grid, 8), dtype=np.uint64)
-        n = L.load().sgd_debug_phase_cycles(self._h, _ptr(out), self.grid)
+        out = np.zeros((2 * self.grid, 8), dtype=np.uint64)
+        n = L.load().sgd_debug_phase_cycles(self._h, _ptr(out), 2 * self.grid)
         if n < 0:
             L.check(n)
-        return out[:n]
+        return out[:self.grid]
+
+    def debug_step_timeline(self) -> np.ndarray:
+        """[grid, 8] globaltimer (ns) at the phase marks of the middle step of the last launch."""
+        out = np.zeros((2 * self.grid, 8), dtype=np.uint64)
+        n = L.load().sgd_debug_phase_cycles(self._h, _ptr(out), 2 * self.grid)
+        if n < 0:
+            L.check(n)
+        return out[self.grid:]
 
     # -- peers (multi-GPU)
     def peer_export(self) -> bytes:

@@ -60,6 +60,17 @@ def run(R, C, B, lr=0.01, epochs=3, warm=1, shuffle=True, **kw):
                "finite": bool(np.all(np.isfinite(w)))}
         if phases:
             out["phase_cycles_mean_max"] = phases
+            tl = eng.debug_step_timeline().astype(np.int64)
+            t0 = tl[:, 0][tl[:, 0] > 0].min()
+            rel = np.where(tl > 0, tl - t0, -1)
+            own = d[:, 3] > 50
+            def stats(col, mask=None):
+                v = rel[:, col] if mask is None else rel[mask, col]
+                v = v[v >= 0]
+                return [int(v.min()), int(np.median(v)), int(v.max())] if v.size else None
+            out["timeline_ns_min_med_max"] = {"rows_done": stats(0), "cta_reduced": stats(1), "published": stats(2),
+                                              "gathered(owners)": stats(3, own), "owner_published": stats(4, own),
+                                              "weights_arrived": stats(5), "step_end": stats(6)}
         out.update({k: v for k, v in kw.items()})
         print(json.dumps(out), flush=True)
         return out
