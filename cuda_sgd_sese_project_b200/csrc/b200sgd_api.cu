@@ -59,16 +59,18 @@ constexpr int kGraphChunk = 256;        // step-kernel nodes per instantiated gr
 
 struct KernelChoice {
   int KC = 0, U = 0, NW = 0;
+  bool wide = false;
   const void* fn = nullptr;
   size_t fixed_smem = 0;
 };
 
-template <int KC, int U, int NW>
+template <int KC, int U, int NW, bool WIDE = false>
 KernelChoice make_choice() {
   KernelChoice k;
   k.KC = KC; k.U = U; k.NW = NW;
-  k.fn = (const void*)b200sgd::sgd_epoch_kernel<KC, U, NW>;
-  k.fixed_smem = b200sgd::EpochSmem<KC, NW>::kFixed;
+  k.wide = WIDE;
+  k.fn = (const void*)b200sgd::sgd_epoch_kernel<KC, U, NW, WIDE>;
+  k.fixed_smem = b200sgd::EpochSmem<KC, NW, WIDE>::kFixed;
   return k;
 }
 
@@ -98,7 +100,14 @@ bool choose_kernel(int C4, int64_t rows_per_cta, KernelChoice* out) {
     if (rows_per_cta > 8 && variant_env() == 2) *out = make_choice<8, 2, 8>();
     else *out = make_choice<8, 1, 8>();
   } else if (C4 <= 512) {
-    *out = make_choice<16, 1, 8>();
+    if (variant_env() == 3) *out = make_choice<2, 1, 8, true>();  // column mapping, A/B
+    else *out = make_choice<16, 1, 8>();
+  } else if (C4 <= 1024) {
+    *out = make_choice<4, 1, 8, true>();   // column mapping: C <= 4096
+  } else if (C4 <= 2048) {
+    *out = make_choice<8, 1, 8, true>();   // C <= 8192
+  } else if (C4 <= 4096) {
+    *out = make_choice<16, 1, 8, true>();  // C <= 16384
   } else {
     return false;
   }
@@ -168,6 +177,7 @@ struct sgd_ctx {
   KernelChoice kc{};
   int grid = 0, reduce_mode = 0, ntiles = 0, tile_log2 = 0, engine = SGD_ENGINE_PERSISTENT;
   int nprod = 1;  // producer warps
+  int tile_rows = 0;
   size_t smem_bytes = 0;
   cudaGraphExec_t graph_exec = nullptr;
   int graph_nodes = 0;
@@ -230,7 +240,7 @@ void free_all(sgd_ctx* c) {
 
 // Decide grid size, reduction mode and ring depth for this shape (DESIGN.md "launch geometry").
 int configure_launch(sgd_ctx* c) {
-  if (c->C4 > 512) return fail(SGD_ERR_ARG, "cols > 2048 is not supported by this build of the step kernel");
+  if (c->C4 > 4096) return fail(SGD_ERR_ARG, "cols > 16384 is not supported by this build of the step kernel");
   // rows this rank sees per step
   const int64_t rows_step = std::max<int64_t>(1, (int64_t)c->B / std::max(1, c->cfg.nranks));
   int grid = c->cfg.grid;
@@ -262,7 +272,16 @@ int configure_launch(sgd_ctx* c) {
     if (const char* e = std::getenv("B200SGD_PRODUCER_WARPS")) np = std::atoi(e);
     c->nprod = std::max(1, std::min(np, b200sgd::kMaxProducerWarps));
   }
-  const size_t tile_bytes = (size_t)c->kc.NW * c->kc.U * slot_bytes;
+  int tile_rows = c->kc.NW * c->kc.U;
+  if (c->kc.wide) {
+    // column mapping: as many rows per tile as two tiles allow (<= 32, a multiple of NW if possible)
+    const size_t avail = kMaxDynSmem - c->kc.fixed_smem;
+    tile_rows = (int)std::min<size_t>(32, avail / (2 * slot_bytes));
+    if (tile_rows >= c->kc.NW) tile_rows -= tile_rows % c->kc.NW;
+    if (tile_rows < 1) return fail(SGD_ERR_ARG, "row too wide for the shared-memory ring");
+  }
+  c->tile_rows = tile_rows;
+  const size_t tile_bytes = (size_t)tile_rows * slot_bytes;
   if (c->kc.fixed_smem + 2 * tile_bytes > kMaxDynSmem)
     return fail(SGD_ERR_ARG, "row too wide for the shared-memory ring");
   int ntiles = 2, lg = 1;
@@ -312,6 +331,7 @@ void fill_params(sgd_ctx* c, b200sgd::EpochParams* p, int32_t epoch, int buf) {
   p->reduce_mode = c->reduce_mode;
   p->ntiles = c->ntiles;
   p->tile_log2 = c->tile_log2;
+  p->tile_rows = c->tile_rows;
   p->slot_bytes = (uint32_t)(c->ld * 4);
   p->nprod = c->nprod;
   p->ll_part = c->d_ll_part;
@@ -722,6 +742,9 @@ int sgd_create(const sgd_config* cfg, const float* X, const float* y, sgd_ctx** 
       for (int i = 0; i < 2; ++i) CUDA_TRY(cudaMallocHost(&c->h_states[i], sizeof(uint32_t) * 31 * (size_t)c->nchunks));
     }
     c->mae_blocks = c->num_sms * 8;
+    if (sizeof(float) * 4 * (size_t)c->C4 > (48u << 10))  // weights in shared memory: opt in above 48 KB
+      CUDA_TRY(cudaFuncSetAttribute((const void*)b200sgd::sgd_mae_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)(sizeof(float) * 4 * (size_t)c->C4)));
     CUDA_TRY(cudaMalloc(&c->d_mae, sizeof(double) * c->mae_blocks));
     if (c->cfg.nranks > 1) {
       c->xchg_bytes = sizeof(uint4) * 2 * 2 * (size_t)c->cfg.nranks * (((size_t)c->C4 + 3) & ~(size_t)3);
@@ -881,9 +904,9 @@ int sgd_get_config(const sgd_ctx* c, sgd_config* out) {
   out->engine = c->engine;
   out->batch = c->B;
   out->reserved[0] = c->nb;
-  out->reserved[1] = c->ntiles * c->kc.NW * c->kc.U;
+  out->reserved[1] = c->ntiles * c->tile_rows;
   out->reserved[2] = (int32_t)c->smem_bytes;
-  out->reserved[3] = c->kc.KC;
+  out->reserved[3] = c->kc.wide ? -c->kc.KC : c->kc.KC;  // negative: column mapping
   out->reserved[4] = c->kc.U;
   out->reserved[5] = c->kc.NW;
   out->reserved[6] = (int32_t)c->ld;

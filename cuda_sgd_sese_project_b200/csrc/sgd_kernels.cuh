@@ -64,6 +64,7 @@ struct EpochParams {
   int32_t reduce_mode;      // 1 = ALLGATHER, 2 = SCATTER
   int32_t ntiles;           // ring tiles (power of two), each NW*U row slots
   int32_t tile_log2;
+  int32_t tile_rows;        // rows per ring tile (column mapping only; NW*U otherwise)
   uint32_t slot_bytes;      // ld * 4
   int32_t nprod;            // producer warps (1..kMaxProducerWarps); block = 32 * (NW + nprod)
   // DATAFLOW reduction (reduce_mode 3): tagged 8-byte words instead of barriers, see ll_store_f4
@@ -383,24 +384,31 @@ __device__ __forceinline__ float4 tree_sum_sources(const float4* src, int64_t st
 //   U  = rows a warp processes concurrently (independent chains hide the shuffle latency)
 //   NW = consumer warps; warp NW is the producer.  Block = 32*(NW+1) threads, 1 CTA per SM.
 // ------------------------------------------------------------------------------------------------
-template <int KC, int NW>
+//   WIDE = false ("row" mapping): a warp keeps a whole row and a full-width gradient in registers
+//          (KC float4 per lane, C <= 128*KC); the warps' gradients are combined through `gred`.
+//   WIDE = true ("column" mapping, any C up to 1024*KC): per ring tile, phase A = one warp per row
+//          computes the residual (row and weights read from shared memory), CTA barrier, phase B =
+//          thread t accumulates r * x for ITS float4 columns t, t+kCT, ... over all rows of the tile
+//          (KC float4 of gradient per thread).  No cross-warp gradient scratch, so the ring is
+//          deeper; the staged row is read from shared memory twice instead of once.
+template <int KC, int NW, bool WIDE>
 struct EpochSmem {
   static constexpr size_t kBarBytes = 2 * kMaxTiles * sizeof(uint64_t);
-  static constexpr size_t kWBytes = 32 * KC * sizeof(float4);
-  static constexpr size_t kGredBytes = (size_t)NW * 32 * KC * sizeof(float4);
+  static constexpr size_t kWBytes = (WIDE ? (size_t)32 * NW * KC : (size_t)32 * KC) * sizeof(float4);
+  static constexpr size_t kGredBytes = WIDE ? 2 * 32 * sizeof(float) : (size_t)NW * 32 * KC * sizeof(float4);
   static constexpr size_t kFixed = kBarBytes + kWBytes + kGredBytes;
 };
 
-template <int KC, int U, int NW>
+template <int KC, int U, int NW, bool WIDE = false>
 __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1) sgd_epoch_kernel(const EpochParams p) {
   const int kThreads = blockDim.x;  // 32 * (NW + p.nprod)
   constexpr int kCT = 32 * NW;  // consumer threads
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw);
   uint64_t* empty_bar = full_bar + kMaxTiles;
-  float4* w_s = reinterpret_cast<float4*>(smem_raw + EpochSmem<KC, NW>::kBarBytes);
-  float4* gred = w_s + 32 * KC;
-  unsigned char* ring = smem_raw + EpochSmem<KC, NW>::kFixed;
+  float4* w_s = reinterpret_cast<float4*>(smem_raw + EpochSmem<KC, NW, WIDE>::kBarBytes);
+  float4* gred = w_s + (WIDE ? 32 * NW * KC : 32 * KC);  // WIDE: float r_s[2][32] lives here instead
+  unsigned char* ring = smem_raw + EpochSmem<KC, NW, WIDE>::kFixed;
   __shared__ float4 xred[NW];  // cross-warp scratch of ll_gather
 
   const int tid = threadIdx.x;
@@ -408,8 +416,11 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1) sgd_epoch_ke
   const int lane = tid & 31;
   const int cta = blockIdx.x;
   const int G = gridDim.x;
-  constexpr int TR = NW * U;  // rows per ring tile = rows of one producer round
-  static_assert(TR <= 32, "a producer round is one warp instruction: at most 32 rows per tile");
+  // rows per ring tile = rows of one producer round: NW*U in the row mapping, chosen by the host
+  // (as many as fit, rows can be tens of KB) in the column mapping
+  constexpr int TRc = NW * U;
+  static_assert(TRc <= 32, "a producer round is one warp instruction: at most 32 rows per tile");
+  const int TR = WIDE ? p.tile_rows : TRc;
   const int ntiles = p.ntiles;
   const uint32_t tile_mask = (uint32_t)ntiles - 1u;
   const uint32_t tile_bytes = (uint32_t)TR * p.slot_bytes;
@@ -440,7 +451,7 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1) sgd_epoch_ke
     fence_barrier_init();
   }
   // weights -> shared (zero beyond C so that the label / pad columns never contribute)
-  for (int c = tid; c < 128 * KC; c += kThreads)
+  for (int c = tid; c < (WIDE ? 128 * NW * KC : 128 * KC); c += kThreads)
     reinterpret_cast<float*>(w_s)[c] = (c < p.C) ? p.w[c] : 0.0f;
   __syncthreads();
 
@@ -621,88 +632,157 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1) sgd_epoch_ke
 #pragma unroll
     for (int k = 0; k < KC; ++k) g[k] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-    // ---- rows of this step, one ring tile (= producer round) at a time: consumer warp cw
-    // takes rows cw, cw+NW, ... of the tile, all U of them concurrently ----
-    const int n32 = (int)n;  // rows of one CTA in one step always fit 32 bits
-    const int nt = (n32 + TR - 1) / TR;
-    for (int ti = 0; ti < nt; ++ti) {
-      const uint32_t tq = tqbase + (uint32_t)ti;
-      const uint32_t tile = tq & tile_mask;
-      const uint32_t use = tq >> p.tile_log2;
-      const int cnt = (n32 - ti * TR) < TR ? (n32 - ti * TR) : TR;
-      const unsigned char* tbase = ring + (size_t)tile * tile_bytes;
-      float4 x[U][KC];
-      float dot[U], y[U];
-      mbar_wait(full0 + 8u * tile, use & 1u);  // all rows of the tile have landed
+    const int n32w = (int)n;
+    if constexpr (WIDE) {
+      // ---- column mapping: phase A residuals, CTA barrier, phase B gradient columns ----
+      float* r_s = reinterpret_cast<float*>(gred);  // [2][32]
+      const int ntw = (n32w + TR - 1) / TR;
+      for (int ti = 0; ti < ntw; ++ti) {
+        const uint32_t tq = tqbase + (uint32_t)ti;
+        const uint32_t tile = tq & tile_mask;
+        const uint32_t use = tq >> p.tile_log2;
+        const int cnt = (n32w - ti * TR) < TR ? (n32w - ti * TR) : TR;
+        const unsigned char* tbase = ring + (size_t)tile * tile_bytes;
+        float* rbuf = r_s + (tq & 1u) * 32;
+        mbar_wait(full0 + 8u * tile, use & 1u);
+        // phase A: warp cw takes rows cw, cw+NW, ... of the tile
+        for (int r = cw; r < cnt; r += NW) {
+          {
+            const float4* row = reinterpret_cast<const float4*>(tbase + (size_t)r * p.slot_bytes);
+            float dot = 0.f;
+            for (int f = lane; f < C4; f += 32) {
+              const float4 xv = row[f];
+              const float4 wv = w_s[f];
+              dot = fmaf(xv.x, wv.x, dot);
+              dot = fmaf(xv.y, wv.y, dot);
+              dot = fmaf(xv.z, wv.z, dot);
+              dot = fmaf(xv.w, wv.w, dot);
+            }
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int r = cw + u * NW;
-        dot[u] = 0.f;
-        y[u] = 0.f;
-        if (r < cnt) {  // warp-uniform
+            for (int m = 16; m >= 1; m >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, m);
+            if (lane == 0) {
+              const float res = dot - reinterpret_cast<const float*>(row)[p.C];  // sgd_thrust.cu:43-48
+              rbuf[r] = res;
+              if (p.r_out != nullptr) p.r_out[off + lo + (int64_t)ti * TR + r] = res;
+            }
+          }
+        }
+        consumer_bar<kCT>();
+        // phase B: thread ctid owns float4 columns ctid, ctid + kCT, ...
+        for (int r = 0; r < cnt; ++r) {
+          const float res = rbuf[r];
           const float4* row = reinterpret_cast<const float4*>(tbase + (size_t)r * p.slot_bytes);
 #pragma unroll
           for (int k = 0; k < KC; ++k) {
-            const int f = k * 32 + lane;
-            x[u][k] = (f < C4) ? row[f] : make_float4(0.f, 0.f, 0.f, 0.f);
+            const int f = ctid + k * kCT;
+            if (f < C4) {
+              const float4 xv = row[f];
+              g[k].x = fmaf(res, xv.x, g[k].x);
+              g[k].y = fmaf(res, xv.y, g[k].y);
+              g[k].z = fmaf(res, xv.z, g[k].z);
+              g[k].w = fmaf(res, xv.w, g[k].w);
+            }
           }
-          y[u] = reinterpret_cast<const float*>(row)[p.C];  // label rides in the record
-        } else {
-#pragma unroll
-          for (int k = 0; k < KC; ++k) x[u][k] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty0 + 8u * tile);  // this warp is done with the tile
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(empty0 + 8u * tile);  // my rows are in registers
-#pragma unroll
-      for (int k = 0; k < KC; ++k) {
-        const float4 wv = w_s[k * 32 + lane];
-#pragma unroll
+      tqbase += (uint32_t)ntw;
+    } else {
+      // ---- rows of this step, one ring tile (= producer round) at a time: consumer warp cw
+      // takes rows cw, cw+NW, ... of the tile, all U of them concurrently ----
+      const int n32 = (int)n;  // rows of one CTA in one step always fit 32 bits
+      const int nt = (n32 + TR - 1) / TR;
+      for (int ti = 0; ti < nt; ++ti) {
+        const uint32_t tq = tqbase + (uint32_t)ti;
+        const uint32_t tile = tq & tile_mask;
+        const uint32_t use = tq >> p.tile_log2;
+        const int cnt = (n32 - ti * TR) < TR ? (n32 - ti * TR) : TR;
+        const unsigned char* tbase = ring + (size_t)tile * tile_bytes;
+        float4 x[U][KC];
+        float dot[U], y[U];
+        mbar_wait(full0 + 8u * tile, use & 1u);  // all rows of the tile have landed
+  #pragma unroll
         for (int u = 0; u < U; ++u) {
-          dot[u] = fmaf(x[u][k].x, wv.x, dot[u]);
-          dot[u] = fmaf(x[u][k].y, wv.y, dot[u]);
-          dot[u] = fmaf(x[u][k].z, wv.z, dot[u]);
-          dot[u] = fmaf(x[u][k].w, wv.w, dot[u]);
+          const int r = cw + u * NW;
+          dot[u] = 0.f;
+          y[u] = 0.f;
+          if (r < cnt) {  // warp-uniform
+            const float4* row = reinterpret_cast<const float4*>(tbase + (size_t)r * p.slot_bytes);
+  #pragma unroll
+            for (int k = 0; k < KC; ++k) {
+              const int f = k * 32 + lane;
+              x[u][k] = (f < C4) ? row[f] : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            y[u] = reinterpret_cast<const float*>(row)[p.C];  // label rides in the record
+          } else {
+  #pragma unroll
+            for (int k = 0; k < KC; ++k) x[u][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
         }
-      }
-#pragma unroll
-      for (int m = 16; m >= 1; m >>= 1) {
-#pragma unroll
-        for (int u = 0; u < U; ++u) dot[u] += __shfl_xor_sync(0xffffffffu, dot[u], m);
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        // r = x.w - y   (sgd_thrust.cu:43-48; Sgemv with beta = -1, sgd_thrust.cu:352-364);
-        // rows beyond the tile have x = 0, y = 0 -> r = 0 and contribute nothing
-        const float r = dot[u] - y[u];
-#pragma unroll
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty0 + 8u * tile);  // my rows are in registers
+  #pragma unroll
         for (int k = 0; k < KC; ++k) {
-          g[k].x = fmaf(r, x[u][k].x, g[k].x);
-          g[k].y = fmaf(r, x[u][k].y, g[k].y);
-          g[k].z = fmaf(r, x[u][k].z, g[k].z);
-          g[k].w = fmaf(r, x[u][k].w, g[k].w);
+          const float4 wv = w_s[k * 32 + lane];
+  #pragma unroll
+          for (int u = 0; u < U; ++u) {
+            dot[u] = fmaf(x[u][k].x, wv.x, dot[u]);
+            dot[u] = fmaf(x[u][k].y, wv.y, dot[u]);
+            dot[u] = fmaf(x[u][k].z, wv.z, dot[u]);
+            dot[u] = fmaf(x[u][k].w, wv.w, dot[u]);
+          }
         }
-        if (p.r_out != nullptr && lane == 0) {
-          const int rr = cw + u * NW;
-          if (rr < cnt) p.r_out[off + lo + (int64_t)ti * TR + rr] = r;
+  #pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) {
+  #pragma unroll
+          for (int u = 0; u < U; ++u) dot[u] += __shfl_xor_sync(0xffffffffu, dot[u], m);
+        }
+  #pragma unroll
+        for (int u = 0; u < U; ++u) {
+          // r = x.w - y   (sgd_thrust.cu:43-48; Sgemv with beta = -1, sgd_thrust.cu:352-364);
+          // rows beyond the tile have x = 0, y = 0 -> r = 0 and contribute nothing
+          const float r = dot[u] - y[u];
+  #pragma unroll
+          for (int k = 0; k < KC; ++k) {
+            g[k].x = fmaf(r, x[u][k].x, g[k].x);
+            g[k].y = fmaf(r, x[u][k].y, g[k].y);
+            g[k].z = fmaf(r, x[u][k].z, g[k].z);
+            g[k].w = fmaf(r, x[u][k].w, g[k].w);
+          }
+          if (p.r_out != nullptr && lane == 0) {
+            const int rr = cw + u * NW;
+            if (rr < cnt) p.r_out[off + lo + (int64_t)ti * TR + rr] = r;
+          }
         }
       }
+      tqbase += (uint32_t)nt;
     }
-    tqbase += (uint32_t)nt;
     mark(0);  // rows of this step done (this warp)
 
-    // ---- CTA partial: fixed-order sum over the warps ----
+    // ---- CTA partial: fixed-order sum over the warps (row mapping); already per thread and
+    // per column in the column mapping: thread ctid holds float4 columns ctid + k*kCT ----
+    if constexpr (!WIDE) {
 #pragma unroll
-    for (int k = 0; k < KC; ++k) gred[(cw * KC + k) * 32 + lane] = g[k];
-    consumer_bar<kCT>();
+      for (int k = 0; k < KC; ++k) gred[(cw * KC + k) * 32 + lane] = g[k];
+      consumer_bar<kCT>();
+    }
     mark(1);  // all warps of the CTA done
     const int par = (first_step + s) & 1;
     auto cta_partial = [&](int f) -> float4 {
-      const int k = f >> 5, l = f & 31;
-      float4 acc = gred[(0 * KC + k) * 32 + l];
+      if constexpr (WIDE) {
+        float4 acc = g[0];  // f == ctid + k*kCT for the calling thread (publish loops stride by kCT)
 #pragma unroll
-      for (int wq = 1; wq < NW; ++wq) acc = f4_add(acc, gred[(wq * KC + k) * 32 + l]);
-      return acc;
+        for (int k = 1; k < KC; ++k)
+          if (f == ctid + k * kCT) acc = g[k];
+        return acc;
+      } else {
+        const int k = f >> 5, l = f & 31;
+        float4 acc = gred[(0 * KC + k) * 32 + l];
+#pragma unroll
+        for (int wq = 1; wq < NW; ++wq) acc = f4_add(acc, gred[(wq * KC + k) * 32 + l]);
+        return acc;
+      }
     };
     if (G == 1 && p.nranks == 1) {
       // single CTA (tiny batches): the CTA partial is the gradient; nothing leaves the SM

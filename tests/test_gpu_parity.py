@@ -142,6 +142,27 @@ def test_feature_counts(C):
     check_run(X, y, 250, 0.02, 2)
 
 
+@pytest.mark.parametrize("C,B", [(2049, 250), (3000, 64), (4096, 600), (5000, 100), (8192, 33), (10000, 200), (16384, 50)])
+def test_wide_feature_counts_column_mapping(C, B):
+    # the reference's feature-scaling experiments go up to 10000 features (results/2000f-10000f-*)
+    X, y, _ = make_regression(600, C, seed=C)
+    check_run(X, y, B, 0.002, 2)
+
+
+def test_more_than_16384_features_is_rejected():
+    with pytest.raises(pkg.SgdError) as ei:
+        pkg.SGDEngine(100, 16385, 10, 0.1)
+    assert ei.value.code == _lib.SGD_ERR_ARG
+
+
+def test_column_mapping_equals_row_mapping_at_2048(monkeypatch):
+    X, y, _ = make_regression(3000, 2048, seed=5)
+    w_row, _ = check_run(X, y, 500, 0.01, 2)
+    monkeypatch.setenv("B200SGD_VARIANT", "3")
+    w_col, _ = check_run(X, y, 500, 0.01, 2)
+    assert rel_l2(w_col, w_row) < 1e-5
+
+
 @pytest.mark.parametrize("R,B", [(1, 0), (2, 1), (7, 7), (1000, 1), (1000, 3), (1000, 999), (1000, 1000),
                                  (1000, 0), (4097, 64), (5000, 4096), (300, 301 - 1)])
 def test_batch_shapes(R, B):

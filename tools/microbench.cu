@@ -199,6 +199,61 @@ __global__ void push_kernel(uint4* inbox, int words, int iters, long long* cycle
   if (cta == 0 && t == 0) *cycles = clock64() - t0;
 }
 
+// cluster all-gather through distributed shared memory: every CTA of a cluster writes `words`
+// float4 into its slot of every peer's shared memory (st.shared::cluster), then one cluster barrier
+// (arrive.release / wait.acquire); second variant adds the L2 exchange among cluster leaders
+// (tagged words, all leaders gather all leaders) and a DSMEM broadcast of the result.
+template <int CS>
+__global__ void __cluster_dims__(CS, 1, 1) cluster_allgather_kernel(int words, int iters, int cross, uint4* lead_buf,
+                                                                    long long* cycles) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ float4 slots[];  // [2 parity][CS][words] + [words] result
+  const int t = threadIdx.x, rank = cluster.block_rank();
+  const int nclusters = gridDim.x / CS, cid = blockIdx.x / CS;
+  float4* result = slots + 2 * CS * words;
+  long long t0 = clock64();
+  for (int it = 1; it <= iters; ++it) {
+    float4* base = slots + (size_t)(it & 1) * CS * words;
+    // push my words to every peer (including myself)
+    for (int i = t; i < CS * words; i += blockDim.x) {
+      const int dst = i / words, w = i - dst * words;
+      float4* remote = cluster.map_shared_rank(base + (size_t)rank * words + w, dst);
+      *remote = make_float4((float)it, (float)rank, (float)w, 1.f);
+    }
+    cluster.sync();
+    float4 acc = make_float4(0, 0, 0, 0);
+    if (t < words)
+      for (int r = 0; r < CS; ++r) {
+        const float4 v = base[(size_t)r * words + t];
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+    if (cross) {
+      const unsigned tag = (unsigned)it;
+      uint4* buf = lead_buf + (size_t)(it & 1) * 64 * 64;
+      if (rank == 0 && t < words)  // leader publishes the cluster sum
+        st_u4(buf + (size_t)cid * 64 + t, make_uint4(__float_as_uint(acc.x), tag, __float_as_uint(acc.y), tag));
+      if (rank == 0) {             // every leader gathers all leaders
+        float s = 0.f;
+        for (int i = t; i < nclusters * words; i += blockDim.x) {
+          const int c = i / words, w = i - c * words;
+          uint4 v;
+          do { v = ld_u4(buf + (size_t)c * 64 + w); } while (v.y != tag || v.w != tag);
+          s += __uint_as_float(v.x);
+        }
+        // broadcast to the cluster through DSMEM
+        if (t < words)
+          for (int dst = 0; dst < CS; ++dst) *cluster.map_shared_rank(result + t, dst) = make_float4(s, 0, 0, 0);
+      }
+      cluster.sync();
+      if (t < words && result[t].x == -1.f) cycles[1] = 1;
+    } else if (t < words && acc.x == -1.f) {
+      cycles[1] = 1;
+    }
+  }
+  if (blockIdx.x == 0 && t == 0) *cycles = clock64() - t0;
+}
+
 // ---- dependent-load latency and load overlap: one thread, lines written long ago by another SM
 template <int MODE>  // 0: ld.volatile  1: ld.global.cg (weak)  2: ld.relaxed.gpu
 __device__ __forceinline__ uint4 ld_mode(const uint4* p) {
@@ -314,6 +369,40 @@ int main() {
                     sleep_ns, (double)*cyc / iters);
       }
     }
+  }
+  // cluster / DSMEM all-gather
+  {
+    uint4* lb2;
+    CK(cudaMalloc(&lb2, 2 * 64 * 64 * 16));
+    const int words = 25;
+    auto run_cluster = [&](auto kern, int cs, int grid, int cross) {
+      CK(cudaMemset(lb2, 0, 2 * 64 * 64 * 16));
+      int it = 5000, w = words;
+      size_t smem = (size_t)(2 * cs * words + words) * sizeof(float4);
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(grid);
+      cfg.blockDim = dim3(256);
+      cfg.dynamicSmemBytes = smem;
+      cudaLaunchAttribute at[2];
+      at[0].id = cudaLaunchAttributeCooperative;
+      at[0].val.cooperative = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      cudaError_t e = cudaLaunchKernelEx(&cfg, kern, w, it, cross, lb2, cyc);
+      if (e != cudaSuccess) { std::printf("{\"test\": \"cluster\", \"cs\": %d, \"error\": \"%s\"}\n", cs, cudaGetErrorString(e)); cudaGetLastError(); return; }
+      CK(cudaDeviceSynchronize());
+      std::printf("{\"test\": \"cluster_allgather\", \"cluster_size\": %d, \"grid\": %d, \"cross_cluster_L2\": %d, \"words16B\": %d, \"cycles_per_iter\": %.1f}\n",
+                  cs, grid, cross, words, (double)*cyc / it);
+    };
+    run_cluster(cluster_allgather_kernel<2>, 2, 2, 0);
+    run_cluster(cluster_allgather_kernel<4>, 4, 4, 0);
+    run_cluster(cluster_allgather_kernel<8>, 8, 8, 0);
+    run_cluster(cluster_allgather_kernel<8>, 8, 32, 0);
+    run_cluster(cluster_allgather_kernel<8>, 8, 32, 1);
+    run_cluster(cluster_allgather_kernel<8>, 8, 144, 0);
+    run_cluster(cluster_allgather_kernel<8>, 8, 144, 1);
+    run_cluster(cluster_allgather_kernel<4>, 4, 148, 1);
+    run_cluster(cluster_allgather_kernel<2>, 2, 148, 1);
   }
   // push all-gather (one hop)
   {
