@@ -24,7 +24,7 @@ SGD_PEER_HANDLE_BYTES = 128
 EXPORTS = [
     "sgd_abi_version", "sgd_last_error", "sgd_device_count", "sgd_read_csv",
     "sgd_get_filename_from_path", "sgd_write_experiment_output", "sgd_init_weights",
-    "sgd_batch_geometry", "sgd_host_shuffle", "sgd_shard_range", "sgd_host_bucket", "sgd_get_local_schedule",
+    "sgd_batch_geometry", "sgd_host_shuffle", "sgd_shard_range", "sgd_host_bucket", "sgd_get_local_schedule", "sgd_get_loss_curve",
     "sgd_create", "sgd_destroy", "sgd_load_rows",
     "sgd_load_synthetic", "sgd_get_rows", "sgd_get_true_weights", "sgd_get_weights",
     "sgd_set_weights", "sgd_get_config", "sgd_local_rows", "sgd_local_row_begin", "sgd_shuffle",
@@ -88,6 +88,7 @@ def load() -> C.CDLL:
         "sgd_shard_range": ([i64, i32, i32, C.POINTER(i64), C.POINTER(i64)], C.c_int),
         "sgd_host_bucket": ([vp, i64, i32, i32, i32, vp, i64, vp], C.c_int),
         "sgd_get_local_schedule": ([vp, vp, i64, vp], C.c_int),
+        "sgd_get_loss_curve": ([vp, vp, vp, i32], C.c_int),
         "sgd_create": ([C.POINTER(SgdConfig), vp, vp, C.POINTER(vp)], C.c_int),
         "sgd_destroy": ([vp], None),
         "sgd_load_rows": ([vp, i64, i64, vp, vp], C.c_int),

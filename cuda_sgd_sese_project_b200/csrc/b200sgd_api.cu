@@ -56,6 +56,7 @@ double ms_since(clk::time_point t0) {
 
 constexpr size_t kMaxDynSmem = 232448;  // 227 KB: sm_100 per-CTA opt-in maximum
 constexpr int kGraphChunk = 256;        // step-kernel nodes per instantiated graph
+constexpr int kLossSlots = 64;          // epochs whose running loss can be in flight uncollected
 
 struct KernelChoice {
   int KC = 0, U = 0, NW = 0;
@@ -150,6 +151,10 @@ struct sgd_ctx {
   unsigned int* d_bar = nullptr;  // [0] barrier counter, [1] watchdog error word
   b200sgd::StepCtl* d_ctl = nullptr;
   unsigned long long* d_dbg = nullptr;  // phase profile, only with B200SGD_PHASE_PROFILE=1
+  double* d_loss = nullptr;             // [kLossSlots][grid][2] running-loss sums, one slot per epoch
+  int loss_pending = 0, loss_next = 0;  // epochs launched but not collected; next slot
+  std::vector<double> curve_abs, curve_sq;  // per-epoch mean |r| and 0.5 * mean r^2 (this rank's rows)
+  std::vector<int64_t> curve_rows;
   double* d_mae = nullptr;
   int mae_blocks = 0;
 
@@ -220,7 +225,7 @@ void free_all(sgd_ctx* c) {
   cudaFree(c->d_perm[0]); cudaFree(c->d_perm[1]); cudaFree(c->d_perm_local);
   cudaFree(c->d_step_off); cudaFree(c->d_counts); cudaFree(c->d_partials); cudaFree(c->d_wstage);
   cudaFree(c->d_glast); cudaFree(c->d_rout); cudaFree(c->d_bar); cudaFree(c->d_ctl);
-  cudaFree(c->d_ll_part); cudaFree(c->d_ll_w); cudaFree(c->d_dbg);
+  cudaFree(c->d_ll_part); cudaFree(c->d_ll_w); cudaFree(c->d_dbg); cudaFree(c->d_loss);
   cudaFree(c->d_tgt); cudaFree(c->d_cnt); cudaFree(c->d_start); cudaFree(c->d_hits); cudaFree(c->d_first);
   cudaFree(c->d_tilesum); cudaFree(c->d_states);
   if (c->h_states[0]) cudaFreeHost(c->h_states[0]);
@@ -405,6 +410,13 @@ int launch_epoch(sgd_ctx* c, int32_t epoch, int buf, int* launches) {
     p.ll_inbox_local = (uint4*)c->d_xchg_block;
     for (int r = 0; r < c->cfg.nranks; ++r) p.ll_inbox_peer[r] = (uint4*)c->peer_block[r];
   }
+  // running-loss slot of this epoch (collected after the next host sync)
+  if (c->loss_pending >= kLossSlots) return fail(SGD_ERR_STATE, "too many epochs in flight without a host sync");
+  double* loss_slot = c->d_loss + (size_t)c->loss_next * 2 * c->grid;
+  CUDA_TRY(cudaMemsetAsync(loss_slot, 0, sizeof(double) * 2 * (size_t)c->grid, c->stream));
+  p.loss = loss_slot;
+  c->loss_next = (c->loss_next + 1) % kLossSlots;
+  c->loss_pending += 1;
   if (c->engine == SGD_ENGINE_GRAPH) {
     SGD_TRY(build_graph(c));
     // per-epoch state of the parameter-free nodes: {perm, a, step = 0, nb}; bar_base keeps counting
@@ -413,6 +425,7 @@ int launch_epoch(sgd_ctx* c, int32_t epoch, int buf, int* launches) {
     head.a = p.a;
     head.step = 0;
     head.nb_total = c->nb;
+    head.loss = loss_slot;
     CUDA_TRY(cudaMemcpyAsync(c->d_ctl, &head, offsetof(b200sgd::StepCtl, bar_base), cudaMemcpyHostToDevice, c->stream));
     const int replays = (c->nb + c->graph_nodes - 1) / c->graph_nodes;
     for (int i = 0; i < replays; ++i) CUDA_TRY(cudaGraphLaunch(c->graph_exec, c->stream));
@@ -475,6 +488,28 @@ int sync_host_ind(sgd_ctx* c) {  // bring h_ind up to date after device shuffles
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   CUDA_TRY(cudaMemcpy(c->h_ind.data(), c->d_perm[c->cur], sizeof(int32_t) * (size_t)c->R, cudaMemcpyDeviceToHost));
   c->host_ind_stale = false;
+  return SGD_OK;
+}
+
+// After a host sync: fold the running-loss sums of the epochs launched since the last collection
+// into the per-epoch curve (mean |r| and 0.5 * mean r^2 over the rows this rank processed).
+int collect_losses(sgd_ctx* c) {
+  if (c->loss_pending == 0) return SGD_OK;
+  std::vector<double> h((size_t)2 * c->grid);
+  const int64_t rows_epoch = c->cfg.nranks > 1 ? -1 : (int64_t)c->nb * c->B;
+  for (int k = c->loss_pending; k >= 1; --k) {
+    const int slot = ((c->loss_next - k) % kLossSlots + kLossSlots) % kLossSlots;
+    CUDA_TRY(cudaMemcpy(h.data(), c->d_loss + (size_t)slot * 2 * c->grid, sizeof(double) * h.size(), cudaMemcpyDeviceToHost));
+    double a = 0.0, b = 0.0;
+    for (int g = 0; g < c->grid; ++g) {
+      a += h[2 * (size_t)g];
+      b += h[2 * (size_t)g + 1];
+    }
+    c->curve_abs.push_back(a);
+    c->curve_sq.push_back(b);
+    c->curve_rows.push_back(rows_epoch);
+  }
+  c->loss_pending = 0;
   return SGD_OK;
 }
 
@@ -714,6 +749,7 @@ int sgd_create(const sgd_config* cfg, const float* X, const float* y, sgd_ctx** 
       CUDA_TRY(cudaMalloc(&c->d_dbg, sizeof(unsigned long long) * 16 * (size_t)c->grid));
       CUDA_TRY(cudaMemset(c->d_dbg, 0, sizeof(unsigned long long) * 16 * (size_t)c->grid));
     }
+    CUDA_TRY(cudaMalloc(&c->d_loss, sizeof(double) * 2 * (size_t)c->grid * kLossSlots));
     CUDA_TRY(cudaMalloc(&c->d_ctl, sizeof(b200sgd::StepCtl)));
     CUDA_TRY(cudaMemset(c->d_ctl, 0, sizeof(b200sgd::StepCtl)));
     if (c->cfg.flags & SGD_FLAG_RESIDUALS) {
@@ -1000,6 +1036,7 @@ int sgd_epoch(sgd_ctx* c, int32_t epoch, sgd_timings* out) {
   CUDA_TRY(cudaEventRecord(c->ev_done[c->cur], c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   SGD_TRY(check_watchdog(c));
+  SGD_TRY(collect_losses(c));
   float ms = 0.f;
   CUDA_TRY(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
   fill_timings(c, out, c->last_shuffle_ms, ms, launches + c->last_shuffle_launches, 1);
@@ -1071,11 +1108,16 @@ int sgd_run(sgd_ctx* c, int32_t first_epoch, int32_t num_epochs, sgd_timings* to
     };
     rc = enqueue();
     if (rc == SGD_OK && e + 1 < num_epochs) rc = stage_next();  // overlaps with the kernel above
+    if (rc == SGD_OK && c->loss_pending >= kLossSlots - 1) {      // very long runs: drain the loss slots
+      if (cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail(SGD_ERR_CUDA, "epoch loop failed");
+      if (rc == SGD_OK) rc = collect_losses(c);
+    }
   }
   cudaError_t se = cudaStreamSynchronize(c->stream);
   if (se == cudaSuccess) se = cudaStreamSynchronize(c->shuf_stream);
   if (rc == SGD_OK && se != cudaSuccess) rc = fail(SGD_ERR_CUDA, std::string("epoch loop: ") + cudaGetErrorString(se));
   if (rc == SGD_OK) rc = check_watchdog(c);
+  if (rc == SGD_OK) rc = collect_losses(c);
   float loop_ms = 0.f;
   if (rc == SGD_OK) {
     for (int e = 0; e < num_epochs; ++e) {
@@ -1131,6 +1173,18 @@ int sgd_mean_abs_error(sgd_ctx* c, float* mae_out, double* sum_out) {
   // sgd_thrust.cu:134: return error_sum / R
   if (mae_out) *mae_out = (float)(total / (double)(c->cfg.nranks > 1 ? std::max<int64_t>(1, c->local_rows) : c->R));
   return SGD_OK;
+}
+
+int sgd_get_loss_curve(sgd_ctx* c, double* sum_abs, double* sum_sq, int32_t max_epochs) {
+  SGD_TRY(check_ctx(c));
+  if (max_epochs < 0) return fail(SGD_ERR_ARG, "bad count");
+  const int n = (int)std::min<size_t>((size_t)max_epochs, c->curve_abs.size());
+  const size_t first = c->curve_abs.size() - (size_t)n;  // the most recent epochs
+  for (int i = 0; i < n; ++i) {
+    if (sum_abs) sum_abs[i] = c->curve_abs[first + i];
+    if (sum_sq) sum_sq[i] = c->curve_sq[first + i];
+  }
+  return n;
 }
 
 int sgd_get_local_schedule(sgd_ctx* c, int32_t* local_perm, int64_t local_cap, int64_t* step_off) {

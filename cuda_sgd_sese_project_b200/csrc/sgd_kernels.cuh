@@ -39,6 +39,7 @@ struct StepCtl {
   float a;              // step size of the running epoch
   int32_t step;         // next step to execute
   int32_t nb_total;     // steps per epoch; launches beyond it exit at once
+  double* loss;         // running-loss slot of the running epoch
   uint32_t bar_base;    // value of the grid-barrier counter when the next launch starts
   uint32_t tag_base;    // dataflow tags handed out so far (see ll_store_f4)
 };
@@ -78,6 +79,7 @@ struct EpochParams {
   uint4* ll_inbox_peer[8];  // the same buffer of every rank, mapped into this process (NVLink)
   StepCtl* ctl;             // GRAPH engine only (nullptr for the persistent engine)
   unsigned long long* dbg;  // optional [grid][8] per-phase cycle sums (sgd_debug_phase_cycles)
+  double* loss;             // [grid][2] per-CTA sums of |r| and r*r over the launch (running loss)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -561,6 +563,9 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1) sgd_epoch_ke
   unsigned int bar_count = 0;  // grid barriers passed so far
   uint32_t tqbase = 0;         // sequence number of the first round of the current step
   float4 g[KC];
+  // running training loss of the epoch (extension; the reference's squared_errors kernel,
+  // sgd_thrust.cu:56-74, is dead code): every residual is already in a register
+  double loss_abs = 0.0, loss_sq = 0.0;
 
   // w = a * (g / B) + w for one float4 column group (sgd_thrust.cu:269, main.cu:147-150 / :287-290)
   auto updated = [&](int f, float4 wv, float4 tot, float4* g_scaled) -> float4 {
@@ -663,6 +668,8 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1) sgd_epoch_ke
             if (lane == 0) {
               const float res = dot - reinterpret_cast<const float*>(row)[p.C];  // sgd_thrust.cu:43-48
               rbuf[r] = res;
+              loss_abs += (double)fabsf(res);
+              loss_sq += (double)res * (double)res;
               if (p.r_out != nullptr) p.r_out[off + lo + (int64_t)ti * TR + r] = res;
             }
           }
@@ -702,30 +709,30 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1) sgd_epoch_ke
         float4 x[U][KC];
         float dot[U], y[U];
         mbar_wait(full0 + 8u * tile, use & 1u);  // all rows of the tile have landed
-  #pragma unroll
+#pragma unroll
         for (int u = 0; u < U; ++u) {
           const int r = cw + u * NW;
           dot[u] = 0.f;
           y[u] = 0.f;
           if (r < cnt) {  // warp-uniform
             const float4* row = reinterpret_cast<const float4*>(tbase + (size_t)r * p.slot_bytes);
-  #pragma unroll
+#pragma unroll
             for (int k = 0; k < KC; ++k) {
               const int f = k * 32 + lane;
               x[u][k] = (f < C4) ? row[f] : make_float4(0.f, 0.f, 0.f, 0.f);
             }
             y[u] = reinterpret_cast<const float*>(row)[p.C];  // label rides in the record
           } else {
-  #pragma unroll
+#pragma unroll
             for (int k = 0; k < KC; ++k) x[u][k] = make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(empty0 + 8u * tile);  // my rows are in registers
-  #pragma unroll
+#pragma unroll
         for (int k = 0; k < KC; ++k) {
           const float4 wv = w_s[k * 32 + lane];
-  #pragma unroll
+#pragma unroll
           for (int u = 0; u < U; ++u) {
             dot[u] = fmaf(x[u][k].x, wv.x, dot[u]);
             dot[u] = fmaf(x[u][k].y, wv.y, dot[u]);
@@ -733,17 +740,19 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1) sgd_epoch_ke
             dot[u] = fmaf(x[u][k].w, wv.w, dot[u]);
           }
         }
-  #pragma unroll
+#pragma unroll
         for (int m = 16; m >= 1; m >>= 1) {
-  #pragma unroll
+#pragma unroll
           for (int u = 0; u < U; ++u) dot[u] += __shfl_xor_sync(0xffffffffu, dot[u], m);
         }
-  #pragma unroll
+#pragma unroll
         for (int u = 0; u < U; ++u) {
           // r = x.w - y   (sgd_thrust.cu:43-48; Sgemv with beta = -1, sgd_thrust.cu:352-364);
           // rows beyond the tile have x = 0, y = 0 -> r = 0 and contribute nothing
           const float r = dot[u] - y[u];
-  #pragma unroll
+          loss_abs += (double)fabsf(r);  // rows beyond the tile have r = 0
+          loss_sq += (double)r * (double)r;
+#pragma unroll
           for (int k = 0; k < KC; ++k) {
             g[k].x = fmaf(r, x[u][k].x, g[k].x);
             g[k].y = fmaf(r, x[u][k].y, g[k].y);
@@ -902,6 +911,25 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1) sgd_epoch_ke
 
   if (prof) {
     for (int i = 0; i < 8; ++i) p.dbg[(int64_t)cta * 8 + i] = ph[i];
+  }
+  double* const loss_out = (p.ctl != nullptr) ? p.ctl->loss : p.loss;
+  if (loss_out != nullptr) {  // lane 0 of every consumer warp holds that warp's sums
+    double* ls = reinterpret_cast<double*>(gred);
+    consumer_bar<kCT>();
+    if (lane == 0) {
+      ls[2 * cw] = loss_abs;
+      ls[2 * cw + 1] = loss_sq;
+    }
+    consumer_bar<kCT>();
+    if (ctid == 0) {
+      double a = 0.0, b = 0.0;
+      for (int wq = 0; wq < NW; ++wq) {
+        a += ls[2 * wq];
+        b += ls[2 * wq + 1];
+      }
+      loss_out[2 * cta] += a;  // accumulated over the launches of an epoch (graph engine: one per step)
+      loss_out[2 * cta + 1] += b;
+    }
   }
   // final weights back to global (every CTA holds the same bits; CTA 0 writes)
   if (cta == 0) {

@@ -255,6 +255,15 @@ class SGDEngine:
         L.check(L.load().sgd_mean_abs_error(self._h, None, C.byref(s)))
         return float(s.value)
 
+    def loss_curve(self, max_epochs: int = 1 << 20):
+        """(sum |r|, sum r^2) per executed epoch (most recent `max_epochs`), this rank's rows."""
+        a = np.zeros(min(max_epochs, 1 << 20), dtype=np.float64)
+        b = np.zeros_like(a)
+        n = L.load().sgd_get_loss_curve(self._h, _ptr(a), _ptr(b), a.shape[0])
+        if n < 0:
+            L.check(n)
+        return a[:n].copy(), b[:n].copy()
+
     def local_schedule(self):
         """nranks > 1: (local_perm, step_off) of the last executed epoch as built on the device."""
         local = np.empty(max(1, self.local_rows), dtype=np.int32)

@@ -182,6 +182,13 @@ int sgd_get_last_gradient(sgd_ctx* ctx, float* g);
  * ranks and divides by R); mae_out is sum/R_local... for nranks == 1 it is the reference's value */
 int sgd_mean_abs_error(sgd_ctx* ctx, float* mae_out, double* sum_out);
 
+/* Running training loss per epoch (extension: the reference's squared_errors kernel,
+ * sgd_thrust.cu:56-74, and its `errors` buffer, main.cu:406-407, are dead code).  For each of the
+ * most recent `max_epochs` executed epochs: sum_abs = sum over the rows this rank processed of |r|,
+ * sum_sq = sum of r*r, r = x.w - y with the weights the step used.  Divide by steps*B for the mean
+ * absolute error / twice the half-MSE (nranks > 1: add the ranks first).  Returns the count. */
+int sgd_get_loss_curve(sgd_ctx* ctx, double* sum_abs, double* sum_sq, int32_t max_epochs);
+
 /* nranks > 1: the bucketed schedule of the last executed epoch, as the device built it */
 int sgd_get_local_schedule(sgd_ctx* ctx, int32_t* local_perm, int64_t local_cap, int64_t* step_off);
 

@@ -221,6 +221,34 @@ def test_linearity_of_the_gradient():
     assert rel_l2(gs[0] + gs[1], gs[2]) < 1e-5
 
 
+def test_running_loss_curve_matches_oracle_residuals():
+    # extension: per-epoch sums of |r| and r^2 over the rows each step used
+    X, y, _ = make_regression(6000, 100, seed=21)
+    R, C, B, lr, epochs = 6000, 100, 500, 0.05, 3
+    g = orc.Rand()
+    ind = np.arange(R, dtype=np.int32)
+    w = orc.init_weights(C)
+    want_abs, want_sq = [], []
+    for e in range(1, epochs + 1):
+        g.shuffle(ind)
+        sa = ss = 0.0
+        a = orc.step_scale(lr, e)
+        for b in range(R // B):
+            rows = ind[b * B:(b + 1) * B]
+            r = orc.residuals(X, y, w, rows).astype(np.float64)
+            sa += np.abs(r).sum(); ss += (r * r).sum()
+            gvec = orc.gradient(X, r.astype(np.float32), float(B), rows)
+            w = (np.float32(a) * gvec + w).astype(np.float32)
+        want_abs.append(sa); want_sq.append(ss)
+    for engine in (_lib.SGD_ENGINE_PERSISTENT, _lib.SGD_ENGINE_GRAPH):
+        with pkg.SGDEngine(R, C, B, lr, data=X, labels=y, engine=engine) as eng:
+            eng.run(1, epochs)
+            got_abs, got_sq = eng.loss_curve()
+        assert got_abs.shape == (epochs,)
+        assert np.allclose(got_abs, want_abs, rtol=2e-4) and np.allclose(got_sq, want_sq, rtol=4e-4)
+        assert got_abs[0] > got_abs[-1]          # the loss goes down
+
+
 # ------------------------------------------------------------------ synthetic generator
 def test_synthetic_generator_properties_and_parity():
     R, C = 50000, 100
