@@ -188,8 +188,9 @@ struct sgd_ctx {
   int graph_nodes = 0;
 
   // multi-GPU
-  void* d_xchg_block = nullptr;  // inbox of tagged slice sums [2][nranks][C4][2] uint4
-  size_t xchg_bytes = 0;
+  void* d_xchg_block = nullptr;  // inbox of tagged slice sums [2][nranks][C4][2] uint4 | direct partials
+  size_t xchg_bytes = 0, xpart_off = 0;
+  bool direct = false;           // narrow rows: partials pushed straight to every rank's owners
   void* peer_block[8] = {nullptr};
   bool peer_open[8] = {false};
   bool peers_ready = false;
@@ -409,6 +410,11 @@ int launch_epoch(sgd_ctx* c, int32_t epoch, int buf, int* launches) {
     if (!c->peers_ready) return fail(SGD_ERR_STATE, "nranks > 1 but sgd_peer_ready was not called");
     p.ll_inbox_local = (uint4*)c->d_xchg_block;
     for (int r = 0; r < c->cfg.nranks; ++r) p.ll_inbox_peer[r] = (uint4*)c->peer_block[r];
+    p.direct = c->direct ? 1 : 0;
+    if (c->direct) {
+      p.ll_xpart_local = (uint4*)((char*)c->d_xchg_block + c->xpart_off);
+      for (int r = 0; r < c->cfg.nranks; ++r) p.ll_xpart_peer[r] = (uint4*)((char*)c->peer_block[r] + c->xpart_off);
+    }
   }
   // running-loss slot of this epoch (collected after the next host sync)
   if (c->loss_pending >= kLossSlots) return fail(SGD_ERR_STATE, "too many epochs in flight without a host sync");
@@ -786,6 +792,11 @@ int sgd_create(const sgd_config* cfg, const float* X, const float* y, sgd_ctx** 
     CUDA_TRY(cudaMalloc(&c->d_mae, sizeof(double) * c->mae_blocks));
     if (c->cfg.nranks > 1) {
       c->xchg_bytes = sizeof(uint4) * 2 * 2 * (size_t)c->cfg.nranks * (((size_t)c->C4 + 3) & ~(size_t)3);
+      // direct push of the partials when the NVLink traffic per step stays small (narrow rows)
+      const size_t push_bytes = (size_t)(c->cfg.nranks - 1) * c->grid * c->C4 * 32;
+      c->direct = (c->grid % 4 == 0) && push_bytes <= (1u << 20) && !std::getenv("B200SGD_NO_DIRECT");
+      c->xpart_off = (c->xchg_bytes + 255) / 256 * 256;
+      if (c->direct) c->xchg_bytes = c->xpart_off + sizeof(uint4) * 2 * 2 * (size_t)c->C4 * c->cfg.nranks * c->grid;
       CUDA_TRY(cudaMalloc(&c->d_xchg_block, c->xchg_bytes));
       CUDA_TRY(cudaMemset(c->d_xchg_block, 0, c->xchg_bytes));
       c->peer_block[c->cfg.rank] = c->d_xchg_block;

@@ -77,6 +77,11 @@ struct EpochParams {
   int32_t rank, nranks;
   uint4* ll_inbox_local;    // [2][nranks][C4][2] slice sums of every rank, written by the peers
   uint4* ll_inbox_peer[8];  // the same buffer of every rank, mapped into this process (NVLink)
+  // narrow rows: every CTA pushes its partial straight into every rank's copy of this array,
+  // [2][C4][nranks*grid] tagged float4; the column owner then gathers nranks*grid sources at once
+  int32_t direct;
+  uint4* ll_xpart_local;
+  uint4* ll_xpart_peer[8];
   StepCtl* ctl;             // GRAPH engine only (nullptr for the persistent engine)
   unsigned long long* dbg;  // optional [grid][8] per-phase cycle sums (sgd_debug_phase_cycles)
   double* loss;             // [grid][2] per-CTA sums of |r| and r*r over the launch (running loss)
@@ -591,8 +596,10 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1) sgd_epoch_ke
   const bool all_cols = (p.reduce_mode == 4 || p.reduce_mode == 1);
   const int ncol = all_cols ? C4 : nf;
   const int col0 = all_cols ? 0 : f0;
+  const bool direct = p.nranks > 1 && p.direct != 0;  // multi-GPU, narrow rows: one gather over all ranks
+  const int nsrc_gather = direct ? p.nranks * G : G;
   int gcap = 1;  // no point in more threads per column than there are sources
-  while (gcap < G) gcap <<= 1;
+  while (gcap < nsrc_gather) gcap <<= 1;
   int Q = 1;
   {
     const int qmax = (p.reduce_mode >= 3) ? kCT : 32;  // the barrier modes reduce inside a warp
@@ -813,7 +820,18 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1) sgd_epoch_ke
       // Column blocks and mailboxes are padded to whole 128-byte lines (Gp, C4p): two owners never
       // poll the same line (grids like 41 or 48 ran 1.5x slower than 32 or 64 without it).
       uint4* parts = p.ll_part + (int64_t)par * Gp * C4 * 2;
-      for (int f = ctid; f < C4; f += kCT) ll_store_f4(parts + ((int64_t)f * Gp + cta) * 2, cta_partial(f), tag);
+      if (direct) {
+        // multi-GPU, narrow rows: the partial goes straight to the column owners of EVERY rank
+        // (NVLink stores), one network hop instead of local gather + slice exchange
+        const int64_t xs = (int64_t)p.nranks * G;  // sources per column (G % 4 == 0 here: line aligned)
+        for (int f = ctid; f < C4; f += kCT) {
+          const float4 v = cta_partial(f);
+          const int64_t at = (((int64_t)par * C4 + f) * xs + (int64_t)p.rank * G + cta) * 2;
+          for (int pr = 0; pr < p.nranks; ++pr) ll_store_f4(p.ll_xpart_peer[pr] + at, v, tag);
+        }
+      } else {
+        for (int f = ctid; f < C4; f += kCT) ll_store_f4(parts + ((int64_t)f * Gp + cta) * 2, cta_partial(f), tag);
+      }
       mark(2);  // partial published
 
       if (p.reduce_mode == 4) {
@@ -846,9 +864,16 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1) sgd_epoch_ke
         // old weights are read before anything of this step is published (the mailbox poll below
         // overwrites w_s once the new ones arrive)
         const float4 w_old = active ? w_s[f] : make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 tot = ll_gather<kCT>(parts, 1, Gp, f, G, my_q, Q, active, tag, p.err, xred, ctid, poll_one_word);
+        float4 tot;
+        if (direct) {
+          const int64_t xs = (int64_t)p.nranks * G;
+          tot = ll_gather<kCT>(p.ll_xpart_local + (int64_t)par * C4 * xs * 2, 1, xs, f, (int)xs, my_q, Q, active, tag,
+                               p.err, xred, ctid, poll_one_word);
+        } else {
+          tot = ll_gather<kCT>(parts, 1, Gp, f, G, my_q, Q, active, tag, p.err, xred, ctid, poll_one_word);
+        }
         mark(3);  // (owners) partials gathered
-        if (p.nranks > 1) {  // uniform over the grid
+        if (p.nranks > 1 && !direct) {  // uniform over the grid
           const int64_t slot = ((int64_t)par * p.nranks) * C4p;
           if (active) {  // lane q writes the inboxes of ranks q, q+Q, ...: NVLink stores in parallel
             for (int pr = my_q; pr < p.nranks; pr += Q)
