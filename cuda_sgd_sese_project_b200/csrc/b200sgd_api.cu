@@ -260,6 +260,11 @@ int configure_launch(sgd_ctx* c) {
       // the same shape (some owners' polling then runs 2.5x late; cause not pinned down)
       grid = 1;
       while (grid * 2 <= 64 && (int64_t)grid * 2 * 24 <= rows_step) grid *= 2;
+    } else if (step_bytes < (400ll << 20) && c->num_sms >= 128) {
+      // 128 CTAs beat 148 until a step streams several hundred MB (C = 512, B = 8192: 7.3 vs 8.8 us;
+      // C = 2048, B = 4096: 13.6 vs 14.8 us; C = 2048, B = 65536: 94.6 vs 93.3 us): the gather tree
+      // of the tail is fully populated at a power of two
+      grid = 128;
     } else {
       grid = c->num_sms;
     }
