@@ -170,8 +170,8 @@ def reference_arm(args, cols, batch, lr):
                 for row, lab in zip(X, y):
                     f.write(",".join("%.9g" % v for v in row) + ",%.9g\n" % lab)
 
-            def run(epochs):
-                r = subprocess.run([ref, repr(lr), str(epochs), csv, str(sample_rows), str(cols), str(batch), "0"],
+            def run(epochs, cuda_run="0"):
+                r = subprocess.run([ref, repr(lr), str(epochs), csv, str(sample_rows), str(cols), str(batch), cuda_run],
                                    capture_output=True, text=True, cwd=tmp, timeout=1500)
                 if r.returncode != 0:
                     raise RuntimeError(r.stderr[-500:])
@@ -181,6 +181,14 @@ def reference_arm(args, cols, batch, lr):
                 t_all = run(W + K)
                 ms = max(t_all - t_w, 1e-6)
                 value = K * nb * batch / (ms * 1e-3)
+                # for the record: the reference's other code path (cudaRun = 1, plain CUDA kernel +
+                # Thrust), which on a B200 is the faster of the two (no cublasCreate per step)
+                try:
+                    ms1 = max(run(W + K, "1") - (run(W, "1") if W > 0 else 0.0), 1e-6)
+                    line["reference_plain_cuda_path"] = {"value": K * nb * batch / (ms1 * 1e-3), "unit": "samples/s",
+                                                         "ms_per_step": ms1 / K}
+                except Exception as ex:
+                    line["reference_plain_cuda_path"] = {"error": str(ex)[:120]}
                 line.update({"value": value, "ms_per_step": ms / K,
                              "cpu_baseline": {"value": value, "unit": "samples/s", "cores": 1, "kind": "reference",
                                               "sample": f"unmodified reference binary (cuBLAS code path, cudaRun=0) on the "

@@ -345,6 +345,10 @@ void fill_params(sgd_ctx* c, b200sgd::EpochParams* p, int32_t epoch, int buf) {
   p->tile_rows = c->tile_rows;
   p->slot_bytes = (uint32_t)(c->ld * 4);
   p->nprod = c->nprod;
+  {
+    const char* e = std::getenv("B200SGD_PREFETCH_STEPS");
+    p->prefetch_steps = e ? std::atoi(e) : 0;
+  }
   p->ll_part = c->d_ll_part;
   p->ll_w = c->d_ll_w;
   p->w_copies = c->w_copies;

@@ -67,6 +67,7 @@ struct EpochParams {
   int32_t tile_log2;
   int32_t tile_rows;        // rows per ring tile (column mapping only; NW*U otherwise)
   uint32_t slot_bytes;      // ld * 4
+  int32_t prefetch_steps;   // experiment: max steps the producer runs ahead (0 = whole ring)
   int32_t nprod;            // producer warps (1..kMaxProducerWarps); block = 32 * (NW + nprod)
   // DATAFLOW reduction (reduce_mode 3): tagged 8-byte words instead of barriers, see ll_store_f4
   uint4* ll_part;           // [grid][C4][2]  per-CTA partial gradients
@@ -417,6 +418,7 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1) sgd_epoch_ke
   float4* gred = w_s + (WIDE ? 32 * NW * KC : 32 * KC);  // WIDE: float r_s[2][32] lives here instead
   unsigned char* ring = smem_raw + EpochSmem<KC, NW, WIDE>::kFixed;
   __shared__ float4 xred[NW];  // cross-warp scratch of ll_gather
+  __shared__ volatile int steps_done;  // experiment switch (prefetch_steps): consumer progress
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -451,6 +453,7 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1) sgd_epoch_ke
   }
 
   if (tid == 0) {
+    steps_done = 0;
     for (int i = 0; i < ntiles; ++i) {
       mbar_init(full0 + 8u * i, 1);    // the producer's arrive.expect_tx; the rows complete the bytes
       mbar_init(empty0 + 8u * i, NW);  // every consumer warp releases every tile once
@@ -538,10 +541,16 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1) sgd_epoch_ke
       const int cur_cnt = cnt;
       const int32_t cur_idx = idx;
       const uint32_t cur_tq = tq;
+      const int cur_s = s;
       // move to my next round and get its indices in flight
       for (int k = 0; k < NP; ++k) advance();
       cnt = round_cnt();
       if (lane < cnt) idx = __ldg(perm + off + lo + j0 + lane);
+      // experiment: cap how many steps the producer may run ahead of the consumers (0 = unlimited)
+      if (p.prefetch_steps > 0) {
+        while (cur_s - steps_done >= p.prefetch_steps) {
+        }
+      }
       // issue the current round: wait for the tile, arm its barrier, one TMA bulk copy per row
       const uint32_t tile = cur_tq & tile_mask;
       const uint32_t use = cur_tq >> p.tile_log2;
@@ -630,6 +639,7 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1) sgd_epoch_ke
 
   for (int s = 0; s < p.nb; ++s) {
     cur_step = s;
+    if (ctid == 0) steps_done = s;  // all consumers have finished step s-1 (they passed its last barrier)
     int64_t off, lo, n;
     if (p.step_off == nullptr) {
       off = ((int64_t)first_step + s) * p.B;

@@ -45,7 +45,7 @@ typedef enum { SGD_PATH_CUBLAS = 0, SGD_PATH_PLAIN_CUDA = 1, SGD_PATH_LVL1 = 2 }
 /* How the sequential step chain is executed. */
 typedef enum {
   SGD_ENGINE_AUTO = 0,
-  SGD_ENGINE_PERSISTENT = 1, /* one cooperative launch per epoch, grid barrier per step         */
+  SGD_ENGINE_PERSISTENT = 1, /* one cooperative launch per epoch, steps chained inside (default) */
   SGD_ENGINE_GRAPH = 2       /* one fused kernel per step, steps captured in a CUDA graph       */
 } sgd_engine;
 
@@ -178,8 +178,9 @@ int sgd_get_residuals(sgd_ctx* ctx, float* r, int64_t count);
  * (sgd_thrust.cu:276-291) leaves in col_sums / main.cu:133 in row_sums */
 int sgd_get_last_gradient(sgd_ctx* ctx, float* g);
 /* replaces calculate_mean_abs_error_cublas (sgd_thrust.cu:79-135, call main.cu:525-530).
- * With nranks > 1 it returns this rank's SUM of absolute errors in *sum_out (the caller adds the
- * ranks and divides by R); mae_out is sum/R_local... for nranks == 1 it is the reference's value */
+ * sum_out (optional) receives the SUM of absolute errors over this rank's rows: with nranks > 1
+ * the caller adds the ranks' sums and divides by R.  mae_out (optional) is sum / R for nranks == 1
+ * (the reference's value, sgd_thrust.cu:134) and sum / local rows otherwise. */
 int sgd_mean_abs_error(sgd_ctx* ctx, float* mae_out, double* sum_out);
 
 /* Running training loss per epoch (extension: the reference's squared_errors kernel,
