@@ -88,6 +88,7 @@ bool choose_kernel(int C4, int64_t rows_per_cta, KernelChoice* out) {
   if (C4 <= 32) {
     if (rows_per_cta <= 8) *out = make_choice<1, 1, 8>();
     else if (rows_per_cta <= 16) *out = make_choice<1, 2, 8>();
+    else if (rows_per_cta <= 32) *out = make_choice<1, 4, 8>();  // 4 % faster than <1,2,16> at config 2
     else *out = make_choice<1, 2, 16>();
   } else if (C4 <= 64) {
     if (rows_per_cta <= 8) *out = make_choice<2, 1, 8>();
