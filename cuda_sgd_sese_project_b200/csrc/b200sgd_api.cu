@@ -10,6 +10,7 @@
 // No Thrust, no cuBLAS, no CPU fallback: every compute entry point needs an sm_100 device.
 #include "b200sgd.h"
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -60,17 +61,18 @@ constexpr int kLossSlots = 64;          // epochs whose running loss can be in f
 
 struct KernelChoice {
   int KC = 0, U = 0, NW = 0;
-  bool wide = false;
+  bool wide = false, narrow8 = false;
   const void* fn = nullptr;
   size_t fixed_smem = 0;
 };
 
-template <int KC, int U, int NW, bool WIDE = false>
+template <int KC, int U, int NW, bool WIDE = false, bool NARROW8 = false>
 KernelChoice make_choice() {
   KernelChoice k;
   k.KC = KC; k.U = U; k.NW = NW;
   k.wide = WIDE;
-  k.fn = (const void*)b200sgd::sgd_epoch_kernel<KC, U, NW, WIDE>;
+  k.narrow8 = NARROW8;
+  k.fn = (const void*)b200sgd::sgd_epoch_kernel<KC, U, NW, WIDE, NARROW8>;
   k.fixed_smem = b200sgd::EpochSmem<KC, NW, WIDE>::kFixed;
   return k;
 }
@@ -88,8 +90,8 @@ bool choose_kernel(int C4, int64_t rows_per_cta, KernelChoice* out) {
   if (C4 <= 32) {
     if (rows_per_cta <= 8) *out = make_choice<1, 1, 8>();
     else if (rows_per_cta <= 16) *out = make_choice<1, 2, 8>();
-    else if (rows_per_cta <= 32) *out = make_choice<1, 4, 8>();  // 4 % faster than <1,2,16> at config 2
-    else *out = make_choice<1, 2, 16>();
+    else if (variant_env() == 5) *out = rows_per_cta <= 32 ? make_choice<1, 4, 8>() : make_choice<1, 2, 16>();
+    else *out = make_choice<1, 4, 8, false, true>();  // 8 lanes per row, 4 rows per warp
   } else if (C4 <= 64) {
     if (rows_per_cta <= 8) *out = make_choice<2, 1, 8>();
     else if (rows_per_cta <= 16) *out = make_choice<2, 2, 8>();
@@ -182,6 +184,8 @@ struct sgd_ctx {
   // kernel configuration
   KernelChoice kc{};
   int grid = 0, reduce_mode = 0, ntiles = 0, tile_log2 = 0, engine = SGD_ENGINE_PERSISTENT;
+  CUtensorMap rec_map{};
+  bool use_gather4 = false;  // narrow rows: TMA tile::gather4, four rows per instruction
   int nprod = 1;  // producer warps
   int tile_rows = 0;
   size_t smem_bytes = 0;
@@ -320,8 +324,37 @@ int configure_launch(sgd_ctx* c) {
   return SGD_OK;
 }
 
+// 2-D tensor map of the records for tile::gather4 (rows of at most 256 floats).  The driver entry
+// point is resolved at run time, so the library does not link libcuda.
+int make_record_tensor_map(sgd_ctx* c) {
+  c->use_gather4 = false;
+  if (c->ld > 256 || c->local_rows < 1 || std::getenv("B200SGD_NO_GATHER4")) return SGD_OK;
+  if ((c->kc.NW * c->kc.U) % 4 != 0 || c->kc.wide) return SGD_OK;
+  typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+      qres != cudaDriverEntryPointSuccess) {
+    cudaGetLastError();
+    return SGD_OK;  // per-row bulk copies still work
+  }
+  const cuuint64_t gdim[2] = {(cuuint64_t)c->ld, (cuuint64_t)c->local_rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)c->ld * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)c->ld, 1};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = ((encode_fn)fn)(&c->rec_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, c->d_rec, gdim, gstride, box, estr,
+                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                     CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  c->use_gather4 = (r == CUDA_SUCCESS);
+  return SGD_OK;
+}
+
 void fill_params(sgd_ctx* c, b200sgd::EpochParams* p, int32_t epoch, int buf) {
   std::memset(p, 0, sizeof(*p));
+  p->rec_map = c->rec_map;
+  p->use_gather4 = c->use_gather4 ? 1 : 0;
   p->rec = c->d_rec;
   p->ld = c->ld;
   p->C = c->C;
@@ -735,6 +768,7 @@ int sgd_create(const sgd_config* cfg, const float* X, const float* y, sgd_ctx** 
       cudaGetLastError();
       return fail(SGD_ERR_NOMEM, "cannot allocate " + std::to_string(rec_bytes >> 20) + " MiB of HBM for the data");
     }
+    SGD_TRY(make_record_tensor_map(c));
     CUDA_TRY(cudaMalloc(&c->d_w, sizeof(float) * c->C));
     CUDA_TRY(cudaMalloc(&c->d_wtrue, sizeof(float) * c->C));
     for (int i = 0; i < 2; ++i) {
@@ -966,7 +1000,7 @@ int sgd_get_config(const sgd_ctx* c, sgd_config* out) {
   out->reserved[1] = c->ntiles * c->tile_rows;
   out->reserved[2] = (int32_t)c->smem_bytes;
   out->reserved[3] = c->kc.wide ? -c->kc.KC : c->kc.KC;  // negative: column mapping
-  out->reserved[4] = c->kc.U;
+  out->reserved[4] = c->kc.narrow8 ? -c->kc.U : c->kc.U;  // negative: 8 lanes per row
   out->reserved[5] = c->kc.NW;
   out->reserved[6] = (int32_t)c->ld;
   return SGD_OK;

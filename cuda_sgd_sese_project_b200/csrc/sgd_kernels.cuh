@@ -22,6 +22,7 @@
 // Record layout in HBM: row i = [x_0 .. x_{C-1}, y_i, 0-pad] with a leading dimension of
 // ld = roundup(C+1, 16) floats, so a row is a whole number of 64-byte HBM bursts and carries its label.
 #pragma once
+#include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -45,6 +46,11 @@ struct StepCtl {
 };
 
 struct EpochParams {
+  // TMA descriptor of the record array as a 2-D tensor {ld, local rows}, box {ld, 1}: narrow rows
+  // (ld <= 256 floats) are fetched four at a time with tile::gather4.  Must stay the first member
+  // (64-byte alignment inside the __grid_constant__ kernel parameter).
+  CUtensorMap rec_map;
+  int32_t use_gather4;
   const float* rec;         // records, ld floats each
   int64_t ld;               // floats per record (multiple of 16)
   int32_t C;                // features
@@ -140,6 +146,15 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
           "r"(dst),
       "l"(src), "r"(bytes), "r"(bar)
+      : "memory");
+}
+// four rows (arbitrary row numbers) of a 2-D tensor -> four consecutive row slots, one instruction
+__device__ __forceinline__ void tma_gather4_g2s(uint32_t dst, const CUtensorMap* map, int32_t r0, int32_t r1,
+                                                int32_t r2, int32_t r3, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(0), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(bar)
       : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() {
@@ -407,8 +422,14 @@ struct EpochSmem {
   static constexpr size_t kFixed = kBarBytes + kWBytes + kGredBytes;
 };
 
-template <int KC, int U, int NW, bool WIDE = false>
-__global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1) sgd_epoch_kernel(const EpochParams p) {
+//   NARROW8 (row mapping, C <= 128, KC = 1, U = 4): a row occupies 8 lanes (4 float4 each) instead
+//          of a whole warp, so a warp handles 4 rows at once with a 3-level shuffle reduction; about
+//          2.5x fewer issued instructions per row than one row per warp (the row phase of narrow
+//          rows is issue-bound: ~100 instructions per 448-byte row otherwise).
+template <int KC, int U, int NW, bool WIDE = false, bool NARROW8 = false>
+__global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1)
+    sgd_epoch_kernel(const __grid_constant__ EpochParams p) {
+  static_assert(!NARROW8 || (KC == 1 && U == 4 && !WIDE), "NARROW8 is the <1,4,NW> row mapping");
   const int kThreads = blockDim.x;  // 32 * (NW + p.nprod)
   constexpr int kCT = 32 * NW;  // consumer threads
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -555,14 +576,34 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1) sgd_epoch_ke
       const uint32_t tile = cur_tq & tile_mask;
       const uint32_t use = cur_tq >> p.tile_log2;
       const uint32_t fb = full0 + 8u * tile;
-      if (lane == 0) {
-        mbar_wait_relaxed(empty0 + 8u * tile, (use & 1u) ^ 1u);  // passes at once on the first use
-        mbar_arrive_expect_tx(fb, (uint32_t)cur_cnt * p.slot_bytes);
+      if (p.use_gather4) {
+        // narrow rows: one tile::gather4 per four rows (lane l takes rows 4l..4l+3 of the round; a
+        // short last group repeats its first row into slots that nobody reads)
+        const int groups = (cur_cnt + 3) >> 2;
+        if (lane == 0) {
+          mbar_wait_relaxed(empty0 + 8u * tile, (use & 1u) ^ 1u);
+          mbar_arrive_expect_tx(fb, (uint32_t)groups * 4u * p.slot_bytes);
+        }
+        const int b4 = (lane << 2) & 31;
+        const int32_t r0 = __shfl_sync(0xffffffffu, cur_idx, b4);
+        int32_t r1 = __shfl_sync(0xffffffffu, cur_idx, (b4 + 1) & 31);
+        int32_t r2 = __shfl_sync(0xffffffffu, cur_idx, (b4 + 2) & 31);
+        int32_t r3 = __shfl_sync(0xffffffffu, cur_idx, (b4 + 3) & 31);
+        if (4 * lane + 1 >= cur_cnt) r1 = r0;
+        if (4 * lane + 2 >= cur_cnt) r2 = r0;
+        if (4 * lane + 3 >= cur_cnt) r3 = r0;
+        if (lane < groups)
+          tma_gather4_g2s(ring0 + tile * tile_bytes + (uint32_t)(4 * lane) * p.slot_bytes, &p.rec_map, r0, r1, r2, r3, fb);
+      } else {
+        if (lane == 0) {
+          mbar_wait_relaxed(empty0 + 8u * tile, (use & 1u) ^ 1u);  // passes at once on the first use
+          mbar_arrive_expect_tx(fb, (uint32_t)cur_cnt * p.slot_bytes);
+        }
+        __syncwarp();
+        if (lane < cur_cnt)
+          bulk_g2s(ring0 + tile * tile_bytes + (uint32_t)lane * p.slot_bytes, p.rec + (int64_t)cur_idx * p.ld,
+                   p.slot_bytes, fb);
       }
-      __syncwarp();
-      if (lane < cur_cnt)
-        bulk_g2s(ring0 + tile * tile_bytes + (uint32_t)lane * p.slot_bytes, p.rec + (int64_t)cur_idx * p.ld,
-                 p.slot_bytes, fb);
       __syncwarp();
     }
     return;
@@ -712,6 +753,71 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1) sgd_epoch_ke
         if (lane == 0) mbar_arrive(empty0 + 8u * tile);  // this warp is done with the tile
       }
       tqbase += (uint32_t)ntw;
+    } else if constexpr (NARROW8) {
+      // ---- narrow rows: 8 lanes per row, 4 rows per warp and tile pass ----
+      const int rg = lane >> 3, sl = lane & 7;  // row group within the warp, sub-lane within the row
+      float4 wv[4], g8[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int f = sl + 8 * k;  // this lane's float4 columns
+        wv[k] = (f < C4) ? w_s[f] : make_float4(0.f, 0.f, 0.f, 0.f);
+        g8[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      const int n32 = (int)n;
+      const int nt = (n32 + TR - 1) / TR;
+      for (int ti = 0; ti < nt; ++ti) {
+        const uint32_t tq = tqbase + (uint32_t)ti;
+        const uint32_t tile = tq & tile_mask;
+        const uint32_t use = tq >> p.tile_log2;
+        const int cnt = (n32 - ti * TR) < TR ? (n32 - ti * TR) : TR;
+        const int r = cw * 4 + rg;  // my row of the tile
+        const bool live = r < cnt;
+        const float4* row = reinterpret_cast<const float4*>(ring + (size_t)tile * tile_bytes + (size_t)r * p.slot_bytes);
+        mbar_wait(full0 + 8u * tile, use & 1u);
+        float4 x[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int f = sl + 8 * k;
+          x[k] = (live && f < C4) ? row[f] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        const float y = live ? reinterpret_cast<const float*>(row)[p.C] : 0.f;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty0 + 8u * tile);
+        float dot = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          dot = fmaf(x[k].x, wv[k].x, dot);
+          dot = fmaf(x[k].y, wv[k].y, dot);
+          dot = fmaf(x[k].z, wv[k].z, dot);
+          dot = fmaf(x[k].w, wv[k].w, dot);
+        }
+        dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+        dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+        dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+        const float res = dot - y;  // sgd_thrust.cu:43-48; dead rows: 0
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          g8[k].x = fmaf(res, x[k].x, g8[k].x);
+          g8[k].y = fmaf(res, x[k].y, g8[k].y);
+          g8[k].z = fmaf(res, x[k].z, g8[k].z);
+          g8[k].w = fmaf(res, x[k].w, g8[k].w);
+        }
+        if (sl == 0) {  // one lane per row keeps the running loss and the residual
+          loss_abs += (double)fabsf(res);
+          loss_sq += (double)res * (double)res;
+          if (p.r_out != nullptr && live) p.r_out[off + lo + (int64_t)ti * TR + r] = res;
+        }
+      }
+      tqbase += (uint32_t)nt;
+      // the four row groups hold partial gradients of the same columns: add them (fixed order)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        g8[k] = f4_add(g8[k], f4_shfl_xor(g8[k], 8));
+        g8[k] = f4_add(g8[k], f4_shfl_xor(g8[k], 16));
+      }
+      // hand the warp's gradient to the generic CTA reduction below, which expects lane l to hold
+      // float4 column l: lane l = 8*rg + sl owns column sl + 8*rg = its own g8[rg]
+      g[0] = rg == 0 ? g8[0] : rg == 1 ? g8[1] : rg == 2 ? g8[2] : g8[3];
     } else {
       // ---- rows of this step, one ring tile (= producer round) at a time: consumer warp cw
       // takes rows cw, cw+NW, ... of the tile, all U of them concurrently ----
@@ -948,6 +1054,12 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1) sgd_epoch_ke
     for (int i = 0; i < 8; ++i) p.dbg[(int64_t)cta * 8 + i] = ph[i];
   }
   double* const loss_out = (p.ctl != nullptr) ? p.ctl->loss : p.loss;
+  if constexpr (NARROW8) {  // the loss lives in the sl == 0 lane of every row group
+    loss_abs += __shfl_xor_sync(0xffffffffu, loss_abs, 8);
+    loss_abs += __shfl_xor_sync(0xffffffffu, loss_abs, 16);
+    loss_sq += __shfl_xor_sync(0xffffffffu, loss_sq, 8);
+    loss_sq += __shfl_xor_sync(0xffffffffu, loss_sq, 16);
+  }
   if (loss_out != nullptr) {  // lane 0 of every consumer warp holds that warp's sums
     double* ls = reinterpret_cast<double*>(gred);
     consumer_bar<kCT>();
