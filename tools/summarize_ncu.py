@@ -59,6 +59,7 @@ def full(src, dst, title, alg_bytes=None):
     stalls = [h for h in sh if h.startswith("stall_") and "Not Issued" not in h]
     st_tot = {h: sum(int(r[ix[h]] or 0) for r in data) for h in stalls}
     ublk = sum(int(r[ix["Instructions Executed"]] or 0) for r in data if "UBLKCP" in r[ix["Source"]])
+    utma = sum(int(r[ix["Instructions Executed"]] or 0) for r in data if "UTMALDG" in r[ix["Source"]])
     with open(dst, "w") as f:
         f.write(f"# {title}\n\n`ncu --set full --clock-control none --import-source on -k regex:sgd_epoch_kernel -s 1 -c 1` "
                 f"on one B200 (`{src.split('/')[-1]}`, not committed: binary). One launch = one epoch.\n\n")
@@ -73,7 +74,8 @@ def full(src, dst, title, alg_bytes=None):
         if alg_bytes:
             f.write(f"| algorithmic bytes per launch (DESIGN.md 3.1) | {float(alg_bytes) / 1e6:.1f} MB |\n")
             f.write(f"| traffic / algorithmic | {(rd + wr) / float(alg_bytes):.3f} |\n")
-        f.write(f"| `UBLKCP` (TMA bulk copy) instructions executed | {ublk} |\n")
+        f.write(f"| `UBLKCP` (TMA bulk copy, one row each) instructions executed | {ublk} |\n")
+        f.write(f"| `UTMALDG.2D.GATHER4` (TMA tile::gather4, four rows each) instructions executed | {utma} |\n")
         f.write(f"\nWarp stall samples ({tot} total), share by reason:\n\n| reason | share |\n|---|---|\n")
         ssum = sum(st_tot.values()) or 1
         for h, v in sorted(st_tot.items(), key=lambda kv: -kv[1])[:8]:
