@@ -26,6 +26,8 @@
 #include "host_io.hpp"
 #include "host_rng.hpp"
 #include "sgd_kernels.cuh"
+#include "sgd_cluster_kernel.cuh"
+#include "sgd_small_kernel.cuh"
 #include "shuffle_kernels.cuh"
 
 namespace {
@@ -63,16 +65,18 @@ struct KernelChoice {
   int KC = 0, U = 0, NW = 0;
   bool wide = false, narrow8 = false;
   const void* fn = nullptr;
+  const void* fn_lean = nullptr;  // same mapping with the run-time switches folded away, or nullptr
   size_t fixed_smem = 0;
 };
 
-template <int KC, int U, int NW, bool WIDE = false, bool NARROW8 = false>
+template <int KC, int U, int NW, bool WIDE = false, bool NARROW8 = false, bool WITH_LEAN = false>
 KernelChoice make_choice() {
   KernelChoice k;
   k.KC = KC; k.U = U; k.NW = NW;
   k.wide = WIDE;
   k.narrow8 = NARROW8;
   k.fn = (const void*)b200sgd::sgd_epoch_kernel<KC, U, NW, WIDE, NARROW8>;
+  if constexpr (WITH_LEAN) k.fn_lean = (const void*)b200sgd::sgd_epoch_kernel<KC, U, NW, WIDE, NARROW8, true>;
   k.fixed_smem = b200sgd::EpochSmem<KC, NW, WIDE>::kFixed;
   return k;
 }
@@ -91,7 +95,8 @@ bool choose_kernel(int C4, int64_t rows_per_cta, KernelChoice* out) {
     if (rows_per_cta <= 8) *out = make_choice<1, 1, 8>();
     else if (rows_per_cta <= 16) *out = make_choice<1, 2, 8>();
     else if (variant_env() == 5) *out = rows_per_cta <= 32 ? make_choice<1, 4, 8>() : make_choice<1, 2, 16>();
-    else *out = make_choice<1, 4, 8, false, true>();  // 8 lanes per row, 4 rows per warp
+    else if (rows_per_cta > 32 && variant_env() == 6) *out = make_choice<1, 4, 16, false, true>();
+    else *out = make_choice<1, 4, 8, false, true, true>();  // 8 lanes per row, 4 rows per warp
   } else if (C4 <= 64) {
     if (rows_per_cta <= 8) *out = make_choice<2, 1, 8>();
     else if (rows_per_cta <= 16) *out = make_choice<2, 2, 8>();
@@ -186,6 +191,14 @@ struct sgd_ctx {
   int grid = 0, reduce_mode = 0, ntiles = 0, tile_log2 = 0, engine = SGD_ENGINE_PERSISTENT;
   CUtensorMap rec_map{};
   bool use_gather4 = false;  // narrow rows: TMA tile::gather4, four rows per instruction
+  // sgd_small_epoch_kernel (small steps of narrow rows): eligibility and its own ring geometry
+  bool have_rec_map = false;
+  // sgd_cluster_epoch_kernel (small steps of narrow rows, single GPU): the grid is one cluster
+  int cluster_cs = 0, cluster_ntiles = 0, cluster_tile_log2 = 0;
+  size_t cluster_smem = 0;
+  bool small_ok = false;
+  int small_ntiles = 0, small_tile_log2 = 0;
+  size_t small_smem = 0;
   int nprod = 1;  // producer warps
   int tile_rows = 0;
   size_t smem_bytes = 0;
@@ -274,6 +287,22 @@ int configure_launch(sgd_ctx* c) {
       grid = c->num_sms;
     }
   }
+  // Small steps of narrow rows on one GPU: the whole grid is one thread-block cluster that exchanges
+  // the gradient through distributed shared memory (sgd_cluster_kernel.cuh).  B200SGD_CLUSTER=0
+  // switches it off, 8 / 16 pick the cluster size (A/B runs).
+  c->cluster_cs = 0;
+  {
+    const char* e = std::getenv("B200SGD_CLUSTER");
+    const int want = e ? std::atoi(e) : b200sgd::kClMaxCS;
+    const bool profile = std::getenv("B200SGD_PHASE_PROFILE") != nullptr;
+    if ((want == 8 || want == 16) && c->ld <= 128 && c->cfg.nranks == 1 && c->cfg.engine != SGD_ENGINE_GRAPH &&
+        (c->cfg.reduce == SGD_REDUCE_AUTO || c->cfg.reduce == SGD_REDUCE_DATAFLOW) &&
+        !(c->cfg.flags & SGD_FLAG_RESIDUALS) && !profile && rows_step >= 48 && rows_step <= 2048 &&
+        (c->cfg.grid <= 0 || c->cfg.grid == want)) {
+      c->cluster_cs = want;
+      grid = want;
+    }
+  }
   grid = std::max(1, std::min(grid, c->num_sms));
   if (!choose_kernel(c->C4, (rows_step + grid - 1) / grid, &c->kc))
     return fail(SGD_ERR_ARG, "unsupported row width");
@@ -310,6 +339,8 @@ int configure_launch(sgd_ctx* c) {
   c->tile_log2 = lg;
   c->smem_bytes = c->kc.fixed_smem + (size_t)ntiles * tile_bytes;
   CUDA_TRY(cudaFuncSetAttribute(c->kc.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
+  if (c->kc.fn_lean)
+    CUDA_TRY(cudaFuncSetAttribute(c->kc.fn_lean, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
   int occ = 0;
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, c->kc.fn, 32 * (c->kc.NW + c->nprod), c->smem_bytes));
   if (occ < 1) return fail(SGD_ERR_CUDA, "step kernel does not fit on an SM");
@@ -324,12 +355,87 @@ int configure_launch(sgd_ctx* c) {
   return SGD_OK;
 }
 
+// Ring geometry, attributes and schedulability of the cluster kernel; falls back to the generic
+// kernel (cluster_cs = 0) when the tensor map or a free GPC for the cluster is missing.
+int configure_cluster(sgd_ctx* c) {
+  if (c->cluster_cs == 0) return SGD_OK;
+  const int cs = c->cluster_cs;
+  c->cluster_cs = 0;
+  if (!c->have_rec_map) return SGD_OK;
+  const size_t tile_bytes = (size_t)b200sgd::kClTileRows * c->ld * 4;
+  int ntiles = 2, lg = 1;
+  while (ntiles * 2 <= b200sgd::kClMaxTiles && b200sgd::kClFixedSmem + (size_t)(ntiles * 2) * tile_bytes <= kMaxDynSmem) {
+    ntiles *= 2;
+    ++lg;
+  }
+  c->cluster_ntiles = ntiles;
+  c->cluster_tile_log2 = lg;
+  c->cluster_smem = b200sgd::kClFixedSmem + (size_t)ntiles * tile_bytes;
+  const void* fn = (const void*)b200sgd::sgd_cluster_epoch_kernel;
+  CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->cluster_smem));
+  if (cs > 8) CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = dim3(cs);
+  lc.blockDim = dim3(32 * (b200sgd::kClNW + 1));
+  lc.dynamicSmemBytes = c->cluster_smem;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = cs;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  lc.attrs = at;
+  lc.numAttrs = 1;
+  int nclusters = 0;
+  if (cudaOccupancyMaxActiveClusters(&nclusters, fn, &lc) != cudaSuccess || nclusters < 1) {
+    cudaGetLastError();
+    return SGD_OK;
+  }
+  c->cluster_cs = cs;
+  return SGD_OK;
+}
+
+const void* small_kernel_fn(const sgd_ctx* c) {
+  if (c->cfg.nranks > 1) return (const void*)b200sgd::sgd_small_epoch_kernel<true>;
+  if (c->d_dbg != nullptr) return (const void*)b200sgd::sgd_small_epoch_kernel<false, true>;
+  return (const void*)b200sgd::sgd_small_epoch_kernel<false>;
+}
+
+// sgd_small_epoch_kernel serves small steps of narrow rows (config 2); everything else, and every
+// context that uses a feature it leaves out, runs the generic sgd_epoch_kernel.
+int configure_small(sgd_ctx* c) {
+  c->small_ok = false;
+  const int64_t rows_step = std::max<int64_t>(1, (int64_t)c->B / std::max(1, c->cfg.nranks));
+  const int64_t rows_cta = (rows_step + c->grid - 1) / c->grid;
+  if (c->cfg.nranks < 2) return SGD_OK;  // one GPU: the cluster kernel or the generic one
+  if (c->ld > 128 || !c->have_rec_map || c->grid < 2 || rows_cta > 256) return SGD_OK;
+  if (c->engine != SGD_ENGINE_PERSISTENT || c->reduce_mode != SGD_REDUCE_DATAFLOW) return SGD_OK;
+  if ((c->cfg.flags & SGD_FLAG_RESIDUALS) || c->w_copies != c->grid) return SGD_OK;
+  if (c->d_dbg != nullptr && c->cfg.nranks > 1) return SGD_OK;  // the profiled instance is single-GPU
+  if (c->cfg.nranks > 1 && !c->direct) return SGD_OK;
+  if (std::getenv("B200SGD_NO_SMALL")) return SGD_OK;
+  const size_t tile_bytes = (size_t)b200sgd::kSmallTileRows * c->ld * 4;
+  int ntiles = 2, lg = 1;
+  while (ntiles * 2 <= 16 && b200sgd::kSmallFixedSmem + (size_t)(ntiles * 2) * tile_bytes <= kMaxDynSmem) {
+    ntiles *= 2;
+    ++lg;
+  }
+  c->small_ntiles = ntiles;
+  c->small_tile_log2 = lg;
+  c->small_smem = b200sgd::kSmallFixedSmem + (size_t)ntiles * tile_bytes;
+  const void* fn = small_kernel_fn(c);
+  CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->small_smem));
+  int occ = 0;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 32 * (b200sgd::kSmallNW + 1), c->small_smem));
+  c->small_ok = occ >= 1;
+  return SGD_OK;
+}
+
 // 2-D tensor map of the records for tile::gather4 (rows of at most 256 floats).  The driver entry
 // point is resolved at run time, so the library does not link libcuda.
 int make_record_tensor_map(sgd_ctx* c) {
   c->use_gather4 = false;
+  c->have_rec_map = false;
   if (c->ld > 256 || c->local_rows < 1 || std::getenv("B200SGD_NO_GATHER4")) return SGD_OK;
-  if ((c->kc.NW * c->kc.U) % 4 != 0 || c->kc.wide) return SGD_OK;
   typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                 const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                 CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -347,7 +453,9 @@ int make_record_tensor_map(sgd_ctx* c) {
   const CUresult r = ((encode_fn)fn)(&c->rec_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, c->d_rec, gdim, gstride, box, estr,
                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                      CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  c->use_gather4 = (r == CUDA_SUCCESS);
+  c->have_rec_map = (r == CUDA_SUCCESS);
+  // the generic kernel issues gather4 when its ring tile is a whole number of four-row groups
+  c->use_gather4 = c->have_rec_map && (c->kc.NW * c->kc.U) % 4 == 0 && !c->kc.wide;
   return SGD_OK;
 }
 
@@ -484,8 +592,40 @@ int launch_epoch(sgd_ctx* c, int32_t epoch, int buf, int* launches) {
   CUDA_TRY(cudaMemsetAsync(c->d_bar, 0, sizeof(unsigned int), c->stream));
   c->step_tag += (uint32_t)c->nb;  // every rank advances identically: tags agree across GPUs
   void* args[] = {&p};
-  CUDA_TRY(cudaLaunchCooperativeKernel(c->kc.fn, dim3(c->grid), dim3(32 * (c->kc.NW + c->nprod)), args,
-                                       c->smem_bytes, c->stream));
+  if (c->cluster_cs > 0) {  // small steps of narrow rows, one GPU: one cluster, exchange in shared memory
+    p.ntiles = c->cluster_ntiles;
+    p.tile_log2 = c->cluster_tile_log2;
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(c->cluster_cs);
+    lc.blockDim = dim3(32 * (b200sgd::kClNW + 1));
+    lc.dynamicSmemBytes = c->cluster_smem;
+    lc.stream = c->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = c->cluster_cs;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    lc.attrs = at;
+    lc.numAttrs = 1;
+    CUDA_TRY(cudaLaunchKernelExC(&lc, (const void*)b200sgd::sgd_cluster_epoch_kernel, args));
+    *launches += 1;
+    return SGD_OK;
+  }
+  if (c->small_ok) {  // small steps of narrow rows: the short-chain kernel (sgd_small_kernel.cuh)
+    p.ntiles = c->small_ntiles;
+    p.tile_log2 = c->small_tile_log2;
+    const void* fn = small_kernel_fn(c);
+    CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(c->grid), dim3(32 * (b200sgd::kSmallNW + 1)), args, c->small_smem,
+                                         c->stream));
+    *launches += 1;
+    return SGD_OK;
+  }
+  // the instantiation without run-time switches, when none of them is in use (see LEAN)
+  const bool lean = c->kc.fn_lean != nullptr && p.ctl == nullptr && p.step_off == nullptr && p.prefetch_steps == 0 &&
+                    p.use_gather4 != 0 && p.r_out == nullptr && p.dbg == nullptr && p.nranks == 1 &&
+                    p.reduce_mode == SGD_REDUCE_DATAFLOW && std::getenv("B200SGD_NO_LEAN") == nullptr;
+  CUDA_TRY(cudaLaunchCooperativeKernel(lean ? c->kc.fn_lean : c->kc.fn, dim3(c->grid),
+                                       dim3(32 * (c->kc.NW + c->nprod)), args, c->smem_bytes, c->stream));
   *launches += 1;
   return SGD_OK;
 }
@@ -568,8 +708,9 @@ int check_watchdog(sgd_ctx* c) {
   if (err != 0) {
     cudaMemset(c->d_bar + 1, 0, sizeof(unsigned int));
     return fail(c->cfg.nranks > 1 ? SGD_ERR_COMM : SGD_ERR_CUDA,
-                err == 3 ? "dataflow reduction timed out (a CTA or a peer rank did not publish)"
-                         : "grid barrier timed out (CTAs not co-resident?)");
+                err == 3   ? "dataflow reduction timed out (a CTA or a peer rank did not publish)"
+                : err == 4 ? "cluster exchange timed out (rows or partial sums did not arrive)"
+                           : "grid barrier timed out (CTAs not co-resident?)");
   }
   return SGD_OK;
 }
@@ -845,6 +986,8 @@ int sgd_create(const sgd_config* cfg, const float* X, const float* y, sgd_ctx** 
       CUDA_TRY(cudaMemset(c->d_xchg_block, 0, c->xchg_bytes));
       c->peer_block[c->cfg.rank] = c->d_xchg_block;
     }
+    SGD_TRY(configure_cluster(c));
+    SGD_TRY(configure_small(c));
     // main.cu:389-395: weights ~ U(0, 0.01) from the Thrust minstd stream, drawn on the host
     std::vector<float> w0(c->C);
     b200sgd::thrust_minstd_weights(w0.data(), c->C);
@@ -999,8 +1142,9 @@ int sgd_get_config(const sgd_ctx* c, sgd_config* out) {
   out->reserved[0] = c->nb;
   out->reserved[1] = c->ntiles * c->tile_rows;
   out->reserved[2] = (int32_t)c->smem_bytes;
-  out->reserved[3] = c->kc.wide ? -c->kc.KC : c->kc.KC;  // negative: column mapping
-  out->reserved[4] = c->kc.narrow8 ? -c->kc.U : c->kc.U;  // negative: 8 lanes per row
+  // KC: negative = column mapping; 0 = small-step kernels (U: cluster size, or 0 for the L2 variant)
+  out->reserved[3] = (c->small_ok || c->cluster_cs > 0) ? 0 : c->kc.wide ? -c->kc.KC : c->kc.KC;
+  out->reserved[4] = c->cluster_cs > 0 ? c->cluster_cs : c->small_ok ? 0 : c->kc.narrow8 ? -c->kc.U : c->kc.U;  // negative: 8 lanes per row
   out->reserved[5] = c->kc.NW;
   out->reserved[6] = (int32_t)c->ld;
   return SGD_OK;

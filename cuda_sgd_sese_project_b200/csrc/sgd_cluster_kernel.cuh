@@ -1,0 +1,306 @@
+// sgd_cluster_kernel.cuh -- the epoch kernel for SMALL steps of narrow rows (BASELINE config 2:
+// 4M x 100, B = 1000: a step moves 0.45 MB = 70 ns of HBM time; what it costs is the cross-SM
+// dependency "step k+1 needs the weights of step k, which need every row of step k").
+//
+// Same algorithm, record layout and summation discipline as sgd_epoch_kernel (sgd_kernels.cuh;
+// reference: cuda_iteration / cublas_iteration, main.cu:56-163 / :168-301), but the whole grid is ONE
+// thread-block cluster (8 or 16 CTAs) and the per-step gradient exchange never leaves the SMs:
+//
+//   * Through L2 (the generic kernel) a hop is "store, then poll": ~800 cycles SM to SM, quantised by
+//     the poll round trip and stretched by the slowest of 32 publishers -- measured 2400 + 2000
+//     cycles for the two hops of a 6500-cycle step.  Here every warp sends its 128 bytes of column
+//     sums straight into the shared memory of every CTA of the cluster with one bulk copy per
+//     destination (cp.async.bulk.shared::cluster.shared::cta), which completes bytes on the
+//     RECEIVER's mbarrier: the receiver sleeps on a local mbarrier instead of polling L2, and there
+//     is no second hop at all -- every CTA adds the same 2*CS partials in the same order and updates
+//     its own copy of the weights (bit-identical in all CTAs, no atomics, reruns reproduce).
+//   * Column mapping of the gradient: phase A (8 lanes per row, 4 rows per warp, 8 warps = one 32-row
+//     ring tile) leaves the residuals in shared memory; after one CTA barrier thread (h, c) adds
+//     res[r] * x[r][c] over the rows 16h..16h+15 of the tile straight from the staged records.  A warp
+//     therefore ends the step with 32 finished column sums in 32 lanes -- exactly what it sends; the
+//     two row halves of a CTA travel as two sources.
+//   * Producer warp: TMA tile::gather4 (four rows per instruction) into the ring, running ahead of
+//     the consumers across step boundaries, as in the generic kernel.
+//
+// Restrictions (the host falls back to sgd_epoch_kernel otherwise): C + 1 <= 128, tile::gather4
+// available, single GPU, persistent engine, dataflow reduction, no residual output.
+#pragma once
+#include "sgd_kernels.cuh"
+
+namespace b200sgd {
+
+constexpr int kClNW = 8;              // consumer warps
+constexpr int kClCT = 32 * kClNW;     // consumer threads
+constexpr int kClTileRows = 32;       // rows per ring tile = one producer round (8 x gather4)
+constexpr int kClMaxCS = 16;          // CTAs per cluster (16 needs the non-portable opt-in)
+constexpr int kClMaxTiles = 16;
+// shared memory map (bytes)
+constexpr uint32_t kClOffFull = 0;      // uint64 full[16]
+constexpr uint32_t kClOffEmpty = 128;   // uint64 empty[16]
+constexpr uint32_t kClOffRecvBar = 256; // uint64 recv[2]
+constexpr uint32_t kClOffW = 512;       // float w_s[128]
+constexpr uint32_t kClOffR = 1024;      // float r_s[2][32]
+constexpr uint32_t kClOffSend = 1536;   // float send[2][8 warps][32]
+constexpr uint32_t kClOffRecv = 3584;   // float recv[2][2*kClMaxCS][128]
+constexpr uint32_t kClOffRing = kClOffRecv + 2 * 2 * kClMaxCS * 128 * 4;  // 36352, 128-byte aligned
+constexpr size_t kClFixedSmem = kClOffRing;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of `smem_addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+// own shared memory -> shared memory of another CTA of the cluster; completes `bytes` on THAT CTA's mbarrier
+__device__ __forceinline__ void bulk_s2cluster(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t bar_cluster) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_cluster),
+               "r"(src_cta), "r"(bytes), "r"(bar_cluster)
+               : "memory");
+}
+// mbarrier wait with the watchdog of the L2 spin loops: a lost message must not hang the GPU
+__device__ __forceinline__ void mbar_wait_guarded(uint32_t bar, uint32_t parity, unsigned int* err) {
+  if (mbar_try_wait(bar, parity)) return;
+  SpinGuard guard;
+  while (!mbar_try_wait(bar, parity)) {
+    if (guard.expired(err, 4u)) break;
+  }
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// EpochParams fields used: rec_map, ld, C, perm, B, nb, first_step, a, w, g_last, ntiles, tile_log2,
+// slot_bytes, loss.  gridDim.x == cluster size (one cluster).
+__global__ void __launch_bounds__(32 * (kClNW + 1), 1) sgd_cluster_epoch_kernel(const __grid_constant__ EpochParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* w_s = reinterpret_cast<float*>(smem_raw + kClOffW);
+  float* r_s = reinterpret_cast<float*>(smem_raw + kClOffR);
+  float* send_s = reinterpret_cast<float*>(smem_raw + kClOffSend);
+  const float* recv_s = reinterpret_cast<const float*>(smem_raw + kClOffRecv);
+  unsigned char* ring = smem_raw + kClOffRing;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int cta = (int)cluster_ctarank(), CS = (int)cluster_nctarank();
+  const uint32_t smem0 = smem_u32(smem_raw);
+  const uint32_t full0 = smem0 + kClOffFull, empty0 = smem0 + kClOffEmpty, recvbar0 = smem0 + kClOffRecvBar;
+  const uint32_t ring0 = smem0 + kClOffRing;
+  const uint32_t tile_mask = (uint32_t)p.ntiles - 1u;
+  const uint32_t tile_bytes = (uint32_t)kClTileRows * p.slot_bytes;
+
+  if (tid == 0) {
+    for (int i = 0; i < p.ntiles; ++i) {
+      mbar_init(full0 + 8u * i, 1);
+      mbar_init(empty0 + 8u * i, kClNW);
+    }
+    mbar_init(recvbar0, 1);
+    mbar_init(recvbar0 + 8u, 1);
+    fence_barrier_init();
+    // arm the receive barriers of steps 0 and 1 before anybody can send (later ones: one step ahead)
+    const uint32_t expect0 = (uint32_t)(cluster_nctarank() * 2u * (uint32_t)((p.C + 31) >> 5) * 128u);
+    mbar_arrive_expect_tx(recvbar0, expect0);
+    mbar_arrive_expect_tx(recvbar0 + 8u, expect0);
+  }
+  for (int c = tid; c < 128; c += blockDim.x) w_s[c] = (c < p.C) ? p.w[c] : 0.0f;
+  __syncthreads();
+  cluster_sync_all();  // every CTA's barriers exist before anybody sends
+
+  const int64_t lo = slice_lo(p.B, cta, CS);
+  const int n = (int)(slice_lo(p.B, cta + 1, CS) - lo);  // my rows of every step
+  const int nt = (n + kClTileRows - 1) / kClTileRows;
+
+  if (warp == 0) {
+    // ===================================== PRODUCER =====================================
+    // round = up to 32 rows of one step = one ring tile: lane 0 does the flow control, then one
+    // tile::gather4 per four rows; the indices of the next round are in flight meanwhile.
+    const int32_t* src = p.perm + (int64_t)p.first_step * p.B + lo;
+    int s = 0, j0 = 0;
+    uint32_t tq = 0;
+    int cnt = (n > 0 && p.nb > 0) ? min(kClTileRows, n) : 0;
+    int32_t idx = 0;
+    if (lane < cnt) idx = __ldg(src + lane);
+    while (cnt > 0) {
+      const int cur_cnt = cnt;
+      const int32_t cur_idx = idx;
+      const uint32_t cur_tq = tq;
+      j0 += cur_cnt;
+      ++tq;
+      if (j0 >= n) {
+        j0 = 0;
+        ++s;
+        src += p.B;
+      }
+      cnt = (s < p.nb) ? min(kClTileRows, n - j0) : 0;
+      idx = 0;
+      if (lane < cnt) idx = __ldg(src + j0 + lane);
+
+      const uint32_t tile = cur_tq & tile_mask;
+      const uint32_t use = cur_tq >> p.tile_log2;
+      const uint32_t fb = full0 + 8u * tile;
+      const int groups = (cur_cnt + 3) >> 2;
+      if (lane == 0) {
+        mbar_wait_relaxed(empty0 + 8u * tile, (use & 1u) ^ 1u);
+        mbar_arrive_expect_tx(fb, (uint32_t)groups * 4u * p.slot_bytes);
+      }
+      const int b4 = (lane << 2) & 31;
+      const int32_t r0 = __shfl_sync(0xffffffffu, cur_idx, b4);
+      int32_t r1 = __shfl_sync(0xffffffffu, cur_idx, (b4 + 1) & 31);
+      int32_t r2 = __shfl_sync(0xffffffffu, cur_idx, (b4 + 2) & 31);
+      int32_t r3 = __shfl_sync(0xffffffffu, cur_idx, (b4 + 3) & 31);
+      if (4 * lane + 1 >= cur_cnt) r1 = r0;  // a short last group repeats its first row into slots nobody reads
+      if (4 * lane + 2 >= cur_cnt) r2 = r0;
+      if (4 * lane + 3 >= cur_cnt) r3 = r0;
+      if (lane < groups)
+        tma_gather4_g2s(ring0 + tile * tile_bytes + (uint32_t)(4 * lane) * p.slot_bytes, &p.rec_map, r0, r1, r2, r3, fb);
+      __syncwarp();
+    }
+  } else {
+    // ======================================= CONSUMERS =======================================
+    const int ctid = tid - 32, cw = warp - 1;
+    const int rg = lane >> 3, sl = lane & 7;  // phase A: row group of the warp, sub-lane within the row
+    const int hb = cw >> 2, cwi = cw & 3;     // phase B: row half of the tile, block of 32 columns
+    const int colB = 32 * cwi + lane;         // my gradient column
+    const int C = p.C, ld = (int)p.ld, ld4 = ld >> 2;
+    const float Bf = (float)p.B, a = p.a;
+    const int ncw = (C + 31) >> 5;            // column blocks that carry features
+    const bool sender = cwi < ncw;
+    const uint32_t expect = (uint32_t)(CS * 2 * ncw * 128);  // bytes every CTA receives per step
+    const int nsrc = 2 * CS;
+
+    double loss_abs = 0.0, loss_sq = 0.0;  // running training loss (lane sl == 0 of every row group)
+    uint32_t tq = 0;
+
+    for (int s = 0; s < p.nb; ++s) {
+      const int par = s & 1;
+      const uint32_t rbar = recvbar0 + 8u * par;
+      // arm the barrier of step s+1: its previous phase (step s-1) is complete and every local waiter
+      // has left it (end-of-step barrier); nobody can send step s+1 before it has my step s
+      if (ctid == 0 && s >= 1 && s + 1 < p.nb) mbar_arrive_expect_tx(recvbar0 + 8u * (par ^ 1), expect);
+      float4 wv[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) wv[k] = reinterpret_cast<const float4*>(w_s)[sl + 8 * k];
+      float acc0 = 0.f, acc1 = 0.f;  // column colB over my row half, even / odd rows
+      for (int ti = 0; ti < nt; ++ti, ++tq) {
+        const uint32_t tile = tq & tile_mask;
+        const uint32_t use = tq >> p.tile_log2;
+        const int cnt = min(kClTileRows, n - ti * kClTileRows);
+        const unsigned char* tbase = ring + (size_t)tile * tile_bytes;
+        float* rr = r_s + (tq & 1u) * 32;
+        // ---- phase A: residual of row cw*4 + rg  (r = x.w - y, sgd_thrust.cu:43-48 / :352-364)
+        const int r = cw * 4 + rg;
+        const bool live = r < cnt;
+        const float4* row = reinterpret_cast<const float4*>(tbase + (size_t)r * p.slot_bytes);
+        mbar_wait_guarded(full0 + 8u * tile, use & 1u, p.err);
+        float4 x[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          x[k] = (live && sl + 8 * k < ld4) ? row[sl + 8 * k] : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float y = live ? reinterpret_cast<const float*>(row)[C] : 0.f;  // the label rides in the record
+        float d[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {  // four independent chains; w_s is zero for the label and the padding
+          d[k] = x[k].x * wv[k].x;
+          d[k] = fmaf(x[k].y, wv[k].y, d[k]);
+          d[k] = fmaf(x[k].z, wv[k].z, d[k]);
+          d[k] = fmaf(x[k].w, wv[k].w, d[k]);
+        }
+        float dot = (d[0] + d[1]) + (d[2] + d[3]);
+        dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+        dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+        dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+        const float res = dot - y;  // rows beyond the tile: 0
+        if (sl == 0) {
+          rr[r] = res;
+          loss_abs += (double)fabsf(res);
+          loss_sq += (double)res * (double)res;
+        }
+        consumer_bar<kClCT>();
+        // ---- phase B: res[r] * x[r][colB] over the rows 16*hb .. 16*hb+15 of the tile
+        if (colB < ld) {
+          const float* col = reinterpret_cast<const float*>(tbase) + colB;
+          const int q1 = min(cnt, 16 * hb + 16);
+          int q = 16 * hb;
+#pragma unroll 4
+          for (; q + 1 < q1; q += 2) {
+            acc0 = fmaf(rr[q], col[(size_t)q * ld], acc0);
+            acc1 = fmaf(rr[q + 1], col[(size_t)(q + 1) * ld], acc1);
+          }
+          if (q < q1) acc0 = fmaf(rr[q], col[(size_t)q * ld], acc0);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty0 + 8u * tile);
+      }
+
+      // ---- exchange: my warp's 32 column sums -> slot [par][2*cta + hb][32*cwi ..] of EVERY CTA
+      if (sender) {
+        float* mine = send_s + (par * kClNW + cw) * 32;
+        mine[lane] = acc0 + acc1;
+        fence_proxy_async_smem();  // the bulk copy reads shared memory through the async proxy
+        __syncwarp();
+        if (lane < CS) {
+          const uint32_t slot = smem0 + kClOffRecv + (uint32_t)(((par * 2 * kClMaxCS + 2 * cta + hb) * 128 + 32 * cwi) * 4);
+          bulk_s2cluster(map_to_cta(slot, (uint32_t)lane), smem_u32(mine), 128u, map_to_cta(rbar, (uint32_t)lane));
+        }
+      }
+      // ---- every CTA adds the 2*CS partials of a column in the same order and applies
+      //      w = a * (g / B) + w   (sgd_thrust.cu:269, main.cu:147-150 / :287-290)
+      if (ctid < 128) {
+        mbar_wait_guarded(rbar, (uint32_t)(s >> 1) & 1u, p.err);
+        if (ctid < C) {
+          const float* rb = recv_s + (size_t)par * 2 * kClMaxCS * 128 + ctid;
+          float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+          for (int i = 0; i < nsrc; i += 4) {
+            t0 += rb[(i + 0) * 128];
+            t1 += rb[(i + 1) * 128];
+            t2 += rb[(i + 2) * 128];
+            t3 += rb[(i + 3) * 128];
+          }
+          const float gs = ((t0 + t1) + (t2 + t3)) / Bf;
+          w_s[ctid] = fmaf(a, gs, w_s[ctid]);
+          if (cta == 0 && s == p.nb - 1) p.g_last[ctid] = gs;
+        }
+      }
+      consumer_bar<kClCT>();  // w_s complete
+    }
+
+    // running loss of the launch: per-CTA sums of |r| and r^2
+    loss_abs += __shfl_xor_sync(0xffffffffu, loss_abs, 8);
+    loss_abs += __shfl_xor_sync(0xffffffffu, loss_abs, 16);
+    loss_sq += __shfl_xor_sync(0xffffffffu, loss_sq, 8);
+    loss_sq += __shfl_xor_sync(0xffffffffu, loss_sq, 16);
+    if (p.loss != nullptr) {
+      double* ls = reinterpret_cast<double*>(r_s);  // free after the last end-of-step barrier
+      if (lane == 0) {
+        ls[2 * cw] = loss_abs;
+        ls[2 * cw + 1] = loss_sq;
+      }
+      consumer_bar<kClCT>();
+      if (ctid == 0) {
+        double sa = 0.0, sb = 0.0;
+        for (int wq = 0; wq < kClNW; ++wq) {
+          sa += ls[2 * wq];
+          sb += ls[2 * wq + 1];
+        }
+        p.loss[2 * cta] += sa;
+        p.loss[2 * cta + 1] += sb;
+      }
+    }
+    if (cta == 0)  // every CTA holds the same bits
+      for (int c = ctid; c < C; c += kClCT) p.w[c] = w_s[c];
+  }
+  cluster_sync_all();  // nobody leaves while a peer may still write into its shared memory
+}
+
+}  // namespace b200sgd

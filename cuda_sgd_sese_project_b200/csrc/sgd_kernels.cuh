@@ -426,10 +426,23 @@ struct EpochSmem {
 //          of a whole warp, so a warp handles 4 rows at once with a 3-level shuffle reduction; about
 //          2.5x fewer issued instructions per row than one row per warp (the row phase of narrow
 //          rows is issue-bound: ~100 instructions per 448-byte row otherwise).
-template <int KC, int U, int NW, bool WIDE = false, bool NARROW8 = false>
+//   LEAN: single GPU, 2-hop dataflow reduction, persistent engine, gather4 producer, no residual
+//          output, no profiling: every run-time switch below folds to a constant.  The latency-
+//          bound shapes (config 2) execute a few hundred instructions per step per warp exactly
+//          once, so the size of the loop body (instruction-cache misses) is part of the step time.
+template <int KC, int U, int NW, bool WIDE = false, bool NARROW8 = false, bool LEAN = false>
 __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1)
     sgd_epoch_kernel(const __grid_constant__ EpochParams p) {
   static_assert(!NARROW8 || (KC == 1 && U == 4 && !WIDE), "NARROW8 is the <1,4,NW> row mapping");
+  // run-time switches, constant-folded in the LEAN instantiations
+  StepCtl* const o_ctl = LEAN ? nullptr : p.ctl;
+  const int64_t* const o_step_off = LEAN ? nullptr : p.step_off;
+  const int o_prefetch_steps = LEAN ? 0 : p.prefetch_steps;
+  const bool o_use_gather4 = LEAN ? true : (p.use_gather4 != 0);
+  float* const o_r_out = LEAN ? nullptr : p.r_out;
+  const int o_reduce_mode = LEAN ? 3 : p.reduce_mode;
+  const int o_nranks = LEAN ? 1 : p.nranks;
+  unsigned long long* const o_dbg = LEAN ? nullptr : p.dbg;
   const int kThreads = blockDim.x;  // 32 * (NW + p.nprod)
   constexpr int kCT = 32 * NW;  // consumer threads
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -449,7 +462,9 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1)
   // rows per ring tile = rows of one producer round: NW*U in the row mapping, chosen by the host
   // (as many as fit, rows can be tens of KB) in the column mapping
   constexpr int TRc = NW * U;
-  static_assert(TRc <= 32, "a producer round is one warp instruction: at most 32 rows per tile");
+  static_assert(TRc <= 32 || NARROW8, "only the narrow-row mapping uses tiles of more than 32 rows");
+  static_assert(TRc <= 128, "a gather4 round is one warp instruction: at most 4 * 32 rows per tile");
+  constexpr int IH = WIDE ? 1 : (TRc + 31) / 32;  // permutation indices a producer lane holds per round
   const int TR = WIDE ? p.tile_rows : TRc;
   const int ntiles = p.ntiles;
   const uint32_t tile_mask = (uint32_t)ntiles - 1u;
@@ -464,13 +479,13 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1)
   const int32_t* perm = p.perm;
   unsigned int bar_base = 0;
   uint32_t tag_base = p.tag_base;
-  if (p.ctl != nullptr) {
-    first_step = p.ctl->step;
-    if (first_step >= p.ctl->nb_total) return;  // surplus node of the last graph replay
-    a_step = p.ctl->a;
-    perm = p.ctl->perm;
-    bar_base = p.ctl->bar_base;
-    tag_base = p.ctl->tag_base;
+  if (o_ctl != nullptr) {
+    first_step = o_ctl->step;
+    if (first_step >= o_ctl->nb_total) return;  // surplus node of the last graph replay
+    a_step = o_ctl->a;
+    perm = o_ctl->perm;
+    bar_base = o_ctl->bar_base;
+    tag_base = o_ctl->tag_base;
   }
 
   if (tid == 0) {
@@ -488,11 +503,11 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1)
 
   auto step_begin = [&](int s) -> int64_t {
     const int64_t sa = (int64_t)first_step + s;
-    return p.step_off ? p.step_off[sa] : sa * p.B;
+    return o_step_off ? o_step_off[sa] : sa * p.B;
   };
   auto step_rows = [&](int s) -> int64_t {
     const int64_t sa = (int64_t)first_step + s;
-    return p.step_off ? (p.step_off[sa + 1] - p.step_off[sa]) : p.B;
+    return o_step_off ? (o_step_off[sa + 1] - o_step_off[sa]) : p.B;
   };
 
   // uniform batches (single GPU): the CTA's slice of a batch is the same every step
@@ -519,7 +534,7 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1)
     auto load_step = [&]() {
       n = 0;
       if (s < p.nb) {
-        if (p.step_off == nullptr) {
+        if (o_step_off == nullptr) {
           off = ((int64_t)first_step + s) * p.B;
           lo = lo_uni;
           n = n_uni;
@@ -556,27 +571,36 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1)
     settle();
     for (int k = 0; k < warp; ++k) advance();  // my first round
     int cnt = round_cnt();
-    int32_t idx = 0;
-    if (lane < cnt) idx = __ldg(perm + off + lo + j0 + lane);
+    int32_t idx[IH];
+    auto load_indices = [&]() {  // lane l holds rows l, l+32, ... of the round
+#pragma unroll
+      for (int h = 0; h < IH; ++h) {
+        idx[h] = 0;
+        if (h * 32 + lane < cnt) idx[h] = __ldg(perm + off + lo + j0 + h * 32 + lane);
+      }
+    };
+    load_indices();
     while (cnt > 0) {
       const int cur_cnt = cnt;
-      const int32_t cur_idx = idx;
+      int32_t cur_idx[IH];
+#pragma unroll
+      for (int h = 0; h < IH; ++h) cur_idx[h] = idx[h];
       const uint32_t cur_tq = tq;
       const int cur_s = s;
       // move to my next round and get its indices in flight
       for (int k = 0; k < NP; ++k) advance();
       cnt = round_cnt();
-      if (lane < cnt) idx = __ldg(perm + off + lo + j0 + lane);
+      load_indices();
       // experiment: cap how many steps the producer may run ahead of the consumers (0 = unlimited)
-      if (p.prefetch_steps > 0) {
-        while (cur_s - steps_done >= p.prefetch_steps) {
+      if (o_prefetch_steps > 0) {
+        while (cur_s - steps_done >= o_prefetch_steps) {
         }
       }
       // issue the current round: wait for the tile, arm its barrier, one TMA bulk copy per row
       const uint32_t tile = cur_tq & tile_mask;
       const uint32_t use = cur_tq >> p.tile_log2;
       const uint32_t fb = full0 + 8u * tile;
-      if (p.use_gather4) {
+      if (o_use_gather4) {
         // narrow rows: one tile::gather4 per four rows (lane l takes rows 4l..4l+3 of the round; a
         // short last group repeats its first row into slots that nobody reads)
         const int groups = (cur_cnt + 3) >> 2;
@@ -585,10 +609,15 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1)
           mbar_arrive_expect_tx(fb, (uint32_t)groups * 4u * p.slot_bytes);
         }
         const int b4 = (lane << 2) & 31;
-        const int32_t r0 = __shfl_sync(0xffffffffu, cur_idx, b4);
-        int32_t r1 = __shfl_sync(0xffffffffu, cur_idx, (b4 + 1) & 31);
-        int32_t r2 = __shfl_sync(0xffffffffu, cur_idx, (b4 + 2) & 31);
-        int32_t r3 = __shfl_sync(0xffffffffu, cur_idx, (b4 + 3) & 31);
+        int32_t r0 = 0, r1 = 0, r2 = 0, r3 = 0;
+#pragma unroll
+        for (int h = 0; h < IH; ++h) {  // rows 4l..4l+3 live in index register (4l)/32 = l/8
+          const int32_t q0 = __shfl_sync(0xffffffffu, cur_idx[h], b4);
+          const int32_t q1 = __shfl_sync(0xffffffffu, cur_idx[h], (b4 + 1) & 31);
+          const int32_t q2 = __shfl_sync(0xffffffffu, cur_idx[h], (b4 + 2) & 31);
+          const int32_t q3 = __shfl_sync(0xffffffffu, cur_idx[h], (b4 + 3) & 31);
+          if ((lane >> 3) == h) { r0 = q0; r1 = q1; r2 = q2; r3 = q3; }
+        }
         if (4 * lane + 1 >= cur_cnt) r1 = r0;
         if (4 * lane + 2 >= cur_cnt) r2 = r0;
         if (4 * lane + 3 >= cur_cnt) r3 = r0;
@@ -600,9 +629,11 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1)
           mbar_arrive_expect_tx(fb, (uint32_t)cur_cnt * p.slot_bytes);
         }
         __syncwarp();
-        if (lane < cur_cnt)
-          bulk_g2s(ring0 + tile * tile_bytes + (uint32_t)lane * p.slot_bytes, p.rec + (int64_t)cur_idx * p.ld,
-                   p.slot_bytes, fb);
+#pragma unroll
+        for (int h = 0; h < IH; ++h)
+          if (h * 32 + lane < cur_cnt)
+            bulk_g2s(ring0 + tile * tile_bytes + (uint32_t)(h * 32 + lane) * p.slot_bytes,
+                     p.rec + (int64_t)cur_idx[h] * p.ld, p.slot_bytes, fb);
       }
       __syncwarp();
     }
@@ -643,16 +674,16 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1)
   // reductions treat every column in every CTA.  Q threads (power of two) share one column.
   const int f0 = (int)slice_lo(C4, cta, G);
   const int nf = (int)slice_lo(C4, cta + 1, G) - f0;
-  const bool all_cols = (p.reduce_mode == 4 || p.reduce_mode == 1);
+  const bool all_cols = (o_reduce_mode == 4 || o_reduce_mode == 1);
   const int ncol = all_cols ? C4 : nf;
   const int col0 = all_cols ? 0 : f0;
-  const bool direct = p.nranks > 1 && p.direct != 0;  // multi-GPU, narrow rows: one gather over all ranks
-  const int nsrc_gather = direct ? p.nranks * G : G;
+  const bool direct = o_nranks > 1 && p.direct != 0;  // multi-GPU, narrow rows: one gather over all ranks
+  const int nsrc_gather = direct ? o_nranks * G : G;
   int gcap = 1;  // no point in more threads per column than there are sources
   while (gcap < nsrc_gather) gcap <<= 1;
   int Q = 1;
   {
-    const int qmax = (p.reduce_mode >= 3) ? kCT : 32;  // the barrier modes reduce inside a warp
+    const int qmax = (o_reduce_mode >= 3) ? kCT : 32;  // the barrier modes reduce inside a warp
     while (Q < qmax && Q < gcap && (int64_t)(ncol > 0 ? ncol : 1) * (Q * 2) <= kCT) Q <<= 1;
   }
   const int cols_per_pass = kCT / Q;
@@ -665,7 +696,7 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1)
   // optional phase profile: consumer thread 0 of every CTA sums the cycles between these marks
   unsigned long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   long long t_prev = 0;
-  const bool prof = (p.dbg != nullptr) && ctid == 0;
+  const bool prof = (o_dbg != nullptr) && ctid == 0;
   int cur_step = 0;
   auto mark = [&](int i) {
     if (prof) {
@@ -673,7 +704,7 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1)
       ph[i] += (unsigned long long)(t - t_prev);
       t_prev = t;
       // wall-clock snapshot of one step (the middle one) for cross-CTA timelines
-      if (cur_step == p.nb / 2) p.dbg[((int64_t)G + cta) * 8 + i] = global_timer_ns();
+      if (cur_step == p.nb / 2) o_dbg[((int64_t)G + cta) * 8 + i] = global_timer_ns();
     }
   };
   if (prof) t_prev = clock64();
@@ -682,7 +713,7 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1)
     cur_step = s;
     if (ctid == 0) steps_done = s;  // all consumers have finished step s-1 (they passed its last barrier)
     int64_t off, lo, n;
-    if (p.step_off == nullptr) {
+    if (o_step_off == nullptr) {
       off = ((int64_t)first_step + s) * p.B;
       lo = lo_uni;
       n = n_uni;
@@ -728,7 +759,7 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1)
               rbuf[r] = res;
               loss_abs += (double)fabsf(res);
               loss_sq += (double)res * (double)res;
-              if (p.r_out != nullptr) p.r_out[off + lo + (int64_t)ti * TR + r] = res;
+              if (o_r_out != nullptr) o_r_out[off + lo + (int64_t)ti * TR + r] = res;
             }
           }
         }
@@ -774,6 +805,7 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1)
         const bool live = r < cnt;
         const float4* row = reinterpret_cast<const float4*>(ring + (size_t)tile * tile_bytes + (size_t)r * p.slot_bytes);
         mbar_wait(full0 + 8u * tile, use & 1u);
+        mark(7);  // (profile) time spent waiting for the rows to land
         float4 x[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -805,8 +837,9 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1)
         if (sl == 0) {  // one lane per row keeps the running loss and the residual
           loss_abs += (double)fabsf(res);
           loss_sq += (double)res * (double)res;
-          if (p.r_out != nullptr && live) p.r_out[off + lo + (int64_t)ti * TR + r] = res;
+          if (o_r_out != nullptr && live) o_r_out[off + lo + (int64_t)ti * TR + r] = res;
         }
+        mark(0);
       }
       tqbase += (uint32_t)nt;
       // the four row groups hold partial gradients of the same columns: add them (fixed order)
@@ -882,9 +915,9 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1)
             g[k].z = fmaf(r, x[u][k].z, g[k].z);
             g[k].w = fmaf(r, x[u][k].w, g[k].w);
           }
-          if (p.r_out != nullptr && lane == 0) {
+          if (o_r_out != nullptr && lane == 0) {
             const int rr = cw + u * NW;
-            if (rr < cnt) p.r_out[off + lo + (int64_t)ti * TR + rr] = r;
+            if (rr < cnt) o_r_out[off + lo + (int64_t)ti * TR + rr] = r;
           }
         }
       }
@@ -916,7 +949,7 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1)
         return acc;
       }
     };
-    if (G == 1 && p.nranks == 1) {
+    if (G == 1 && o_nranks == 1) {
       // single CTA (tiny batches): the CTA partial is the gradient; nothing leaves the SM
       for (int f = ctid; f < C4; f += kCT) {
         float4 gs;
@@ -926,7 +959,7 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1)
       consumer_bar<kCT>();
       continue;
     }
-    if (p.reduce_mode >= 3) {
+    if (o_reduce_mode >= 3) {
       // ================= DATAFLOW: no barrier, no atomics, tagged words =================
       const uint32_t tag = tag_base + (uint32_t)s + 1u;
       // every CTA publishes its partial gradient (double-buffered by step parity).  Layout
@@ -939,18 +972,18 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1)
       if (direct) {
         // multi-GPU, narrow rows: the partial goes straight to the column owners of EVERY rank
         // (NVLink stores), one network hop instead of local gather + slice exchange
-        const int64_t xs = (int64_t)p.nranks * G;  // sources per column (G % 4 == 0 here: line aligned)
+        const int64_t xs = (int64_t)o_nranks * G;  // sources per column (G % 4 == 0 here: line aligned)
         for (int f = ctid; f < C4; f += kCT) {
           const float4 v = cta_partial(f);
           const int64_t at = (((int64_t)par * C4 + f) * xs + (int64_t)p.rank * G + cta) * 2;
-          for (int pr = 0; pr < p.nranks; ++pr) ll_store_f4(p.ll_xpart_peer[pr] + at, v, tag);
+          for (int pr = 0; pr < o_nranks; ++pr) ll_store_f4(p.ll_xpart_peer[pr] + at, v, tag);
         }
       } else {
         for (int f = ctid; f < C4; f += kCT) ll_store_f4(parts + ((int64_t)f * Gp + cta) * 2, cta_partial(f), tag);
       }
       mark(2);  // partial published
 
-      if (p.reduce_mode == 4) {
+      if (o_reduce_mode == 4) {
         // ---- ONE hop (latency-bound shapes, small grids): every CTA gathers all G partials
         // itself, in the same fixed order, and updates its own copy of the weights.
         for (int base = 0; base < C4; base += cols_per_pass) {
@@ -982,21 +1015,21 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1)
         const float4 w_old = active ? w_s[f] : make_float4(0.f, 0.f, 0.f, 0.f);
         float4 tot;
         if (direct) {
-          const int64_t xs = (int64_t)p.nranks * G;
+          const int64_t xs = (int64_t)o_nranks * G;
           tot = ll_gather<kCT>(p.ll_xpart_local + (int64_t)par * C4 * xs * 2, 1, xs, f, (int)xs, my_q, Q, active, tag,
                                p.err, xred, ctid, poll_one_word);
         } else {
           tot = ll_gather<kCT>(parts, 1, Gp, f, G, my_q, Q, active, tag, p.err, xred, ctid, poll_one_word);
         }
         mark(3);  // (owners) partials gathered
-        if (p.nranks > 1 && !direct) {  // uniform over the grid
-          const int64_t slot = ((int64_t)par * p.nranks) * C4p;
+        if (o_nranks > 1 && !direct) {  // uniform over the grid
+          const int64_t slot = ((int64_t)par * o_nranks) * C4p;
           if (active) {  // lane q writes the inboxes of ranks q, q+Q, ...: NVLink stores in parallel
-            for (int pr = my_q; pr < p.nranks; pr += Q)
+            for (int pr = my_q; pr < o_nranks; pr += Q)
               ll_store_f4(p.ll_inbox_peer[pr] + (slot + (int64_t)p.rank * C4p + f) * 2, tot, tag);
           }
           // the ranks' slices are gathered like the partials: lane q polls rank q, fixed tree
-          tot = ll_gather<kCT>(p.ll_inbox_local + slot * 2, C4p, 1, f, p.nranks, my_q, Q, active, tag, p.err, xred, ctid, poll_one_word);
+          tot = ll_gather<kCT>(p.ll_inbox_local + slot * 2, C4p, 1, f, o_nranks, my_q, Q, active, tag, p.err, xred, ctid, poll_one_word);
         }
         // every lane of the group holds `tot`: lane q publishes the new weights into the
         // mailboxes of CTAs q, q+Q, ... (private copies keep 148 pollers off one line)
@@ -1031,7 +1064,7 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1)
       if (active && my_q == 0) {
         float4 gs;
         const float4 wv = updated(f, w_s[f], tot, &gs);
-        if (p.reduce_mode == 1) {
+        if (o_reduce_mode == 1) {
           // ALLGATHER: every CTA summed all G partials itself (same order -> same bits)
           w_s[f] = wv;
           if (cta == 0) reinterpret_cast<float4*>(p.g_last)[f] = gs;
@@ -1042,7 +1075,7 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1)
         }
       }
     }
-    if (p.reduce_mode != 1) {  // SCATTER: second grid barrier, then everybody reloads the weights
+    if (o_reduce_mode != 1) {  // SCATTER: second grid barrier, then everybody reloads the weights
       bar_count += 1;
       grid_barrier<kCT>(p.bar, bar_base + bar_count * (unsigned)G, ctid, p.err);
       for (int f = ctid; f < C4; f += kCT) w_s[f] = ld_cg_f4(p.w_stage + f);
@@ -1051,9 +1084,9 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1)
   }
 
   if (prof) {
-    for (int i = 0; i < 8; ++i) p.dbg[(int64_t)cta * 8 + i] = ph[i];
+    for (int i = 0; i < 8; ++i) o_dbg[(int64_t)cta * 8 + i] = ph[i];
   }
-  double* const loss_out = (p.ctl != nullptr) ? p.ctl->loss : p.loss;
+  double* const loss_out = (o_ctl != nullptr) ? o_ctl->loss : p.loss;
   if constexpr (NARROW8) {  // the loss lives in the sl == 0 lane of every row group
     loss_abs += __shfl_xor_sync(0xffffffffu, loss_abs, 8);
     loss_abs += __shfl_xor_sync(0xffffffffu, loss_abs, 16);
@@ -1081,10 +1114,10 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1)
   // final weights back to global (every CTA holds the same bits; CTA 0 writes)
   if (cta == 0) {
     for (int c = ctid; c < p.C; c += kCT) p.w[c] = reinterpret_cast<float*>(w_s)[c];
-    if (p.ctl != nullptr && ctid == 0) {  // every CTA has read ctl before its first grid barrier
-      p.ctl->step = first_step + p.nb;
-      p.ctl->bar_base = bar_base + bar_count * (unsigned)G;
-      p.ctl->tag_base = tag_base + (uint32_t)p.nb;
+    if (o_ctl != nullptr && ctid == 0) {  // every CTA has read ctl before its first grid barrier
+      o_ctl->step = first_step + p.nb;
+      o_ctl->bar_base = bar_base + bar_count * (unsigned)G;
+      o_ctl->tag_base = tag_base + (uint32_t)p.nb;
     }
   }
 }

@@ -42,7 +42,7 @@ def run(R, C, B, lr=0.01, epochs=3, warm=1, shuffle=True, **kw):
         phases = None
         if os.environ.get("B200SGD_PHASE_PROFILE") == "1":
             d = eng.debug_phase_cycles().astype(np.float64) / max(1, best["steps"])
-            names = ["rows", "cta_reduce", "publish", "gather", "owner_publish", "wait_w", "bar2", "-"]
+            names = ["rows", "cta_reduce", "publish", "gather", "owner_publish", "wait_w", "bar2", "wait_rows"]
             own = d[:, 3] > 50   # CTAs that own columns (2-hop) / all CTAs (1-hop)
             phases = {n: [round(float(d[:, i].mean())), round(float(d[:, i].max()))] for i, n in enumerate(names) if d[:, i].any()}
             if own.any():
@@ -58,7 +58,17 @@ def run(R, C, B, lr=0.01, epochs=3, warm=1, shuffle=True, **kw):
                "frac_of_peak": round(best["bytes"] / (best["steploop_ms"] * 1e-3) * 1e-9 / PEAK, 4),
                "msamples_per_s": round(best["samples"] / (best["steploop_ms"] * 1e-3) * 1e-6, 1),
                "finite": bool(np.all(np.isfinite(w)))}
-        if phases:
+        if phases and out["kernel"][0] == 0:   # small-step kernel: column warp 0 / owner warp 4 of every CTA
+            col = eng.debug_phase_cycles().astype(np.int64)
+            own = eng.debug_step_timeline().astype(np.int64)
+            t0 = col[:, 7:8]   # end of the previous step (column warp's clock; same SM clock for the owner warp)
+            cn = ["rows_landed", "phaseA", "barA", "phaseB", "published", "weights", "end_bar"]
+            on = ["rows_landed", "phaseA", "barA", "-", "gathered", "answered", "end_bar"]
+            cr, orr = col[:, :7] - t0, own[:, :7] - t0
+            out["column_warp_clock_min_med_max"] = {n: [int(cr[:, i].min()), int(np.median(cr[:, i])), int(cr[:, i].max())] for i, n in enumerate(cn)}
+            out["owner_warp_clock_min_med_max"] = {n: [int(orr[:, i].min()), int(np.median(orr[:, i])), int(orr[:, i].max())] for i, n in enumerate(on) if n != "-"}
+            out["owner_prev_end"] = [int((own[:, 7] - col[:, 7]).min()), int((own[:, 7] - col[:, 7]).max())]
+        elif phases:
             out["phase_cycles_mean_max"] = phases
             tl = eng.debug_step_timeline().astype(np.int64)
             t0 = tl[:, 0][tl[:, 0] > 0].min()
@@ -86,6 +96,13 @@ def main():
                 run(1_000_000, 100, 1000, reduce=reduce, grid=grid)
         for engine in (2,):
             run(1_000_000, 100, 1000, engine=engine, grid=148)
+    elif what == "small":   # small grids for the latency-bound c2 shape: fewer sources per gather
+        for variant in ("0", "6"):
+            os.environ["B200SGD_VARIANT"] = variant
+            for reduce in (4, 3):
+                for grid in (2, 4, 8, 16, 32):
+                    r = run(1_000_000, 100, 1000, reduce=reduce, grid=grid)
+        os.environ.pop("B200SGD_VARIANT", None)
     elif what == "batch":
         for B in (10, 100, 1000, 4096, 10000, 100000):
             run(4_000_000, 100, B, lr=0.001, epochs=2 if B >= 100 else 1, warm=1 if B >= 100 else 0)
