@@ -195,6 +195,7 @@ struct sgd_ctx {
   bool have_rec_map = false;
   // sgd_cluster_epoch_kernel (small steps of narrow rows, single GPU): the grid is one cluster
   int cluster_cs = 0, cluster_ntiles = 0, cluster_tile_log2 = 0;
+  const void* cluster_fn = nullptr;
   size_t cluster_smem = 0;
   bool small_ok = false;
   int small_ntiles = 0, small_tile_log2 = 0;
@@ -294,10 +295,9 @@ int configure_launch(sgd_ctx* c) {
   {
     const char* e = std::getenv("B200SGD_CLUSTER");
     const int want = e ? std::atoi(e) : b200sgd::kClMaxCS;
-    const bool profile = std::getenv("B200SGD_PHASE_PROFILE") != nullptr;
     if ((want == 8 || want == 16) && c->ld <= 128 && c->cfg.nranks == 1 && c->cfg.engine != SGD_ENGINE_GRAPH &&
         (c->cfg.reduce == SGD_REDUCE_AUTO || c->cfg.reduce == SGD_REDUCE_DATAFLOW) &&
-        !(c->cfg.flags & SGD_FLAG_RESIDUALS) && !profile && rows_step >= 48 && rows_step <= 2048 &&
+        !(c->cfg.flags & SGD_FLAG_RESIDUALS) && rows_step >= 48 && rows_step <= 2048 &&
         (c->cfg.grid <= 0 || c->cfg.grid == want)) {
       c->cluster_cs = want;
       grid = want;
@@ -371,12 +371,20 @@ int configure_cluster(sgd_ctx* c) {
   c->cluster_ntiles = ntiles;
   c->cluster_tile_log2 = lg;
   c->cluster_smem = b200sgd::kClFixedSmem + (size_t)ntiles * tile_bytes;
-  const void* fn = (const void*)b200sgd::sgd_cluster_epoch_kernel;
+  // tiles of one CTA per step -> phase-A block size
+  const int64_t rows_cta = ((int64_t)c->B + cs - 1) / cs;
+  const int tiles_step = (int)((rows_cta + b200sgd::kClTileRows - 1) / b200sgd::kClTileRows);
+  const bool prof = c->d_dbg != nullptr;
+  const void* fn = nullptr;
+  if (tiles_step <= 1) fn = prof ? (const void*)b200sgd::sgd_cluster_epoch_kernel<1, true> : (const void*)b200sgd::sgd_cluster_epoch_kernel<1>;
+  else if (tiles_step <= 2) fn = prof ? (const void*)b200sgd::sgd_cluster_epoch_kernel<2, true> : (const void*)b200sgd::sgd_cluster_epoch_kernel<2>;
+  else fn = prof ? (const void*)b200sgd::sgd_cluster_epoch_kernel<4, true> : (const void*)b200sgd::sgd_cluster_epoch_kernel<4>;
+  c->cluster_fn = fn;
   CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->cluster_smem));
   if (cs > 8) CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   cudaLaunchConfig_t lc = {};
   lc.gridDim = dim3(cs);
-  lc.blockDim = dim3(32 * (b200sgd::kClNW + 1));
+  lc.blockDim = dim3(32 * (b200sgd::kClNW + b200sgd::kClNP));
   lc.dynamicSmemBytes = c->cluster_smem;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
@@ -597,7 +605,7 @@ int launch_epoch(sgd_ctx* c, int32_t epoch, int buf, int* launches) {
     p.tile_log2 = c->cluster_tile_log2;
     cudaLaunchConfig_t lc = {};
     lc.gridDim = dim3(c->cluster_cs);
-    lc.blockDim = dim3(32 * (b200sgd::kClNW + 1));
+    lc.blockDim = dim3(32 * (b200sgd::kClNW + b200sgd::kClNP));
     lc.dynamicSmemBytes = c->cluster_smem;
     lc.stream = c->stream;
     cudaLaunchAttribute at[1];
@@ -607,7 +615,7 @@ int launch_epoch(sgd_ctx* c, int32_t epoch, int buf, int* launches) {
     at[0].val.clusterDim.z = 1;
     lc.attrs = at;
     lc.numAttrs = 1;
-    CUDA_TRY(cudaLaunchKernelExC(&lc, (const void*)b200sgd::sgd_cluster_epoch_kernel, args));
+    CUDA_TRY(cudaLaunchKernelExC(&lc, c->cluster_fn, args));
     *launches += 1;
     return SGD_OK;
   }

@@ -29,20 +29,22 @@
 
 namespace b200sgd {
 
+constexpr int kClNP = 4;              // producer warps (a round's indices come from HBM: ~1600 cycles per round and warp)
 constexpr int kClNW = 8;              // consumer warps
 constexpr int kClCT = 32 * kClNW;     // consumer threads
 constexpr int kClTileRows = 32;       // rows per ring tile = one producer round (8 x gather4)
 constexpr int kClMaxCS = 16;          // CTAs per cluster (16 needs the non-portable opt-in)
 constexpr int kClMaxTiles = 16;
+constexpr int kClMaxChunk = 4;        // ring tiles whose phase A runs as one block
 // shared memory map (bytes)
 constexpr uint32_t kClOffFull = 0;      // uint64 full[16]
 constexpr uint32_t kClOffEmpty = 128;   // uint64 empty[16]
 constexpr uint32_t kClOffRecvBar = 256; // uint64 recv[2]
 constexpr uint32_t kClOffW = 512;       // float w_s[128]
-constexpr uint32_t kClOffR = 1024;      // float r_s[2][32]
-constexpr uint32_t kClOffSend = 1536;   // float send[2][8 warps][32]
-constexpr uint32_t kClOffRecv = 3584;   // float recv[2][2*kClMaxCS][128]
-constexpr uint32_t kClOffRing = kClOffRecv + 2 * 2 * kClMaxCS * 128 * 4;  // 36352, 128-byte aligned
+constexpr uint32_t kClOffR = 1024;      // float r_s[2][kClMaxChunk][32]
+constexpr uint32_t kClOffSend = 2048;   // float send[2][128]
+constexpr uint32_t kClOffRecv = 3072;   // float recv[2][kClMaxCS][128]
+constexpr uint32_t kClOffRing = kClOffRecv + 2 * kClMaxCS * 128 * 4;  // 19456, 128-byte aligned
 constexpr size_t kClFixedSmem = kClOffRing;
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -78,13 +80,24 @@ __device__ __forceinline__ void mbar_wait_guarded(uint32_t bar, uint32_t parity,
     if (guard.expired(err, 4u)) break;
   }
 }
+// remote 4-byte store into another CTA's shared memory; completes 4 bytes on THAT CTA's mbarrier
+__device__ __forceinline__ void st_async_f32(uint32_t dst_cluster, float v, uint32_t bar_cluster) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(dst_cluster),
+               "r"(__float_as_uint(v)), "r"(bar_cluster)
+               : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
 // EpochParams fields used: rec_map, ld, C, perm, B, nb, first_step, a, w, g_last, ntiles, tile_log2,
-// slot_bytes, loss.  gridDim.x == cluster size (one cluster).
-__global__ void __launch_bounds__(32 * (kClNW + 1), 1) sgd_cluster_epoch_kernel(const __grid_constant__ EpochParams p) {
+// slot_bytes, loss, err.  gridDim.x == cluster size (one cluster).
+//   CHUNK = ring tiles per phase-A block (1, 2 or 4: the host takes the tiles of a step, capped at 4)
+//   PROF  = (B200SGD_PHASE_PROFILE=1) lane 0 of consumer warp 0 stores the SM clock at the marks of the
+//           middle step into p.dbg[cta][0..7], the clock at the end of the step before into p.dbg[grid+cta][0]
+template <int CHUNK, bool PROF = false>
+__global__ void __launch_bounds__(32 * (kClNW + kClNP), 1) sgd_cluster_epoch_kernel(const __grid_constant__ EpochParams p) {
+  static_assert(CHUNK >= 1 && CHUNK <= kClMaxChunk, "r_s holds kClMaxChunk tiles of residuals");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* w_s = reinterpret_cast<float*>(smem_raw + kClOffW);
   float* r_s = reinterpret_cast<float*>(smem_raw + kClOffR);
@@ -109,11 +122,16 @@ __global__ void __launch_bounds__(32 * (kClNW + 1), 1) sgd_cluster_epoch_kernel(
     mbar_init(recvbar0 + 8u, 1);
     fence_barrier_init();
     // arm the receive barriers of steps 0 and 1 before anybody can send (later ones: one step ahead)
-    const uint32_t expect0 = (uint32_t)(cluster_nctarank() * 2u * (uint32_t)((p.C + 31) >> 5) * 128u);
+    const uint32_t expect0 = cluster_nctarank() * (((uint32_t)p.C * 4u + 15u) & ~15u);
     mbar_arrive_expect_tx(recvbar0, expect0);
     mbar_arrive_expect_tx(recvbar0 + 8u, expect0);
   }
   for (int c = tid; c < 128; c += blockDim.x) w_s[c] = (c < p.C) ? p.w[c] : 0.0f;
+  // phase B reads whole tiles (rows beyond a short slice are multiplied by a zero residual): the
+  // ring must never hold bit patterns of NaN or Inf
+  for (uint32_t i = tid; i < (uint32_t)p.ntiles * tile_bytes / 16u; i += blockDim.x)
+    reinterpret_cast<float4*>(ring)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  fence_proxy_async_smem();  // the TMA writes that follow go through the async proxy
   __syncthreads();
   cluster_sync_all();  // every CTA's barriers exist before anybody sends
 
@@ -121,28 +139,36 @@ __global__ void __launch_bounds__(32 * (kClNW + 1), 1) sgd_cluster_epoch_kernel(
   const int n = (int)(slice_lo(p.B, cta + 1, CS) - lo);  // my rows of every step
   const int nt = (n + kClTileRows - 1) / kClTileRows;
 
-  if (warp == 0) {
-    // ===================================== PRODUCER =====================================
-    // round = up to 32 rows of one step = one ring tile: lane 0 does the flow control, then one
-    // tile::gather4 per four rows; the indices of the next round are in flight meanwhile.
+  if (warp < kClNP) {
+    // ===================================== PRODUCERS =====================================
+    // round = up to 32 rows of one step = one ring tile; producer warp w issues rounds w, w + NP, ...:
+    // lane 0 does the flow control, then one tile::gather4 per four rows.  The indices of a warp's next
+    // round are in flight while it issues the current one (they come from HBM, ~1600 cycles: one warp
+    // alone sustains only one round per that time).
     const int32_t* src = p.perm + (int64_t)p.first_step * p.B + lo;
     int s = 0, j0 = 0;
     uint32_t tq = 0;
-    int cnt = (n > 0 && p.nb > 0) ? min(kClTileRows, n) : 0;
-    int32_t idx = 0;
-    if (lane < cnt) idx = __ldg(src + lane);
-    while (cnt > 0) {
-      const int cur_cnt = cnt;
-      const int32_t cur_idx = idx;
-      const uint32_t cur_tq = tq;
-      j0 += cur_cnt;
+    auto advance = [&]() {  // to the next round of the CTA's sequence
+      if (s >= p.nb || n <= 0) return;
+      j0 += min(kClTileRows, n - j0);
       ++tq;
       if (j0 >= n) {
         j0 = 0;
         ++s;
         src += p.B;
       }
-      cnt = (s < p.nb) ? min(kClTileRows, n - j0) : 0;
+    };
+    auto round_cnt = [&]() -> int { return (s < p.nb && n > 0) ? min(kClTileRows, n - j0) : 0; };
+    for (int k = 0; k < warp; ++k) advance();
+    int cnt = round_cnt();
+    int32_t idx = 0;
+    if (lane < cnt) idx = __ldg(src + j0 + lane);
+    while (cnt > 0) {
+      const int cur_cnt = cnt;
+      const int32_t cur_idx = idx;
+      const uint32_t cur_tq = tq;
+      for (int k = 0; k < kClNP; ++k) advance();
+      cnt = round_cnt();
       idx = 0;
       if (lane < cnt) idx = __ldg(src + j0 + lane);
 
@@ -168,111 +194,186 @@ __global__ void __launch_bounds__(32 * (kClNW + 1), 1) sgd_cluster_epoch_kernel(
     }
   } else {
     // ======================================= CONSUMERS =======================================
-    const int ctid = tid - 32, cw = warp - 1;
+    const int ctid = tid - 32 * kClNP, cw = warp - kClNP;
     const int rg = lane >> 3, sl = lane & 7;  // phase A: row group of the warp, sub-lane within the row
-    const int hb = cw >> 2, cwi = cw & 3;     // phase B: row half of the tile, block of 32 columns
-    const int colB = 32 * cwi + lane;         // my gradient column
+    const int hp = lane >> 4;                 // phase B: row parity of this half warp ...
+    const int colB = 16 * cw + (lane & 15);   // ... and its gradient column (16 columns per warp)
     const int C = p.C, ld = (int)p.ld, ld4 = ld >> 2;
     const float Bf = (float)p.B, a = p.a;
-    const int ncw = (C + 31) >> 5;            // column blocks that carry features
-    const bool sender = cwi < ncw;
-    const uint32_t expect = (uint32_t)(CS * 2 * ncw * 128);  // bytes every CTA receives per step
-    const int nsrc = 2 * CS;
+    const uint32_t expect = (uint32_t)CS * (((uint32_t)C * 4u + 15u) & ~15u);  // bytes every CTA receives per step
+    const bool armer = ctid == kClCT - 1;  // arms the receive barriers (kept off warp 0's path)
+    const uint32_t msg_bytes = ((uint32_t)C * 4u + 15u) & ~15u;  // the CTA's column sums, whole 16-byte units
+    const int rowA = cw * 4 + rg;             // my row of every tile in phase A
+    const int rslot = (rowA & 1) * 16 + (rowA >> 1);  // residuals are stored even rows first, then odd rows
+    const int nch0 = min(CHUNK, nt);          // tiles in the first phase-A block of a step
 
     double loss_abs = 0.0, loss_sq = 0.0;  // running training loss (lane sl == 0 of every row group)
-    uint32_t tq = 0;
+    uint32_t tq = 0, chunk_seq = 0;
+    int cur_s = 0;
+    auto mark = [&](int i) {
+      if (PROF && ctid == 0 && p.dbg != nullptr) {
+        const long long t = clock64();
+        if (cur_s == p.nb / 2) p.dbg[(int64_t)cta * 8 + i] = (unsigned long long)t;
+        if (cur_s == p.nb / 2 - 1 && i == 7) p.dbg[((int64_t)CS + cta) * 8] = (unsigned long long)t;
+      }
+    };
+
+    // rows of a phase-A block: wait for the tiles, fetch my row of each into registers
+    const unsigned char* tb[CHUNK];
+    float4 x[CHUNK][4];
+    float y[CHUNK];
+    auto load_block = [&](int t0, int nch) {
+#pragma unroll
+      for (int u = 0; u < CHUNK; ++u) {
+        const uint32_t q = tq + (uint32_t)u;
+        const uint32_t tile = q & tile_mask;
+        tb[u] = ring + (size_t)tile * tile_bytes;
+        if (u < nch) mbar_wait_guarded(full0 + 8u * tile, (q >> p.tile_log2) & 1u, p.err);
+      }
+#pragma unroll
+      for (int u = 0; u < CHUNK; ++u) {
+        const bool live = u < nch && rowA < n - (t0 + u) * kClTileRows;
+        const float4* row = reinterpret_cast<const float4*>(tb[u] + (size_t)rowA * p.slot_bytes);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          x[u][k] = (live && sl + 8 * k < ld4) ? row[sl + 8 * k] : make_float4(0.f, 0.f, 0.f, 0.f);
+        y[u] = live ? reinterpret_cast<const float*>(row)[C] : 0.f;  // the label rides in the record
+      }
+    };
+    if (p.nb > 0) load_block(0, nch0);
 
     for (int s = 0; s < p.nb; ++s) {
+      if (PROF) cur_s = s;
       const int par = s & 1;
       const uint32_t rbar = recvbar0 + 8u * par;
       // arm the barrier of step s+1: its previous phase (step s-1) is complete and every local waiter
       // has left it (end-of-step barrier); nobody can send step s+1 before it has my step s
-      if (ctid == 0 && s >= 1 && s + 1 < p.nb) mbar_arrive_expect_tx(recvbar0 + 8u * (par ^ 1), expect);
+      if (armer && s >= 1 && s + 1 < p.nb) mbar_arrive_expect_tx(recvbar0 + 8u * (par ^ 1), expect);
       float4 wv[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) wv[k] = reinterpret_cast<const float4*>(w_s)[sl + 8 * k];
-      float acc0 = 0.f, acc1 = 0.f;  // column colB over my row half, even / odd rows
-      for (int ti = 0; ti < nt; ++ti, ++tq) {
-        const uint32_t tile = tq & tile_mask;
-        const uint32_t use = tq >> p.tile_log2;
-        const int cnt = min(kClTileRows, n - ti * kClTileRows);
-        const unsigned char* tbase = ring + (size_t)tile * tile_bytes;
-        float* rr = r_s + (tq & 1u) * 32;
-        // ---- phase A: residual of row cw*4 + rg  (r = x.w - y, sgd_thrust.cu:43-48 / :352-364)
-        const int r = cw * 4 + rg;
-        const bool live = r < cnt;
-        const float4* row = reinterpret_cast<const float4*>(tbase + (size_t)r * p.slot_bytes);
-        mbar_wait_guarded(full0 + 8u * tile, use & 1u, p.err);
-        float4 x[4];
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};  // column colB over the rows of my parity
+      // the tiles of the step, CHUNK at a time: phase A of all of them as one straight-line block
+      // (their latencies overlap), one CTA barrier, phase B of all of them.  The rows of the first
+      // block are already in registers (fetched while the previous step's exchange was in flight).
+      for (int t0 = 0; t0 < nt; t0 += CHUNK, ++chunk_seq) {
+        const int nch = min(CHUNK, nt - t0);
+        float* rr = r_s + (chunk_seq & 1u) * (kClMaxChunk * 32);
+        if (t0 > 0) load_block(t0, nch);
+        mark(0);  // rows in registers
+        // ---- phase A: residual of row rowA of every tile  (r = x.w - y, sgd_thrust.cu:43-48 / :352-364)
+        float dot[CHUNK];
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          x[k] = (live && sl + 8 * k < ld4) ? row[sl + 8 * k] : make_float4(0.f, 0.f, 0.f, 0.f);
-        const float y = live ? reinterpret_cast<const float*>(row)[C] : 0.f;  // the label rides in the record
-        float d[4];
+        for (int u = 0; u < CHUNK; ++u) {
+          float d[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {  // four independent chains; w_s is zero for the label and the padding
-          d[k] = x[k].x * wv[k].x;
-          d[k] = fmaf(x[k].y, wv[k].y, d[k]);
-          d[k] = fmaf(x[k].z, wv[k].z, d[k]);
-          d[k] = fmaf(x[k].w, wv[k].w, d[k]);
-        }
-        float dot = (d[0] + d[1]) + (d[2] + d[3]);
-        dot += __shfl_xor_sync(0xffffffffu, dot, 1);
-        dot += __shfl_xor_sync(0xffffffffu, dot, 2);
-        dot += __shfl_xor_sync(0xffffffffu, dot, 4);
-        const float res = dot - y;  // rows beyond the tile: 0
-        if (sl == 0) {
-          rr[r] = res;
-          loss_abs += (double)fabsf(res);
-          loss_sq += (double)res * (double)res;
-        }
-        consumer_bar<kClCT>();
-        // ---- phase B: res[r] * x[r][colB] over the rows 16*hb .. 16*hb+15 of the tile
-        if (colB < ld) {
-          const float* col = reinterpret_cast<const float*>(tbase) + colB;
-          const int q1 = min(cnt, 16 * hb + 16);
-          int q = 16 * hb;
-#pragma unroll 4
-          for (; q + 1 < q1; q += 2) {
-            acc0 = fmaf(rr[q], col[(size_t)q * ld], acc0);
-            acc1 = fmaf(rr[q + 1], col[(size_t)(q + 1) * ld], acc1);
+          for (int k = 0; k < 4; ++k) {  // independent chains; w_s is zero for the label and the padding
+            d[k] = x[u][k].x * wv[k].x;
+            d[k] = fmaf(x[u][k].y, wv[k].y, d[k]);
+            d[k] = fmaf(x[u][k].z, wv[k].z, d[k]);
+            d[k] = fmaf(x[u][k].w, wv[k].w, d[k]);
           }
-          if (q < q1) acc0 = fmaf(rr[q], col[(size_t)q * ld], acc0);
+          dot[u] = (d[0] + d[1]) + (d[2] + d[3]);
+        }
+#pragma unroll
+        for (int m = 1; m <= 4; m <<= 1) {
+#pragma unroll
+          for (int u = 0; u < CHUNK; ++u) dot[u] += __shfl_xor_sync(0xffffffffu, dot[u], m);
+        }
+#pragma unroll
+        for (int u = 0; u < CHUNK; ++u) {
+          const float res = dot[u] - y[u];  // rows beyond the step's slice: 0
+          if (sl == 0) {
+            rr[u * 32 + rslot] = res;
+            loss_abs += (double)fabsf(res);
+            loss_sq += (double)res * (double)res;
+          }
+        }
+        mark(1);  // phase A done
+        consumer_bar<kClCT>();
+        mark(2);  // residuals visible
+        // ---- phase B: res[r] * x[r][colB] over the 16 rows of my parity of every tile.  No row
+        // bound: rows beyond the slice have res = 0 and finite (stale or zero-initialised) records.
+        // (Adjacent rows are ld = 16 mod 32 floats apart for C = 100: the half warps hit disjoint banks.)
+        if (colB < ld) {
+#pragma unroll
+          for (int u = 0; u < CHUNK; ++u) {
+            if (u < nch) {
+              const float* col = reinterpret_cast<const float*>(tb[u]) + (size_t)hp * ld + colB;
+              const float4* r4 = reinterpret_cast<const float4*>(rr + u * 32 + 16 * hp);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float4 rv = r4[j];  // rows 2*(4j..4j+3) + hp
+                acc[0] = fmaf(rv.x, col[(size_t)(8 * j + 0) * ld], acc[0]);
+                acc[1] = fmaf(rv.y, col[(size_t)(8 * j + 2) * ld], acc[1]);
+                acc[2] = fmaf(rv.z, col[(size_t)(8 * j + 4) * ld], acc[2]);
+                acc[3] = fmaf(rv.w, col[(size_t)(8 * j + 6) * ld], acc[3]);
+              }
+            }
+          }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(empty0 + 8u * tile);
+        if (lane == 0) {
+#pragma unroll
+          for (int u = 0; u < CHUNK; ++u)
+            if (u < nch) mbar_arrive(empty0 + 8u * ((tq + (uint32_t)u) & tile_mask));
+        }
+        tq += (uint32_t)nch;
       }
 
-      // ---- exchange: my warp's 32 column sums -> slot [par][2*cta + hb][32*cwi ..] of EVERY CTA
-      if (sender) {
-        float* mine = send_s + (par * kClNW + cw) * 32;
-        mine[lane] = acc0 + acc1;
+      // ---- exchange: fold the two row parities (one shuffle), stage the CTA's C column sums in shared
+      // memory, and send them with ONE bulk copy per destination CTA into slot [par][cta] there,
+      // completing the bytes on the destination's barrier; warp w serves CTAs 2w and 2w+1.  (Issuing
+      // a bulk copy costs a warp ~60 cycles: 16 destinations per warp were 1000 cycles per step.)
+      {
+        float v = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        float* mine = send_s + par * 128;
+        if (lane < 16) mine[16 * cw + lane] = v;
         fence_proxy_async_smem();  // the bulk copy reads shared memory through the async proxy
-        __syncwarp();
-        if (lane < CS) {
-          const uint32_t slot = smem0 + kClOffRecv + (uint32_t)(((par * 2 * kClMaxCS + 2 * cta + hb) * 128 + 32 * cwi) * 4);
-          bulk_s2cluster(map_to_cta(slot, (uint32_t)lane), smem_u32(mine), 128u, map_to_cta(rbar, (uint32_t)lane));
+        consumer_bar<kClCT>();
+        const int dst = 2 * cw + lane;
+        if (lane < 2 && dst < CS) {
+          const uint32_t slot = smem0 + kClOffRecv + (uint32_t)((par * kClMaxCS + cta) * 128 * 4);
+          bulk_s2cluster(map_to_cta(slot, (uint32_t)dst), smem_u32(mine), msg_bytes, map_to_cta(rbar, (uint32_t)dst));
         }
+        mark(3);  // sent
       }
-      // ---- every CTA adds the 2*CS partials of a column in the same order and applies
+      // the rows of the next step do not depend on the weights: fetch them while the exchange is in flight
+      if (s + 1 < p.nb) load_block(0, nch0);
+      mark(4);
+      // ---- every CTA adds the CS partials of a column in the same order and applies
       //      w = a * (g / B) + w   (sgd_thrust.cu:269, main.cu:147-150 / :287-290)
       if (ctid < 128) {
         mbar_wait_guarded(rbar, (uint32_t)(s >> 1) & 1u, p.err);
+        mark(5);  // all partials arrived
         if (ctid < C) {
-          const float* rb = recv_s + (size_t)par * 2 * kClMaxCS * 128 + ctid;
+          const float* rb = recv_s + (size_t)par * kClMaxCS * 128 + ctid;
           float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
-          for (int i = 0; i < nsrc; i += 4) {
+#pragma unroll
+          for (int i = 0; i < 8; i += 4) {
             t0 += rb[(i + 0) * 128];
             t1 += rb[(i + 1) * 128];
             t2 += rb[(i + 2) * 128];
             t3 += rb[(i + 3) * 128];
+          }
+          if (CS > 8) {
+#pragma unroll
+            for (int i = 8; i < 16; i += 4) {
+              t0 += rb[(i + 0) * 128];
+              t1 += rb[(i + 1) * 128];
+              t2 += rb[(i + 2) * 128];
+              t3 += rb[(i + 3) * 128];
+            }
           }
           const float gs = ((t0 + t1) + (t2 + t3)) / Bf;
           w_s[ctid] = fmaf(a, gs, w_s[ctid]);
           if (cta == 0 && s == p.nb - 1) p.g_last[ctid] = gs;
         }
       }
+      mark(6);  // weights updated
       consumer_bar<kClCT>();  // w_s complete
+      mark(7);
     }
 
     // running loss of the launch: per-CTA sums of |r| and r^2

@@ -58,16 +58,12 @@ def run(R, C, B, lr=0.01, epochs=3, warm=1, shuffle=True, **kw):
                "frac_of_peak": round(best["bytes"] / (best["steploop_ms"] * 1e-3) * 1e-9 / PEAK, 4),
                "msamples_per_s": round(best["samples"] / (best["steploop_ms"] * 1e-3) * 1e-6, 1),
                "finite": bool(np.all(np.isfinite(w)))}
-        if phases and out["kernel"][0] == 0:   # small-step kernel: column warp 0 / owner warp 4 of every CTA
+        if phases and out["kernel"][0] == 0 and out["kernel"][1] > 0:   # cluster kernel: SM clock at the marks of one step
             col = eng.debug_phase_cycles().astype(np.int64)
-            own = eng.debug_step_timeline().astype(np.int64)
-            t0 = col[:, 7:8]   # end of the previous step (column warp's clock; same SM clock for the owner warp)
-            cn = ["rows_landed", "phaseA", "barA", "phaseB", "published", "weights", "end_bar"]
-            on = ["rows_landed", "phaseA", "barA", "-", "gathered", "answered", "end_bar"]
-            cr, orr = col[:, :7] - t0, own[:, :7] - t0
-            out["column_warp_clock_min_med_max"] = {n: [int(cr[:, i].min()), int(np.median(cr[:, i])), int(cr[:, i].max())] for i, n in enumerate(cn)}
-            out["owner_warp_clock_min_med_max"] = {n: [int(orr[:, i].min()), int(np.median(orr[:, i])), int(orr[:, i].max())] for i, n in enumerate(on) if n != "-"}
-            out["owner_prev_end"] = [int((own[:, 7] - col[:, 7]).min()), int((own[:, 7] - col[:, 7]).max())]
+            prev = eng.debug_step_timeline().astype(np.int64)[:, 0:1]
+            cn = ["step_top", "phaseA", "barA", "phaseB+sent", "next_rows_loaded", "all_arrived", "updated", "end_bar"]
+            cr = col - prev
+            out["step_clock_min_med_max"] = {n: [int(cr[:, i].min()), int(np.median(cr[:, i])), int(cr[:, i].max())] for i, n in enumerate(cn)}
         elif phases:
             out["phase_cycles_mean_max"] = phases
             tl = eng.debug_step_timeline().astype(np.int64)
