@@ -360,15 +360,17 @@ def main() -> int:
                                    f"{rows_pg} rows per GPU), batch {B}, lr {lr}, {steps_epoch} steps per epoch; "
                                    "one bench step = one SGD epoch incl. its bit-exact permutation",
                        "l2": "inputs larger than L2 (per-GPU data %.1f GB vs 126 MB)" % (4 * rows_pg * (cols + 1) / 1e9),
-                       "engine": args.engine, "grid": eng.grid, "reduce": {1: "allgather", 2: "scatter", 3: "dataflow-2hop", 4: "dataflow-1hop"}[eng.reduce],
-                       "kernel": "sgd_epoch_kernel<KC=%d,U=%d,NW=%d>" % eng.kernel_shape,
+                       "engine": args.engine, "grid": eng.grid,
+                       "reduce": "cluster all-gather in shared memory" if eng.cluster_size else
+                                 {1: "allgather", 2: "scatter", 3: "dataflow-2hop", 4: "dataflow-1hop"}[eng.reduce],
+                       "kernel": eng.kernel_name,
                        "ring_slots": eng.nslots, "smem_bytes": eng.smem_bytes,
                        "parallelism": f"dp{N} row-sharded, fused NVLink gradient exchange" if N > 1 else "single GPU"},
             "steploop": {"samples_per_s": samples / loop_s, "ms_per_epoch": loop_s * 1e3 / K,
                          "us_per_sgd_step": loop_s * 1e6 / t["steps"], "hbm_gbs_per_gpu": achieved},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": profile_traffic(args.workload),
-                         "peak_source": peak_src, "kernel": "sgd_epoch_kernel (1 launch per epoch)",
+                         "peak_source": peak_src, "kernel": eng.kernel_name.split("<")[0].split(" (")[0] + " (1 launch per epoch)",
                          "algorithmic_bytes_per_launch": bytes_rank // K},
             "clocks": clocks,
             "gpu_launches": t["launches"],

@@ -131,7 +131,8 @@ class SGDEngine:
         self.num_batches = out.reserved[0]
         self.grid, self.reduce, self.engine = out.grid, out.reduce, out.engine
         self.nslots, self.smem_bytes = out.reserved[1], out.reserved[2]
-        self.kernel_shape = (out.reserved[3], out.reserved[4], out.reserved[5])  # KC, U, NW
+        self.kernel_shape = (out.reserved[3], out.reserved[4], out.reserved[5])  # KC, U, NW; KC = 0: small-step kernels
+        self.cluster_size = out.reserved[4] if out.reserved[3] == 0 else 0             # CTAs of the one cluster, or 0
         self.ld = out.reserved[6]
         self.rank, self.nranks = rank, nranks
         self.local_rows = int(lib.sgd_local_rows(self._h))
@@ -270,6 +271,15 @@ class SGDEngine:
         off = np.empty(self.num_batches + 1, dtype=np.int64)
         L.check(L.load().sgd_get_local_schedule(self._h, _ptr(local), local.shape[0], _ptr(off)))
         return local[: off[self.num_batches]].copy(), off
+
+    @property
+    def kernel_name(self) -> str:
+        kc, u, nw = self.kernel_shape
+        if kc == 0 and u > 0:
+            return "sgd_cluster_epoch_kernel (one %d-CTA cluster, %d consumer warps)" % (u, nw)
+        if kc == 0:
+            return "sgd_small_epoch_kernel"
+        return "sgd_epoch_kernel<KC=%d,U=%d,NW=%d%s%s>" % (abs(kc), abs(u), nw, ",WIDE" if kc < 0 else "", ",NARROW8" if u < 0 else "")
 
     def debug_phase_cycles(self) -> np.ndarray:
         """[grid, 8] cycle sums per phase of the last launch (needs B200SGD_PHASE_PROFILE=1)."""

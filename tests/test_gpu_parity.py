@@ -185,11 +185,48 @@ def test_reduction_modes_and_grids(reduce, grid):
 
 
 @pytest.mark.parametrize("C,B", [(100, 1000), (512, 256), (2048, 96)])
-def test_graph_engine(C, B):
+def test_graph_engine(C, B, monkeypatch):
+    monkeypatch.setenv("B200SGD_CLUSTER", "0")   # the persistent engine on the same (generic) kernel
     X, y, _ = make_regression(3000, C, seed=C + 1)
     w_p, _ = check_run(X, y, B, 0.02, 2, engine=_lib.SGD_ENGINE_PERSISTENT)
     w_g, _ = check_run(X, y, B, 0.02, 2, engine=_lib.SGD_ENGINE_GRAPH)
     assert np.array_equal(w_p, w_g)     # same kernel, same order of operations
+
+
+# ------------------------------------------------------------------ the cluster kernel (small steps, narrow rows)
+@pytest.mark.parametrize("cluster", [8, 16])
+@pytest.mark.parametrize("R,C,B", [
+    (3000, 1, 48), (3000, 3, 100), (4000, 31, 333), (5000, 64, 777), (20000, 100, 1000),
+    (9000, 127, 2048),      # 128 / 256 rows per CTA and step: four-tile blocks, two blocks per step at 8 CTAs
+    (2500, 100, 1200),      # 2 steps, tail rows dropped
+    (5000, 15, 49),         # fewer rows than lanes in most CTAs
+])
+def test_cluster_kernel_shapes(R, C, B, cluster, monkeypatch):
+    monkeypatch.setenv("B200SGD_CLUSTER", str(cluster))
+    X, y, _ = make_regression(R, C, seed=R + C + B)
+    with pkg.SGDEngine(R, C, B, 0.02) as probe:
+        assert probe.kernel_shape[0] == 0 and probe.kernel_shape[1] == cluster and probe.grid == cluster
+    check_run(X, y, B, 0.02, 3)
+
+
+def test_cluster_kernel_agrees_with_the_generic_kernel(monkeypatch):
+    X, y, _ = make_regression(20000, 100, seed=77)
+    w_c, mae_c = check_run(X, y, 1000, 0.05, 3)
+    monkeypatch.setenv("B200SGD_CLUSTER", "0")
+    with pkg.SGDEngine(20000, 100, 1000, 0.05) as probe:
+        assert probe.kernel_shape[0] != 0
+    w_g, mae_g = check_run(X, y, 1000, 0.05, 3)
+    assert rel_l2(w_c, w_g) < 1e-5 and abs(mae_c - mae_g) <= 1e-5 * abs(mae_g) + 1e-6 * float(np.mean(np.abs(y)))
+
+
+def test_cluster_kernel_is_not_used_where_it_does_not_apply():
+    for kw in (dict(C=128, B=1000), dict(C=100, B=4096), dict(C=100, B=24)):
+        with pkg.SGDEngine(20000, kw["C"], kw["B"], 0.1) as eng:
+            assert eng.kernel_shape[0] != 0, kw
+    with pkg.SGDEngine(20000, 100, 1000, 0.1, keep_residuals=True) as eng:
+        assert eng.kernel_shape[0] != 0
+    with pkg.SGDEngine(20000, 100, 1000, 0.1, engine=_lib.SGD_ENGINE_GRAPH) as eng:
+        assert eng.kernel_shape[0] != 0
 
 
 def test_graph_engine_many_steps_reuses_graph():
