@@ -27,7 +27,6 @@
 #include "host_rng.hpp"
 #include "sgd_kernels.cuh"
 #include "sgd_cluster_kernel.cuh"
-#include "sgd_small_kernel.cuh"
 #include "shuffle_kernels.cuh"
 
 namespace {
@@ -191,15 +190,11 @@ struct sgd_ctx {
   int grid = 0, reduce_mode = 0, ntiles = 0, tile_log2 = 0, engine = SGD_ENGINE_PERSISTENT;
   CUtensorMap rec_map{};
   bool use_gather4 = false;  // narrow rows: TMA tile::gather4, four rows per instruction
-  // sgd_small_epoch_kernel (small steps of narrow rows): eligibility and its own ring geometry
-  bool have_rec_map = false;
-  // sgd_cluster_epoch_kernel (small steps of narrow rows, single GPU): the grid is one cluster
+  bool have_rec_map = false;  // the tensor map of the records exists
+  // sgd_cluster_epoch_kernel (small steps of narrow rows): the grid is one cluster of cluster_cs CTAs
   int cluster_cs = 0, cluster_ntiles = 0, cluster_tile_log2 = 0;
   const void* cluster_fn = nullptr;
   size_t cluster_smem = 0;
-  bool small_ok = false;
-  int small_ntiles = 0, small_tile_log2 = 0;
-  size_t small_smem = 0;
   int nprod = 1;  // producer warps
   int tile_rows = 0;
   size_t smem_bytes = 0;
@@ -288,14 +283,14 @@ int configure_launch(sgd_ctx* c) {
       grid = c->num_sms;
     }
   }
-  // Small steps of narrow rows on one GPU: the whole grid is one thread-block cluster that exchanges
-  // the gradient through distributed shared memory (sgd_cluster_kernel.cuh).  B200SGD_CLUSTER=0
+  // Small steps of narrow rows: the whole grid is one thread-block cluster that exchanges the gradient
+  // through distributed shared memory (sgd_cluster_kernel.cuh); multi-GPU adds one NVLink hop.  B200SGD_CLUSTER=0
   // switches it off, 8 / 16 pick the cluster size (A/B runs).
   c->cluster_cs = 0;
   {
     const char* e = std::getenv("B200SGD_CLUSTER");
     const int want = e ? std::atoi(e) : b200sgd::kClMaxCS;
-    if ((want == 8 || want == 16) && c->ld <= 128 && c->cfg.nranks == 1 && c->cfg.engine != SGD_ENGINE_GRAPH &&
+    if ((want == 8 || want == 16) && c->ld <= 128 && c->cfg.engine != SGD_ENGINE_GRAPH &&
         (c->cfg.reduce == SGD_REDUCE_AUTO || c->cfg.reduce == SGD_REDUCE_DATAFLOW) &&
         !(c->cfg.flags & SGD_FLAG_RESIDUALS) && rows_step >= 48 && rows_step <= 2048 &&
         (c->cfg.grid <= 0 || c->cfg.grid == want)) {
@@ -372,13 +367,23 @@ int configure_cluster(sgd_ctx* c) {
   c->cluster_tile_log2 = lg;
   c->cluster_smem = b200sgd::kClFixedSmem + (size_t)ntiles * tile_bytes;
   // tiles of one CTA per step -> phase-A block size
-  const int64_t rows_cta = ((int64_t)c->B + cs - 1) / cs;
-  const int tiles_step = (int)((rows_cta + b200sgd::kClTileRows - 1) / b200sgd::kClTileRows);
   const bool prof = c->d_dbg != nullptr;
+  const bool multi = c->cfg.nranks > 1;
+  const int64_t rows_rank = std::max<int64_t>(1, (int64_t)c->B / c->cfg.nranks);
+  const int tiles = (int)(((rows_rank + cs - 1) / cs + b200sgd::kClTileRows - 1) / b200sgd::kClTileRows);
   const void* fn = nullptr;
-  if (tiles_step <= 1) fn = prof ? (const void*)b200sgd::sgd_cluster_epoch_kernel<1, true> : (const void*)b200sgd::sgd_cluster_epoch_kernel<1>;
-  else if (tiles_step <= 2) fn = prof ? (const void*)b200sgd::sgd_cluster_epoch_kernel<2, true> : (const void*)b200sgd::sgd_cluster_epoch_kernel<2>;
-  else fn = prof ? (const void*)b200sgd::sgd_cluster_epoch_kernel<4, true> : (const void*)b200sgd::sgd_cluster_epoch_kernel<4>;
+  using namespace b200sgd;
+  if (multi) {
+    fn = tiles <= 1 ? (const void*)sgd_cluster_epoch_kernel<1, false, true>
+       : tiles <= 2 ? (const void*)sgd_cluster_epoch_kernel<2, false, true>
+                    : (const void*)sgd_cluster_epoch_kernel<4, false, true>;
+  } else if (prof) {
+    fn = tiles <= 1 ? (const void*)sgd_cluster_epoch_kernel<1, true> : tiles <= 2 ? (const void*)sgd_cluster_epoch_kernel<2, true>
+                                                                                  : (const void*)sgd_cluster_epoch_kernel<4, true>;
+  } else {
+    fn = tiles <= 1 ? (const void*)sgd_cluster_epoch_kernel<1> : tiles <= 2 ? (const void*)sgd_cluster_epoch_kernel<2>
+                                                                            : (const void*)sgd_cluster_epoch_kernel<4>;
+  }
   c->cluster_fn = fn;
   CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->cluster_smem));
   if (cs > 8) CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
@@ -399,42 +404,6 @@ int configure_cluster(sgd_ctx* c) {
     return SGD_OK;
   }
   c->cluster_cs = cs;
-  return SGD_OK;
-}
-
-const void* small_kernel_fn(const sgd_ctx* c) {
-  if (c->cfg.nranks > 1) return (const void*)b200sgd::sgd_small_epoch_kernel<true>;
-  if (c->d_dbg != nullptr) return (const void*)b200sgd::sgd_small_epoch_kernel<false, true>;
-  return (const void*)b200sgd::sgd_small_epoch_kernel<false>;
-}
-
-// sgd_small_epoch_kernel serves small steps of narrow rows (config 2); everything else, and every
-// context that uses a feature it leaves out, runs the generic sgd_epoch_kernel.
-int configure_small(sgd_ctx* c) {
-  c->small_ok = false;
-  const int64_t rows_step = std::max<int64_t>(1, (int64_t)c->B / std::max(1, c->cfg.nranks));
-  const int64_t rows_cta = (rows_step + c->grid - 1) / c->grid;
-  if (c->cfg.nranks < 2) return SGD_OK;  // one GPU: the cluster kernel or the generic one
-  if (c->ld > 128 || !c->have_rec_map || c->grid < 2 || rows_cta > 256) return SGD_OK;
-  if (c->engine != SGD_ENGINE_PERSISTENT || c->reduce_mode != SGD_REDUCE_DATAFLOW) return SGD_OK;
-  if ((c->cfg.flags & SGD_FLAG_RESIDUALS) || c->w_copies != c->grid) return SGD_OK;
-  if (c->d_dbg != nullptr && c->cfg.nranks > 1) return SGD_OK;  // the profiled instance is single-GPU
-  if (c->cfg.nranks > 1 && !c->direct) return SGD_OK;
-  if (std::getenv("B200SGD_NO_SMALL")) return SGD_OK;
-  const size_t tile_bytes = (size_t)b200sgd::kSmallTileRows * c->ld * 4;
-  int ntiles = 2, lg = 1;
-  while (ntiles * 2 <= 16 && b200sgd::kSmallFixedSmem + (size_t)(ntiles * 2) * tile_bytes <= kMaxDynSmem) {
-    ntiles *= 2;
-    ++lg;
-  }
-  c->small_ntiles = ntiles;
-  c->small_tile_log2 = lg;
-  c->small_smem = b200sgd::kSmallFixedSmem + (size_t)ntiles * tile_bytes;
-  const void* fn = small_kernel_fn(c);
-  CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->small_smem));
-  int occ = 0;
-  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 32 * (b200sgd::kSmallNW + 1), c->small_smem));
-  c->small_ok = occ >= 1;
   return SGD_OK;
 }
 
@@ -600,7 +569,7 @@ int launch_epoch(sgd_ctx* c, int32_t epoch, int buf, int* launches) {
   CUDA_TRY(cudaMemsetAsync(c->d_bar, 0, sizeof(unsigned int), c->stream));
   c->step_tag += (uint32_t)c->nb;  // every rank advances identically: tags agree across GPUs
   void* args[] = {&p};
-  if (c->cluster_cs > 0) {  // small steps of narrow rows, one GPU: one cluster, exchange in shared memory
+  if (c->cluster_cs > 0) {  // small steps of narrow rows: one cluster, gradient exchange in shared memory
     p.ntiles = c->cluster_ntiles;
     p.tile_log2 = c->cluster_tile_log2;
     cudaLaunchConfig_t lc = {};
@@ -616,15 +585,6 @@ int launch_epoch(sgd_ctx* c, int32_t epoch, int buf, int* launches) {
     lc.attrs = at;
     lc.numAttrs = 1;
     CUDA_TRY(cudaLaunchKernelExC(&lc, c->cluster_fn, args));
-    *launches += 1;
-    return SGD_OK;
-  }
-  if (c->small_ok) {  // small steps of narrow rows: the short-chain kernel (sgd_small_kernel.cuh)
-    p.ntiles = c->small_ntiles;
-    p.tile_log2 = c->small_tile_log2;
-    const void* fn = small_kernel_fn(c);
-    CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(c->grid), dim3(32 * (b200sgd::kSmallNW + 1)), args, c->small_smem,
-                                         c->stream));
     *launches += 1;
     return SGD_OK;
   }
@@ -995,7 +955,6 @@ int sgd_create(const sgd_config* cfg, const float* X, const float* y, sgd_ctx** 
       c->peer_block[c->cfg.rank] = c->d_xchg_block;
     }
     SGD_TRY(configure_cluster(c));
-    SGD_TRY(configure_small(c));
     // main.cu:389-395: weights ~ U(0, 0.01) from the Thrust minstd stream, drawn on the host
     std::vector<float> w0(c->C);
     b200sgd::thrust_minstd_weights(w0.data(), c->C);
@@ -1150,9 +1109,9 @@ int sgd_get_config(const sgd_ctx* c, sgd_config* out) {
   out->reserved[0] = c->nb;
   out->reserved[1] = c->ntiles * c->tile_rows;
   out->reserved[2] = (int32_t)c->smem_bytes;
-  // KC: negative = column mapping; 0 = small-step kernels (U: cluster size, or 0 for the L2 variant)
-  out->reserved[3] = (c->small_ok || c->cluster_cs > 0) ? 0 : c->kc.wide ? -c->kc.KC : c->kc.KC;
-  out->reserved[4] = c->cluster_cs > 0 ? c->cluster_cs : c->small_ok ? 0 : c->kc.narrow8 ? -c->kc.U : c->kc.U;  // negative: 8 lanes per row
+  // KC: negative = column mapping; 0 = cluster kernel (then U = CTAs of the cluster)
+  out->reserved[3] = c->cluster_cs > 0 ? 0 : c->kc.wide ? -c->kc.KC : c->kc.KC;
+  out->reserved[4] = c->cluster_cs > 0 ? c->cluster_cs : c->kc.narrow8 ? -c->kc.U : c->kc.U;  // negative: 8 lanes per row
   out->reserved[5] = c->kc.NW;
   out->reserved[6] = (int32_t)c->ld;
   return SGD_OK;

@@ -72,6 +72,15 @@ __device__ __forceinline__ void bulk_s2cluster(uint32_t dst_cluster, uint32_t sr
                "r"(src_cta), "r"(bytes), "r"(bar_cluster)
                : "memory");
 }
+// tagged 8-byte words {value, tag} through global memory (cross-GPU hop): see ll_store_f4
+__device__ __forceinline__ void ll_store_f1(uint2* dst, float v, uint32_t tag) {
+  asm volatile("st.volatile.global.v2.u32 [%0], {%1,%2};" ::"l"(dst), "r"(__float_as_uint(v)), "r"(tag) : "memory");
+}
+__device__ __forceinline__ uint2 ld_volatile_u2(const uint2* p) {
+  uint2 v;
+  asm volatile("ld.volatile.global.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+  return v;
+}
 // mbarrier wait with the watchdog of the L2 spin loops: a lost message must not hang the GPU
 __device__ __forceinline__ void mbar_wait_guarded(uint32_t bar, uint32_t parity, unsigned int* err) {
   if (mbar_try_wait(bar, parity)) return;
@@ -95,7 +104,11 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
 //   CHUNK = ring tiles per phase-A block (1, 2 or 4: the host takes the tiles of a step, capped at 4)
 //   PROF  = (B200SGD_PHASE_PROFILE=1) lane 0 of consumer warp 0 stores the SM clock at the marks of the
 //           middle step into p.dbg[cta][0..7], the clock at the end of the step before into p.dbg[grid+cta][0]
-template <int CHUNK, bool PROF = false>
+//   MULTI = nranks > 1: the rank's rows of a step come from the bucketed row list (step_off); after the
+//           cluster exchange CTA 0 stores the rank's column sums as tagged words into the inbox of every
+//           peer over NVLink, every CTA polls its own rank's inbox for the peers' sums and adds the ranks'
+//           sums in rank order (identical bits on every GPU).  Inbox: ll_inbox as uint2 [2][nranks][4*C4p].
+template <int CHUNK, bool PROF = false, bool MULTI = false>
 __global__ void __launch_bounds__(32 * (kClNW + kClNP), 1) sgd_cluster_epoch_kernel(const __grid_constant__ EpochParams p) {
   static_assert(CHUNK >= 1 && CHUNK <= kClMaxChunk, "r_s holds kClMaxChunk tiles of residuals");
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -135,9 +148,18 @@ __global__ void __launch_bounds__(32 * (kClNW + kClNP), 1) sgd_cluster_epoch_ker
   __syncthreads();
   cluster_sync_all();  // every CTA's barriers exist before anybody sends
 
-  const int64_t lo = slice_lo(p.B, cta, CS);
-  const int n = (int)(slice_lo(p.B, cta + 1, CS) - lo);  // my rows of every step
-  const int nt = (n + kClTileRows - 1) / kClTileRows;
+  // my rows of step s: [off, off + n) of the row list (single GPU: the same slice of every batch)
+  auto step_rows = [&](int s, int64_t* off, int* n) {
+    const int64_t sa = (int64_t)p.first_step + s;
+    int64_t rows = p.B, o = sa * p.B;
+    if (MULTI) {
+      o = p.step_off[sa];
+      rows = p.step_off[sa + 1] - o;
+    }
+    const int64_t lo = slice_lo(rows, cta, CS);
+    *off = o + lo;
+    *n = (int)(slice_lo(rows, cta + 1, CS) - lo);
+  };
 
   if (warp < kClNP) {
     // ===================================== PRODUCERS =====================================
@@ -145,24 +167,32 @@ __global__ void __launch_bounds__(32 * (kClNW + kClNP), 1) sgd_cluster_epoch_ker
     // lane 0 does the flow control, then one tile::gather4 per four rows.  The indices of a warp's next
     // round are in flight while it issues the current one (they come from HBM, ~1600 cycles: one warp
     // alone sustains only one round per that time).
-    const int32_t* src = p.perm + (int64_t)p.first_step * p.B + lo;
-    int s = 0, j0 = 0;
+    int s = 0, j0 = 0, n = 0;
+    int64_t off = 0;
     uint32_t tq = 0;
+    auto settle = [&]() {  // to the next step in which this CTA has rows
+      while (s < p.nb) {
+        step_rows(s, &off, &n);
+        if (n > 0) break;
+        ++s;
+      }
+    };
     auto advance = [&]() {  // to the next round of the CTA's sequence
-      if (s >= p.nb || n <= 0) return;
+      if (s >= p.nb) return;
       j0 += min(kClTileRows, n - j0);
       ++tq;
       if (j0 >= n) {
         j0 = 0;
         ++s;
-        src += p.B;
+        settle();
       }
     };
-    auto round_cnt = [&]() -> int { return (s < p.nb && n > 0) ? min(kClTileRows, n - j0) : 0; };
+    auto round_cnt = [&]() -> int { return (s < p.nb) ? min(kClTileRows, n - j0) : 0; };
+    settle();
     for (int k = 0; k < warp; ++k) advance();
     int cnt = round_cnt();
     int32_t idx = 0;
-    if (lane < cnt) idx = __ldg(src + j0 + lane);
+    if (lane < cnt) idx = __ldg(p.perm + off + j0 + lane);
     while (cnt > 0) {
       const int cur_cnt = cnt;
       const int32_t cur_idx = idx;
@@ -170,7 +200,7 @@ __global__ void __launch_bounds__(32 * (kClNW + kClNP), 1) sgd_cluster_epoch_ker
       for (int k = 0; k < kClNP; ++k) advance();
       cnt = round_cnt();
       idx = 0;
-      if (lane < cnt) idx = __ldg(src + j0 + lane);
+      if (lane < cnt) idx = __ldg(p.perm + off + j0 + lane);
 
       const uint32_t tile = cur_tq & tile_mask;
       const uint32_t use = cur_tq >> p.tile_log2;
@@ -205,7 +235,12 @@ __global__ void __launch_bounds__(32 * (kClNW + kClNP), 1) sgd_cluster_epoch_ker
     const uint32_t msg_bytes = ((uint32_t)C * 4u + 15u) & ~15u;  // the CTA's column sums, whole 16-byte units
     const int rowA = cw * 4 + rg;             // my row of every tile in phase A
     const int rslot = (rowA & 1) * 16 + (rowA >> 1);  // residuals are stored even rows first, then odd rows
-    const int nch0 = min(CHUNK, nt);          // tiles in the first phase-A block of a step
+    int n;                                    // my rows of the current step
+    {
+      int64_t off_unused;
+      if (p.nb > 0) step_rows(0, &off_unused, &n); else n = 0;
+    }
+    const int cpad = 4 * ((p.C4 + 3) & ~3);   // MULTI: columns per rank in the inbox
 
     double loss_abs = 0.0, loss_sq = 0.0;  // running training loss (lane sl == 0 of every row group)
     uint32_t tq = 0, chunk_seq = 0;
@@ -222,7 +257,7 @@ __global__ void __launch_bounds__(32 * (kClNW + kClNP), 1) sgd_cluster_epoch_ker
     const unsigned char* tb[CHUNK];
     float4 x[CHUNK][4];
     float y[CHUNK];
-    auto load_block = [&](int t0, int nch) {
+    auto load_block = [&](int t0, int nch, int n) {
 #pragma unroll
       for (int u = 0; u < CHUNK; ++u) {
         const uint32_t q = tq + (uint32_t)u;
@@ -240,12 +275,18 @@ __global__ void __launch_bounds__(32 * (kClNW + kClNP), 1) sgd_cluster_epoch_ker
         y[u] = live ? reinterpret_cast<const float*>(row)[C] : 0.f;  // the label rides in the record
       }
     };
-    if (p.nb > 0) load_block(0, nch0);
+    if (p.nb > 0) load_block(0, min(CHUNK, (n + kClTileRows - 1) / kClTileRows), n);
 
     for (int s = 0; s < p.nb; ++s) {
       if (PROF) cur_s = s;
       const int par = s & 1;
       const uint32_t rbar = recvbar0 + 8u * par;
+      const int nt = (n + kClTileRows - 1) / kClTileRows;
+      int n_next = n;  // rows of the next step (MULTI: from the row list, loads in flight during the step)
+      if (MULTI && s + 1 < p.nb) {
+        int64_t off_unused;
+        step_rows(s + 1, &off_unused, &n_next);
+      }
       // arm the barrier of step s+1: its previous phase (step s-1) is complete and every local waiter
       // has left it (end-of-step barrier); nobody can send step s+1 before it has my step s
       if (armer && s >= 1 && s + 1 < p.nb) mbar_arrive_expect_tx(recvbar0 + 8u * (par ^ 1), expect);
@@ -259,7 +300,7 @@ __global__ void __launch_bounds__(32 * (kClNW + kClNP), 1) sgd_cluster_epoch_ker
       for (int t0 = 0; t0 < nt; t0 += CHUNK, ++chunk_seq) {
         const int nch = min(CHUNK, nt - t0);
         float* rr = r_s + (chunk_seq & 1u) * (kClMaxChunk * 32);
-        if (t0 > 0) load_block(t0, nch);
+        if (t0 > 0) load_block(t0, nch, n);
         mark(0);  // rows in registers
         // ---- phase A: residual of row rowA of every tile  (r = x.w - y, sgd_thrust.cu:43-48 / :352-364)
         float dot[CHUNK];
@@ -340,7 +381,7 @@ __global__ void __launch_bounds__(32 * (kClNW + kClNP), 1) sgd_cluster_epoch_ker
         mark(3);  // sent
       }
       // the rows of the next step do not depend on the weights: fetch them while the exchange is in flight
-      if (s + 1 < p.nb) load_block(0, nch0);
+      if (s + 1 < p.nb) load_block(0, min(CHUNK, (n_next + kClTileRows - 1) / kClTileRows), n_next);
       mark(4);
       // ---- every CTA adds the CS partials of a column in the same order and applies
       //      w = a * (g / B) + w   (sgd_thrust.cu:269, main.cu:147-150 / :287-290)
@@ -366,7 +407,41 @@ __global__ void __launch_bounds__(32 * (kClNW + kClNP), 1) sgd_cluster_epoch_ker
               t3 += rb[(i + 3) * 128];
             }
           }
-          const float gs = ((t0 + t1) + (t2 + t3)) / Bf;
+          float tot = (t0 + t1) + (t2 + t3);  // this GPU's rows
+          if (MULTI) {
+            // second hop, over NVLink: CTA 0 gives the rank's sum to every peer; everybody polls the
+            // own rank's inbox and adds the ranks' sums in rank order
+            const uint32_t tag = p.tag_base + (uint32_t)s + 1u;
+            const int64_t at = ((int64_t)par * p.nranks + p.rank) * cpad + ctid;
+            if (cta == 0)
+              for (int q = 0; q < p.nranks; ++q)
+                if (q != p.rank) ll_store_f1(reinterpret_cast<uint2*>(p.ll_inbox_peer[q]) + at, tot, tag);
+            const uint2* inbox = reinterpret_cast<const uint2*>(p.ll_inbox_local) + (int64_t)par * p.nranks * cpad + ctid;
+            uint2 u[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              if (q < p.nranks && q != p.rank) u[q] = ld_volatile_u2(inbox + (int64_t)q * cpad);
+            float all = 0.f;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              if (q < p.nranks) {
+                float vq = tot;
+                if (q != p.rank) {
+                  if (u[q].y != tag) {
+                    SpinGuard guard;
+                    do {
+                      if (guard.expired(p.err, 3u)) break;
+                      u[q] = ld_volatile_u2(inbox + (int64_t)q * cpad);
+                    } while (u[q].y != tag);
+                  }
+                  vq = __uint_as_float(u[q].x);
+                }
+                all += vq;
+              }
+            }
+            tot = all;
+          }
+          const float gs = tot / Bf;
           w_s[ctid] = fmaf(a, gs, w_s[ctid]);
           if (cta == 0 && s == p.nb - 1) p.g_last[ctid] = gs;
         }
@@ -374,6 +449,7 @@ __global__ void __launch_bounds__(32 * (kClNW + kClNP), 1) sgd_cluster_epoch_ker
       mark(6);  // weights updated
       consumer_bar<kClCT>();  // w_s complete
       mark(7);
+      n = n_next;
     }
 
     // running loss of the launch: per-CTA sums of |r| and r^2

@@ -131,7 +131,7 @@ class SGDEngine:
         self.num_batches = out.reserved[0]
         self.grid, self.reduce, self.engine = out.grid, out.reduce, out.engine
         self.nslots, self.smem_bytes = out.reserved[1], out.reserved[2]
-        self.kernel_shape = (out.reserved[3], out.reserved[4], out.reserved[5])  # KC, U, NW; KC = 0: small-step kernels
+        self.kernel_shape = (out.reserved[3], out.reserved[4], out.reserved[5])  # KC, U, NW; KC = 0: cluster kernel (U = cluster size)
         self.cluster_size = out.reserved[4] if out.reserved[3] == 0 else 0             # CTAs of the one cluster, or 0
         self.ld = out.reserved[6]
         self.rank, self.nranks = rank, nranks
@@ -277,8 +277,6 @@ class SGDEngine:
         kc, u, nw = self.kernel_shape
         if kc == 0 and u > 0:
             return "sgd_cluster_epoch_kernel (one %d-CTA cluster, %d consumer warps)" % (u, nw)
-        if kc == 0:
-            return "sgd_small_epoch_kernel"
         return "sgd_epoch_kernel<KC=%d,U=%d,NW=%d%s%s>" % (abs(kc), abs(u), nw, ",WIDE" if kc < 0 else "", ",NARROW8" if u < 0 else "")
 
     def debug_phase_cycles(self) -> np.ndarray:

@@ -83,6 +83,11 @@ def test_two_ranks_match_single_rank_oracle(tmp_path, R, C, B):
     _run(2, R, C, B, 0.05, 2, tmp_path)
 
 
+def test_two_ranks_generic_kernel_direct_push(tmp_path, monkeypatch):
+    monkeypatch.setenv("B200SGD_CLUSTER", "0")   # narrow rows on sgd_epoch_kernel: partials pushed to the peers' owners
+    _run(2, 40000, 100, 1000, 0.05, 2, tmp_path)
+
+
 def test_four_ranks(tmp_path):
     _run(4, 60000, 100, 2000, 0.05, 2, tmp_path)
 

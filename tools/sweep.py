@@ -58,7 +58,7 @@ def run(R, C, B, lr=0.01, epochs=3, warm=1, shuffle=True, **kw):
                "frac_of_peak": round(best["bytes"] / (best["steploop_ms"] * 1e-3) * 1e-9 / PEAK, 4),
                "msamples_per_s": round(best["samples"] / (best["steploop_ms"] * 1e-3) * 1e-6, 1),
                "finite": bool(np.all(np.isfinite(w)))}
-        if phases and out["kernel"][0] == 0 and out["kernel"][1] > 0:   # cluster kernel: SM clock at the marks of one step
+        if phases and out["kernel"][0] == 0:   # cluster kernel: SM clock at the marks of one step
             col = eng.debug_phase_cycles().astype(np.int64)
             prev = eng.debug_step_timeline().astype(np.int64)[:, 0:1]
             cn = ["step_top", "phaseA", "barA", "phaseB+sent", "next_rows_loaded", "all_arrived", "updated", "end_bar"]
