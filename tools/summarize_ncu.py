@@ -45,7 +45,7 @@ KEYS = [
 ]
 
 
-def full(src, dst, title, alg_bytes=None):
+def full(src, dst, title, alg_bytes=None, kregex="sgd_epoch_kernel"):
     raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, vals = rows[0], rows[1], rows[2]
@@ -61,7 +61,7 @@ def full(src, dst, title, alg_bytes=None):
     ublk = sum(int(r[ix["Instructions Executed"]] or 0) for r in data if "UBLKCP" in r[ix["Source"]])
     utma = sum(int(r[ix["Instructions Executed"]] or 0) for r in data if "UTMALDG" in r[ix["Source"]])
     with open(dst, "w") as f:
-        f.write(f"# {title}\n\n`ncu --set full --clock-control none --import-source on -k regex:sgd_epoch_kernel -s 1 -c 1` "
+        f.write(f"# {title}\n\n`ncu --set full --clock-control none --import-source on -k regex:{kregex} -s 1 -c 1` "
                 f"on one B200 (`{src.split('/')[-1]}`, not committed: binary). One launch = one epoch.\n\n")
         f.write("| metric | value |\n|---|---|\n")
         f.write(f"| kernel | `{d['Kernel Name'][0] if 'Kernel Name' in d else 'sgd_epoch_kernel'}` |\n")
@@ -91,5 +91,6 @@ if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(sys.argv[2], sys.argv[3])
     else:
-        t = full(sys.argv[2], sys.argv[3], sys.argv[4], sys.argv[5] if len(sys.argv) > 5 else None)
+        t = full(sys.argv[2], sys.argv[3], sys.argv[4], sys.argv[5] if len(sys.argv) > 5 else None,
+                 sys.argv[6] if len(sys.argv) > 6 else "sgd_epoch_kernel")
         print(int(t))
