@@ -42,10 +42,11 @@ constexpr uint32_t kClOffEmpty = 128;   // uint64 empty[16]
 constexpr uint32_t kClOffRecvBar = 256; // uint64 recv[2]
 constexpr uint32_t kClOffW = 512;       // float w_s[128]
 constexpr uint32_t kClOffR = 1024;      // float r_s[2][kClMaxChunk][32]
-constexpr uint32_t kClOffSend = 2048;   // float send[2][128]
-constexpr uint32_t kClOffRecv = 3072;   // float recv[2][kClMaxCS][128]
-constexpr uint32_t kClOffRing = kClOffRecv + 2 * kClMaxCS * 128 * 4;  // 19456, 128-byte aligned
-constexpr size_t kClFixedSmem = kClOffRing;
+constexpr int kClSlot = 144;            // floats per source slot: 128 columns + 16, so that consecutive sources sit 16 banks apart
+constexpr uint32_t kClOffRecv = 2048;   // float recv[2][kClMaxCS][kClSlot]
+constexpr uint32_t kClOffRing = kClOffRecv + 2 * kClMaxCS * kClSlot * 4;  // 20480, 128-byte aligned
+constexpr uint32_t kClRingSlack = 512;  // the last row's unpredicated 128-float read may run past the ring
+constexpr size_t kClFixedSmem = kClOffRing + kClRingSlack;
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -89,10 +90,11 @@ __device__ __forceinline__ void mbar_wait_guarded(uint32_t bar, uint32_t parity,
     if (guard.expired(err, 4u)) break;
   }
 }
-// remote 4-byte store into another CTA's shared memory; completes 4 bytes on THAT CTA's mbarrier
-__device__ __forceinline__ void st_async_f32(uint32_t dst_cluster, float v, uint32_t bar_cluster) {
-  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(dst_cluster),
-               "r"(__float_as_uint(v)), "r"(bar_cluster)
+// remote 16-byte store into another CTA's shared memory; completes 16 bytes on THAT CTA's mbarrier
+__device__ __forceinline__ void st_async_f4(uint32_t dst_cluster, float4 v, uint32_t bar_cluster) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1,%2,%3,%4}, [%5];" ::"r"(dst_cluster),
+               "r"(__float_as_uint(v.x)), "r"(__float_as_uint(v.y)), "r"(__float_as_uint(v.z)), "r"(__float_as_uint(v.w)),
+               "r"(bar_cluster)
                : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async_smem() {
@@ -114,7 +116,6 @@ __global__ void __launch_bounds__(32 * (kClNW + kClNP), 1) sgd_cluster_epoch_ker
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* w_s = reinterpret_cast<float*>(smem_raw + kClOffW);
   float* r_s = reinterpret_cast<float*>(smem_raw + kClOffR);
-  float* send_s = reinterpret_cast<float*>(smem_raw + kClOffSend);
   const float* recv_s = reinterpret_cast<const float*>(smem_raw + kClOffRecv);
   unsigned char* ring = smem_raw + kClOffRing;
 
@@ -142,7 +143,7 @@ __global__ void __launch_bounds__(32 * (kClNW + kClNP), 1) sgd_cluster_epoch_ker
   for (int c = tid; c < 128; c += blockDim.x) w_s[c] = (c < p.C) ? p.w[c] : 0.0f;
   // phase B reads whole tiles (rows beyond a short slice are multiplied by a zero residual): the
   // ring must never hold bit patterns of NaN or Inf
-  for (uint32_t i = tid; i < (uint32_t)p.ntiles * tile_bytes / 16u; i += blockDim.x)
+  for (uint32_t i = tid; i < ((uint32_t)p.ntiles * tile_bytes + kClRingSlack) / 16u; i += blockDim.x)
     reinterpret_cast<float4*>(ring)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   fence_proxy_async_smem();  // the TMA writes that follow go through the async proxy
   __syncthreads();
@@ -232,7 +233,6 @@ __global__ void __launch_bounds__(32 * (kClNW + kClNP), 1) sgd_cluster_epoch_ker
     const float Bf = (float)p.B, a = p.a;
     const uint32_t expect = (uint32_t)CS * (((uint32_t)C * 4u + 15u) & ~15u);  // bytes every CTA receives per step
     const bool armer = ctid == kClCT - 1;  // arms the receive barriers (kept off warp 0's path)
-    const uint32_t msg_bytes = ((uint32_t)C * 4u + 15u) & ~15u;  // the CTA's column sums, whole 16-byte units
     const int rowA = cw * 4 + rg;             // my row of every tile in phase A
     const int rslot = (rowA & 1) * 16 + (rowA >> 1);  // residuals are stored even rows first, then odd rows
     int n;                                    // my rows of the current step
@@ -242,7 +242,8 @@ __global__ void __launch_bounds__(32 * (kClNW + kClNP), 1) sgd_cluster_epoch_ker
     }
     const int cpad = 4 * ((p.C4 + 3) & ~3);   // MULTI: columns per rank in the inbox
 
-    double loss_abs = 0.0, loss_sq = 0.0;  // running training loss (lane sl == 0 of every row group)
+    // running training loss: fp32 per lane (a lane sees <= 2 * nb * tiles residuals per launch), double from there on
+    float loss_abs = 0.f, loss_sq = 0.f;
     uint32_t tq = 0, chunk_seq = 0;
     int cur_s = 0;
     auto mark = [&](int i) {
@@ -257,6 +258,7 @@ __global__ void __launch_bounds__(32 * (kClNW + kClNP), 1) sgd_cluster_epoch_ker
     const unsigned char* tb[CHUNK];
     float4 x[CHUNK][4];
     float y[CHUNK];
+    bool live[CHUNK];
     auto load_block = [&](int t0, int nch, int n) {
 #pragma unroll
       for (int u = 0; u < CHUNK; ++u) {
@@ -267,12 +269,13 @@ __global__ void __launch_bounds__(32 * (kClNW + kClNP), 1) sgd_cluster_epoch_ker
       }
 #pragma unroll
       for (int u = 0; u < CHUNK; ++u) {
-        const bool live = u < nch && rowA < n - (t0 + u) * kClTileRows;
+        // no predicates on the loads: the ring (plus the slack after it) only ever holds finite values,
+        // columns beyond C meet zero weights, and rows beyond the slice get their residual forced to 0
+        live[u] = u < nch && rowA < n - (t0 + u) * kClTileRows;
         const float4* row = reinterpret_cast<const float4*>(tb[u] + (size_t)rowA * p.slot_bytes);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          x[u][k] = (live && sl + 8 * k < ld4) ? row[sl + 8 * k] : make_float4(0.f, 0.f, 0.f, 0.f);
-        y[u] = live ? reinterpret_cast<const float*>(row)[C] : 0.f;  // the label rides in the record
+        for (int k = 0; k < 4; ++k) x[u][k] = row[sl + 8 * k];
+        y[u] = reinterpret_cast<const float*>(row)[C];  // the label rides in the record
       }
     };
     if (p.nb > 0) load_block(0, min(CHUNK, (n + kClTileRows - 1) / kClTileRows), n);
@@ -323,12 +326,10 @@ __global__ void __launch_bounds__(32 * (kClNW + kClNP), 1) sgd_cluster_epoch_ker
         }
 #pragma unroll
         for (int u = 0; u < CHUNK; ++u) {
-          const float res = dot[u] - y[u];  // rows beyond the step's slice: 0
-          if (sl == 0) {
-            rr[u * 32 + rslot] = res;
-            loss_abs += (double)fabsf(res);
-            loss_sq += (double)res * (double)res;
-          }
+          const float res = live[u] ? dot[u] - y[u] : 0.f;  // rows beyond the step's slice: 0
+          if (sl == 0) rr[u * 32 + rslot] = res;
+          loss_abs += fabsf(res);  // every lane of the row group carries the same residual
+          loss_sq = fmaf(res, res, loss_sq);
         }
         mark(1);  // phase A done
         consumer_bar<kClCT>();
@@ -362,21 +363,28 @@ __global__ void __launch_bounds__(32 * (kClNW + kClNP), 1) sgd_cluster_epoch_ker
         tq += (uint32_t)nch;
       }
 
-      // ---- exchange: fold the two row parities (one shuffle), stage the CTA's C column sums in shared
-      // memory, and send them with ONE bulk copy per destination CTA into slot [par][cta] there,
-      // completing the bytes on the destination's barrier; warp w serves CTAs 2w and 2w+1.  (Issuing
-      // a bulk copy costs a warp ~60 cycles: 16 destinations per warp were 1000 cycles per step.)
+      // ---- exchange: fold the two row parities (one shuffle); the warp's 16 column sums then go to
+      // slot [par][cta][16*cw ..] of EVERY CTA straight from registers: lane l carries the four columns
+      // 4*(l & 3) .. +3 to CTA (l >> 2) (+ 8 in the second pass), so ONE st.async.v4 serves 8 destination
+      // CTAs, each store completing its 16 bytes on its destination's barrier.  No staging, no proxy
+      // fence, no CTA barrier.  (Issuing costs a warp ~60 cycles per remote-store instruction or bulk
+      // copy whatever its size: 16 of them per warp were 1000 cycles per step.)
       {
         float v = (acc[0] + acc[1]) + (acc[2] + acc[3]);
         v += __shfl_xor_sync(0xffffffffu, v, 16);
-        float* mine = send_s + par * 128;
-        if (lane < 16) mine[16 * cw + lane] = v;
-        fence_proxy_async_smem();  // the bulk copy reads shared memory through the async proxy
-        consumer_bar<kClCT>();
-        const int dst = 2 * cw + lane;
-        if (lane < 2 && dst < CS) {
-          const uint32_t slot = smem0 + kClOffRecv + (uint32_t)((par * kClMaxCS + cta) * 128 * 4);
-          bulk_s2cluster(map_to_cta(slot, (uint32_t)dst), smem_u32(mine), msg_bytes, map_to_cta(rbar, (uint32_t)dst));
+        const int q4 = 4 * (lane & 3);
+        float4 f;
+        f.x = __shfl_sync(0xffffffffu, v, q4 + 0);
+        f.y = __shfl_sync(0xffffffffu, v, q4 + 1);
+        f.z = __shfl_sync(0xffffffffu, v, q4 + 2);
+        f.w = __shfl_sync(0xffffffffu, v, q4 + 3);
+        if (16 * cw + q4 < C) {  // whole 16-byte units up to C (the sum of these is `expect`)
+          const uint32_t slot = smem0 + kClOffRecv + (uint32_t)(((par * kClMaxCS + cta) * kClSlot + 16 * cw + q4) * 4);
+#pragma unroll
+          for (int pass = 0; pass < kClMaxCS / 8; ++pass) {
+            const uint32_t dst = (uint32_t)(8 * pass + (lane >> 2));
+            if ((int)dst < CS) st_async_f4(map_to_cta(slot, dst), f, map_to_cta(rbar, dst));
+          }
         }
         mark(3);  // sent
       }
@@ -385,38 +393,38 @@ __global__ void __launch_bounds__(32 * (kClNW + kClNP), 1) sgd_cluster_epoch_ker
       mark(4);
       // ---- every CTA adds the CS partials of a column in the same order and applies
       //      w = a * (g / B) + w   (sgd_thrust.cu:269, main.cu:147-150 / :287-290)
-      if (ctid < 128) {
+      // (warp cw owns columns 16*cw ..: its half warps add one half of the sources each, one shuffle folds)
+      {
         mbar_wait_guarded(rbar, (uint32_t)(s >> 1) & 1u, p.err);
         mark(5);  // all partials arrived
-        if (ctid < C) {
-          const float* rb = recv_s + (size_t)par * kClMaxCS * 128 + ctid;
-          float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+        const int c = 16 * cw + (lane & 15);
+        // half warp hp adds the sources hp, hp + 2, ... (16 banks apart from the other half's)
+        const float* rb = recv_s + ((size_t)par * kClMaxCS + (size_t)hp) * kClSlot + c;
+        float t0 = 0.f, t1 = 0.f;
 #pragma unroll
-          for (int i = 0; i < 8; i += 4) {
-            t0 += rb[(i + 0) * 128];
-            t1 += rb[(i + 1) * 128];
-            t2 += rb[(i + 2) * 128];
-            t3 += rb[(i + 3) * 128];
-          }
-          if (CS > 8) {
+        for (int i = 0; i < 4; i += 2) {
+          t0 += rb[(2 * i + 0) * kClSlot];
+          t1 += rb[(2 * i + 2) * kClSlot];
+        }
+        if (CS > 8) {
 #pragma unroll
-            for (int i = 8; i < 16; i += 4) {
-              t0 += rb[(i + 0) * 128];
-              t1 += rb[(i + 1) * 128];
-              t2 += rb[(i + 2) * 128];
-              t3 += rb[(i + 3) * 128];
-            }
+          for (int i = 4; i < 8; i += 2) {
+            t0 += rb[(2 * i + 0) * kClSlot];
+            t1 += rb[(2 * i + 2) * kClSlot];
           }
-          float tot = (t0 + t1) + (t2 + t3);  // this GPU's rows
+        }
+        float tot = t0 + t1;
+        tot += __shfl_xor_sync(0xffffffffu, tot, 16);  // this GPU's rows
+        if (lane < 16 && c < C) {
           if (MULTI) {
             // second hop, over NVLink: CTA 0 gives the rank's sum to every peer; everybody polls the
             // own rank's inbox and adds the ranks' sums in rank order
             const uint32_t tag = p.tag_base + (uint32_t)s + 1u;
-            const int64_t at = ((int64_t)par * p.nranks + p.rank) * cpad + ctid;
+            const int64_t at = ((int64_t)par * p.nranks + p.rank) * cpad + c;
             if (cta == 0)
               for (int q = 0; q < p.nranks; ++q)
                 if (q != p.rank) ll_store_f1(reinterpret_cast<uint2*>(p.ll_inbox_peer[q]) + at, tot, tag);
-            const uint2* inbox = reinterpret_cast<const uint2*>(p.ll_inbox_local) + (int64_t)par * p.nranks * cpad + ctid;
+            const uint2* inbox = reinterpret_cast<const uint2*>(p.ll_inbox_local) + (int64_t)par * p.nranks * cpad + c;
             uint2 u[8];
 #pragma unroll
             for (int q = 0; q < 8; ++q)
@@ -442,8 +450,8 @@ __global__ void __launch_bounds__(32 * (kClNW + kClNP), 1) sgd_cluster_epoch_ker
             tot = all;
           }
           const float gs = tot / Bf;
-          w_s[ctid] = fmaf(a, gs, w_s[ctid]);
-          if (cta == 0 && s == p.nb - 1) p.g_last[ctid] = gs;
+          w_s[c] = fmaf(a, gs, w_s[c]);
+          if (cta == 0 && s == p.nb - 1) p.g_last[c] = gs;
         }
       }
       mark(6);  // weights updated
@@ -452,16 +460,17 @@ __global__ void __launch_bounds__(32 * (kClNW + kClNP), 1) sgd_cluster_epoch_ker
       n = n_next;
     }
 
-    // running loss of the launch: per-CTA sums of |r| and r^2
-    loss_abs += __shfl_xor_sync(0xffffffffu, loss_abs, 8);
-    loss_abs += __shfl_xor_sync(0xffffffffu, loss_abs, 16);
-    loss_sq += __shfl_xor_sync(0xffffffffu, loss_sq, 8);
-    loss_sq += __shfl_xor_sync(0xffffffffu, loss_sq, 16);
+    // running loss of the launch: per-CTA sums of |r| and r^2 (lanes 0, 8, 16, 24 hold the four row groups)
+    double la = (double)loss_abs, lq = (double)loss_sq;
+    la += __shfl_xor_sync(0xffffffffu, la, 8);
+    la += __shfl_xor_sync(0xffffffffu, la, 16);
+    lq += __shfl_xor_sync(0xffffffffu, lq, 8);
+    lq += __shfl_xor_sync(0xffffffffu, lq, 16);
     if (p.loss != nullptr) {
       double* ls = reinterpret_cast<double*>(r_s);  // free after the last end-of-step barrier
       if (lane == 0) {
-        ls[2 * cw] = loss_abs;
-        ls[2 * cw + 1] = loss_sq;
+        ls[2 * cw] = la;
+        ls[2 * cw + 1] = lq;
       }
       consumer_bar<kClCT>();
       if (ctid == 0) {
