@@ -361,7 +361,7 @@ def main() -> int:
                                    "one bench step = one SGD epoch incl. its bit-exact permutation",
                        "l2": "inputs larger than L2 (per-GPU data %.1f GB vs 126 MB)" % (4 * rows_pg * (cols + 1) / 1e9),
                        "engine": args.engine, "grid": eng.grid,
-                       "reduce": "cluster all-gather in shared memory" if eng.cluster_size else
+                       "reduce": ("cluster all-gather in shared memory" + (" + L2 hop between clusters" if eng.grid > eng.cluster_size else "")) if eng.cluster_size else
                                  {1: "allgather", 2: "scatter", 3: "dataflow-2hop", 4: "dataflow-1hop"}[eng.reduce],
                        "kernel": eng.kernel_name,
                        "ring_slots": eng.nslots, "smem_bytes": eng.smem_bytes,

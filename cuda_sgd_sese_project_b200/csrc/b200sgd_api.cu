@@ -192,8 +192,10 @@ struct sgd_ctx {
   bool use_gather4 = false;  // narrow rows: TMA tile::gather4, four rows per instruction
   bool have_rec_map = false;  // the tensor map of the records exists
   // sgd_cluster_epoch_kernel (small steps of narrow rows): the grid is one cluster of cluster_cs CTAs
-  int cluster_cs = 0, cluster_ntiles = 0, cluster_tile_log2 = 0;
+  int cluster_cs = 0, cluster_ng = 1, cluster_ntiles = 0, cluster_tile_log2 = 0;  // CTAs per cluster, clusters
   const void* cluster_fn = nullptr;
+  bool cluster_coop = true;        // pass the cooperative attribute with several clusters (dropped if refused)
+  uint2* d_cl_inbox = nullptr;     // one GPU, several clusters: tagged cluster sums [2][clusters][4*C4p]
   size_t cluster_smem = 0;
   int nprod = 1;  // producer warps
   int tile_rows = 0;
@@ -245,7 +247,7 @@ void free_all(sgd_ctx* c) {
   cudaFree(c->d_tilesum); cudaFree(c->d_states);
   if (c->h_states[0]) cudaFreeHost(c->h_states[0]);
   if (c->h_states[1]) cudaFreeHost(c->h_states[1]);
-  cudaFree(c->d_mae); cudaFree(c->d_xchg_block);
+  cudaFree(c->d_mae); cudaFree(c->d_xchg_block); cudaFree(c->d_cl_inbox);
   if (c->h_stage[0]) cudaFreeHost(c->h_stage[0]);
   if (c->h_stage[1]) cudaFreeHost(c->h_stage[1]);
   cudaEvent_t evs[] = {c->ev0, c->ev1, c->ev_perm[0], c->ev_perm[1], c->ev_done[0], c->ev_done[1], c->ev_done[2]};
@@ -287,15 +289,33 @@ int configure_launch(sgd_ctx* c) {
   // through distributed shared memory (sgd_cluster_kernel.cuh); multi-GPU adds one NVLink hop.  B200SGD_CLUSTER=0
   // switches it off, 8 / 16 pick the cluster size (A/B runs).
   c->cluster_cs = 0;
+  c->cluster_ng = 1;
   {
     const char* e = std::getenv("B200SGD_CLUSTER");
     const int want = e ? std::atoi(e) : b200sgd::kClMaxCS;
+    const char* em = std::getenv("B200SGD_CLUSTER_MAX_ROWS");  // largest step (rows per rank) the cluster kernel takes
+    // measured at C = 100 (us per step, cluster / generic kernel): 4096 rows 2.95 / 3.87, 8192 4.05 / 4.4,
+    // 10000 4.42 / 4.6, 30000 7.4 / 6.2, 100000 15.7 / 12.7: beyond ~10k rows the per-warp streaming of
+    // the generic kernel wins over the per-tile CTA barrier of this one
+    const int64_t max_rows = em ? std::atoll(em) : 10240;
     if ((want == 8 || want == 16) && c->ld <= 128 && c->cfg.engine != SGD_ENGINE_GRAPH &&
         (c->cfg.reduce == SGD_REDUCE_AUTO || c->cfg.reduce == SGD_REDUCE_DATAFLOW) &&
-        !(c->cfg.flags & SGD_FLAG_RESIDUALS) && rows_step >= 48 && rows_step <= 2048 &&
-        (c->cfg.grid <= 0 || c->cfg.grid == want)) {
-      c->cluster_cs = want;
-      grid = want;
+        !(c->cfg.flags & SGD_FLAG_RESIDUALS) && rows_step >= 48 && rows_step <= max_rows) {
+      // clusters: the L2 hop between clusters costs ~1.2 us per step, a ring tile of 32 rows ~0.3 us, so one
+      // cluster serves steps of up to 4095 rows; beyond, enough clusters for <= 64 rows per CTA and
+      // step, as far as they fit on the GPU at once (configure_cluster: 7 clusters of 16 CTAs on a
+      // B200).  Several GPUs: one cluster per GPU.
+      int ng = 1;
+      if (c->cfg.nranks == 1 && rows_step >= 4096)
+        ng = (int)std::min<int64_t>(c->num_sms / want, (rows_step + 64 * want - 1) / (64 * want));
+      if (const char* en = std::getenv("B200SGD_CLUSTERS")) ng = std::max(1, std::atoi(en));
+      if (c->cfg.grid > 0 && c->cfg.grid % want == 0) ng = c->cfg.grid / want;  // explicit grid: that many clusters
+      if (c->cfg.nranks > 1) ng = 1;
+      if ((c->cfg.grid <= 0 || c->cfg.grid == ng * want) && ng * want <= c->num_sms) {
+        c->cluster_cs = want;
+        c->cluster_ng = ng;
+        grid = ng * want;
+      }
     }
   }
   grid = std::max(1, std::min(grid, c->num_sms));
@@ -352,6 +372,11 @@ int configure_launch(sgd_ctx* c) {
 
 // Ring geometry, attributes and schedulability of the cluster kernel; falls back to the generic
 // kernel (cluster_cs = 0) when the tensor map or a free GPC for the cluster is missing.
+int configure_cluster(sgd_ctx* c);
+int configure_cluster_retry(sgd_ctx* c, int cs) {  // with a smaller number of clusters
+  c->cluster_cs = cs;
+  return configure_cluster(c);
+}
 int configure_cluster(sgd_ctx* c) {
   if (c->cluster_cs == 0) return SGD_OK;
   const int cs = c->cluster_cs;
@@ -368,9 +393,10 @@ int configure_cluster(sgd_ctx* c) {
   c->cluster_smem = b200sgd::kClFixedSmem + (size_t)ntiles * tile_bytes;
   // tiles of one CTA per step -> phase-A block size
   const bool prof = c->d_dbg != nullptr;
-  const bool multi = c->cfg.nranks > 1;
+  const bool multi = c->cfg.nranks > 1 || c->cluster_ng > 1;
   const int64_t rows_rank = std::max<int64_t>(1, (int64_t)c->B / c->cfg.nranks);
-  const int tiles = (int)(((rows_rank + cs - 1) / cs + b200sgd::kClTileRows - 1) / b200sgd::kClTileRows);
+  const int64_t ctas = (int64_t)cs * c->cluster_ng;
+  const int tiles = (int)(((rows_rank + ctas - 1) / ctas + b200sgd::kClTileRows - 1) / b200sgd::kClTileRows);
   const void* fn = nullptr;
   using namespace b200sgd;
   if (multi) {
@@ -388,7 +414,7 @@ int configure_cluster(sgd_ctx* c) {
   CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->cluster_smem));
   if (cs > 8) CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   cudaLaunchConfig_t lc = {};
-  lc.gridDim = dim3(cs);
+  lc.gridDim = dim3(cs * c->cluster_ng);
   lc.blockDim = dim3(32 * (b200sgd::kClNW + b200sgd::kClNP));
   lc.dynamicSmemBytes = c->cluster_smem;
   cudaLaunchAttribute at[1];
@@ -399,9 +425,23 @@ int configure_cluster(sgd_ctx* c) {
   lc.attrs = at;
   lc.numAttrs = 1;
   int nclusters = 0;
+  // every cluster of the launch must be resident at once: they wait for one another's sums
   if (cudaOccupancyMaxActiveClusters(&nclusters, fn, &lc) != cudaSuccess || nclusters < 1) {
     cudaGetLastError();
     return SGD_OK;
+  }
+  if (std::getenv("B200SGD_DEBUG"))
+    std::fprintf(stderr, "[b200sgd] cluster size %d: at most %d clusters resident, %d wanted\n", cs, nclusters, c->cluster_ng);
+  if (nclusters < c->cluster_ng) {
+    if (c->cfg.grid > 0) return SGD_OK;  // an explicit grid that does not fit: generic kernel
+    c->cluster_ng = nclusters;
+    c->grid = cs * c->cluster_ng;
+    return configure_cluster_retry(c, cs);
+  }
+  if (c->cluster_ng > 1 && c->cfg.nranks == 1) {
+    const size_t words = 2 * (size_t)c->cluster_ng * 4 * (((size_t)c->C4 + 3) & ~(size_t)3);
+    CUDA_TRY(cudaMalloc(&c->d_cl_inbox, sizeof(uint2) * words));
+    CUDA_TRY(cudaMemset(c->d_cl_inbox, 0, sizeof(uint2) * words));
   }
   c->cluster_cs = cs;
   return SGD_OK;
@@ -569,22 +609,35 @@ int launch_epoch(sgd_ctx* c, int32_t epoch, int buf, int* launches) {
   CUDA_TRY(cudaMemsetAsync(c->d_bar, 0, sizeof(unsigned int), c->stream));
   c->step_tag += (uint32_t)c->nb;  // every rank advances identically: tags agree across GPUs
   void* args[] = {&p};
-  if (c->cluster_cs > 0) {  // small steps of narrow rows: one cluster, gradient exchange in shared memory
+  if (c->cluster_cs > 0) {  // narrow rows, small and mid-size steps: clusters, gradient exchange in shared memory
     p.ntiles = c->cluster_ntiles;
     p.tile_log2 = c->cluster_tile_log2;
+    if (c->cfg.nranks == 1 && c->cluster_ng > 1) {  // the clusters of this GPU meet in a local inbox
+      p.ll_inbox_local = (uint4*)c->d_cl_inbox;
+      p.ll_inbox_peer[0] = (uint4*)c->d_cl_inbox;
+    }
     cudaLaunchConfig_t lc = {};
-    lc.gridDim = dim3(c->cluster_cs);
+    lc.gridDim = dim3(c->cluster_cs * c->cluster_ng);
     lc.blockDim = dim3(32 * (b200sgd::kClNW + b200sgd::kClNP));
     lc.dynamicSmemBytes = c->cluster_smem;
     lc.stream = c->stream;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = c->cluster_cs;
     at[0].val.clusterDim.y = 1;
     at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeCooperative;  // several clusters wait for one another: co-residency
+    at[1].val.cooperative = 1;
     lc.attrs = at;
-    lc.numAttrs = 1;
-    CUDA_TRY(cudaLaunchKernelExC(&lc, c->cluster_fn, args));
+    lc.numAttrs = (c->cluster_ng > 1 && c->cluster_coop) ? 2 : 1;
+    cudaError_t e = cudaLaunchKernelExC(&lc, c->cluster_fn, args);
+    if (e != cudaSuccess && lc.numAttrs == 2) {  // cooperative + cluster refused: the occupancy check stands in
+      cudaGetLastError();
+      c->cluster_coop = false;
+      lc.numAttrs = 1;
+      e = cudaLaunchKernelExC(&lc, c->cluster_fn, args);
+    }
+    CUDA_TRY(e);
     *launches += 1;
     return SGD_OK;
   }

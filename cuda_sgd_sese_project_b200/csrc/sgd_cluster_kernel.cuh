@@ -106,10 +106,13 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
 //   CHUNK = ring tiles per phase-A block (1, 2 or 4: the host takes the tiles of a step, capped at 4)
 //   PROF  = (B200SGD_PHASE_PROFILE=1) lane 0 of consumer warp 0 stores the SM clock at the marks of the
 //           middle step into p.dbg[cta][0..7], the clock at the end of the step before into p.dbg[grid+cta][0]
-//   MULTI = nranks > 1: the rank's rows of a step come from the bucketed row list (step_off); after the
-//           cluster exchange CTA 0 stores the rank's column sums as tagged words into the inbox of every
-//           peer over NVLink, every CTA polls its own rank's inbox for the peers' sums and adds the ranks'
-//           sums in rank order (identical bits on every GPU).  Inbox: ll_inbox as uint2 [2][nranks][4*C4p].
+//   MULTI = more than one cluster takes part in a step: several clusters on this GPU (gridDim.x = NG * CS,
+//           mid-size batches) and / or several GPUs (nranks > 1, one cluster each, rows of a step from the
+//           bucketed row list step_off).  "Group" q = rank * NG + cluster.  After the cluster exchange the
+//           first CTA of a cluster stores the cluster's column sums as tagged 8-byte words into slot
+//           [parity][q] of the inbox of every rank (own rank: L2; peers: NVLink), every CTA polls its own
+//           rank's inbox for the other groups and adds the groups' sums in group order (identical bits
+//           in every CTA of every GPU).  Inbox: ll_inbox as uint2 [2][nranks * NG][4*C4p].
 template <int CHUNK, bool PROF = false, bool MULTI = false>
 __global__ void __launch_bounds__(32 * (kClNW + kClNP), 1) sgd_cluster_epoch_kernel(const __grid_constant__ EpochParams p) {
   static_assert(CHUNK >= 1 && CHUNK <= kClMaxChunk, "r_s holds kClMaxChunk tiles of residuals");
@@ -121,6 +124,8 @@ __global__ void __launch_bounds__(32 * (kClNW + kClNP), 1) sgd_cluster_epoch_ker
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cta = (int)cluster_ctarank(), CS = (int)cluster_nctarank();
+  const int gcta = (int)blockIdx.x, G = (int)gridDim.x;  // CTA within the rank; the rank's rows are cut over all G CTAs
+  const int NG = G / CS, grp = gcta / CS;                // clusters of this rank, mine
   const uint32_t smem0 = smem_u32(smem_raw);
   const uint32_t full0 = smem0 + kClOffFull, empty0 = smem0 + kClOffEmpty, recvbar0 = smem0 + kClOffRecvBar;
   const uint32_t ring0 = smem0 + kClOffRing;
@@ -153,13 +158,13 @@ __global__ void __launch_bounds__(32 * (kClNW + kClNP), 1) sgd_cluster_epoch_ker
   auto step_rows = [&](int s, int64_t* off, int* n) {
     const int64_t sa = (int64_t)p.first_step + s;
     int64_t rows = p.B, o = sa * p.B;
-    if (MULTI) {
+    if (MULTI && p.step_off != nullptr) {
       o = p.step_off[sa];
       rows = p.step_off[sa + 1] - o;
     }
-    const int64_t lo = slice_lo(rows, cta, CS);
+    const int64_t lo = slice_lo(rows, gcta, G);
     *off = o + lo;
-    *n = (int)(slice_lo(rows, cta + 1, CS) - lo);
+    *n = (int)(slice_lo(rows, gcta + 1, G) - lo);
   };
 
   if (warp < kClNP) {
@@ -240,7 +245,7 @@ __global__ void __launch_bounds__(32 * (kClNW + kClNP), 1) sgd_cluster_epoch_ker
       int64_t off_unused;
       if (p.nb > 0) step_rows(0, &off_unused, &n); else n = 0;
     }
-    const int cpad = 4 * ((p.C4 + 3) & ~3);   // MULTI: columns per rank in the inbox
+    const int cpad = 4 * ((p.C4 + 3) & ~3);   // MULTI: columns per group in the inbox
 
     // running training loss: fp32 per lane (a lane sees <= 2 * nb * tiles residuals per launch), double from there on
     float loss_abs = 0.f, loss_sq = 0.f;
@@ -249,8 +254,8 @@ __global__ void __launch_bounds__(32 * (kClNW + kClNP), 1) sgd_cluster_epoch_ker
     auto mark = [&](int i) {
       if (PROF && ctid == 0 && p.dbg != nullptr) {
         const long long t = clock64();
-        if (cur_s == p.nb / 2) p.dbg[(int64_t)cta * 8 + i] = (unsigned long long)t;
-        if (cur_s == p.nb / 2 - 1 && i == 7) p.dbg[((int64_t)CS + cta) * 8] = (unsigned long long)t;
+        if (cur_s == p.nb / 2) p.dbg[(int64_t)gcta * 8 + i] = (unsigned long long)t;
+        if (cur_s == p.nb / 2 - 1 && i == 7) p.dbg[((int64_t)G + gcta) * 8] = (unsigned long long)t;
       }
     };
 
@@ -286,7 +291,7 @@ __global__ void __launch_bounds__(32 * (kClNW + kClNP), 1) sgd_cluster_epoch_ker
       const uint32_t rbar = recvbar0 + 8u * par;
       const int nt = (n + kClTileRows - 1) / kClTileRows;
       int n_next = n;  // rows of the next step (MULTI: from the row list, loads in flight during the step)
-      if (MULTI && s + 1 < p.nb) {
+      if (MULTI && p.step_off != nullptr && s + 1 < p.nb) {
         int64_t off_unused;
         step_rows(s + 1, &off_unused, &n_next);
       }
@@ -417,41 +422,45 @@ __global__ void __launch_bounds__(32 * (kClNW + kClNP), 1) sgd_cluster_epoch_ker
         tot += __shfl_xor_sync(0xffffffffu, tot, 16);  // this GPU's rows
         if (lane < 16 && c < C) {
           if (MULTI) {
-            // second hop, over NVLink: CTA 0 gives the rank's sum to every peer; everybody polls the
-            // own rank's inbox and adds the ranks' sums in rank order
+            // second hop through global memory (L2 on this GPU, NVLink to the peers): the cluster's first
+            // CTA publishes the cluster's sum, everybody polls the own rank's inbox for the other
+            // groups and adds the groups' sums in group order
             const uint32_t tag = p.tag_base + (uint32_t)s + 1u;
-            const int64_t at = ((int64_t)par * p.nranks + p.rank) * cpad + c;
+            const int TG = p.nranks * NG, me = p.rank * NG + grp;
+            const int64_t at = ((int64_t)par * TG + me) * cpad + c;
             if (cta == 0)
-              for (int q = 0; q < p.nranks; ++q)
-                if (q != p.rank) ll_store_f1(reinterpret_cast<uint2*>(p.ll_inbox_peer[q]) + at, tot, tag);
-            const uint2* inbox = reinterpret_cast<const uint2*>(p.ll_inbox_local) + (int64_t)par * p.nranks * cpad + c;
-            uint2 u[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-              if (q < p.nranks && q != p.rank) u[q] = ld_volatile_u2(inbox + (int64_t)q * cpad);
+              for (int r = 0; r < p.nranks; ++r)
+                if (NG > 1 || r != p.rank) ll_store_f1(reinterpret_cast<uint2*>(p.ll_inbox_peer[r]) + at, tot, tag);
+            const uint2* inbox = reinterpret_cast<const uint2*>(p.ll_inbox_local) + (int64_t)par * TG * cpad + c;
             float all = 0.f;
+            for (int q0 = 0; q0 < TG; q0 += 8) {  // eight polls in flight
+              uint2 u[8];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              if (q < p.nranks) {
-                float vq = tot;
-                if (q != p.rank) {
-                  if (u[q].y != tag) {
-                    SpinGuard guard;
-                    do {
-                      if (guard.expired(p.err, 3u)) break;
-                      u[q] = ld_volatile_u2(inbox + (int64_t)q * cpad);
-                    } while (u[q].y != tag);
+              for (int k = 0; k < 8; ++k)
+                if (q0 + k < TG && q0 + k != me) u[k] = ld_volatile_u2(inbox + (int64_t)(q0 + k) * cpad);
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                if (q0 + k < TG) {
+                  float vq = tot;
+                  if (q0 + k != me) {
+                    if (u[k].y != tag) {
+                      SpinGuard guard;
+                      do {
+                        if (guard.expired(p.err, 3u)) break;
+                        u[k] = ld_volatile_u2(inbox + (int64_t)(q0 + k) * cpad);
+                      } while (u[k].y != tag);
+                    }
+                    vq = __uint_as_float(u[k].x);
                   }
-                  vq = __uint_as_float(u[q].x);
+                  all += vq;
                 }
-                all += vq;
               }
             }
             tot = all;
           }
           const float gs = tot / Bf;
           w_s[c] = fmaf(a, gs, w_s[c]);
-          if (cta == 0 && s == p.nb - 1) p.g_last[c] = gs;
+          if (gcta == 0 && s == p.nb - 1) p.g_last[c] = gs;
         }
       }
       mark(6);  // weights updated
@@ -479,11 +488,11 @@ __global__ void __launch_bounds__(32 * (kClNW + kClNP), 1) sgd_cluster_epoch_ker
           sa += ls[2 * wq];
           sb += ls[2 * wq + 1];
         }
-        p.loss[2 * cta] += sa;
-        p.loss[2 * cta + 1] += sb;
+        p.loss[2 * gcta] += sa;
+        p.loss[2 * gcta + 1] += sb;
       }
     }
-    if (cta == 0)  // every CTA holds the same bits
+    if (gcta == 0)  // every CTA holds the same bits
       for (int c = ctid; c < C; c += kClCT) p.w[c] = w_s[c];
   }
   cluster_sync_all();  // nobody leaves while a peer may still write into its shared memory

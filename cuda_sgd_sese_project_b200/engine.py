@@ -276,7 +276,8 @@ class SGDEngine:
     def kernel_name(self) -> str:
         kc, u, nw = self.kernel_shape
         if kc == 0 and u > 0:
-            return "sgd_cluster_epoch_kernel (one %d-CTA cluster, %d consumer warps)" % (u, nw)
+            return "sgd_cluster_epoch_kernel (%d cluster%s of %d CTAs, %d consumer warps)" % (
+                self.grid // u, "" if self.grid == u else "s", u, nw)
         return "sgd_epoch_kernel<KC=%d,U=%d,NW=%d%s%s>" % (abs(kc), abs(u), nw, ",WIDE" if kc < 0 else "", ",NARROW8" if u < 0 else "")
 
     def debug_phase_cycles(self) -> np.ndarray:

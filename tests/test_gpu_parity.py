@@ -205,7 +205,27 @@ def test_cluster_kernel_shapes(R, C, B, cluster, monkeypatch):
     monkeypatch.setenv("B200SGD_CLUSTER", str(cluster))
     X, y, _ = make_regression(R, C, seed=R + C + B)
     with pkg.SGDEngine(R, C, B, 0.02) as probe:
-        assert probe.kernel_shape[0] == 0 and probe.kernel_shape[1] == cluster and probe.grid == cluster
+        assert probe.kernel_shape[0] == 0 and probe.cluster_size == cluster and probe.grid % cluster == 0
+    check_run(X, y, B, 0.02, 3)
+
+
+@pytest.mark.parametrize("R,C,B,clusters", [
+    (20000, 100, 4096, 0),      # the launch heuristic picks the number of clusters (4 x 16 CTAs)
+    (20000, 100, 1000, 2),      # forced: two clusters on a small step (some tiles nearly empty)
+    (30000, 64, 10000, 8),      # 8 x 16 CTAs, 78 rows per CTA and step
+    (9000, 7, 3000, 3),         # an odd number of clusters
+    (150000, 100, 50000, 0),    # 390 rows per CTA: many four-tile blocks per step
+])
+def test_cluster_kernel_several_clusters(R, C, B, clusters, monkeypatch):
+    # mid-size batches: every cluster sums its rows in shared memory, the clusters meet in an L2 inbox
+    if clusters:
+        monkeypatch.setenv("B200SGD_CLUSTERS", str(clusters))
+    monkeypatch.setenv("B200SGD_CLUSTER_MAX_ROWS", "100000")   # beyond the default hand-over to sgd_epoch_kernel
+    X, y, _ = make_regression(R, C, seed=R + C + B)
+    with pkg.SGDEngine(R, C, B, 0.02) as probe:
+        assert probe.kernel_shape[0] == 0 and probe.grid > probe.cluster_size
+        if clusters and clusters <= 7:
+            assert probe.grid == clusters * probe.cluster_size
     check_run(X, y, B, 0.02, 3)
 
 
@@ -220,7 +240,7 @@ def test_cluster_kernel_agrees_with_the_generic_kernel(monkeypatch):
 
 
 def test_cluster_kernel_is_not_used_where_it_does_not_apply():
-    for kw in (dict(C=128, B=1000), dict(C=100, B=4096), dict(C=100, B=24)):
+    for kw in (dict(C=128, B=1000), dict(C=100, B=24), dict(C=100, B=16384)):
         with pkg.SGDEngine(20000, kw["C"], kw["B"], 0.1) as eng:
             assert eng.kernel_shape[0] != 0, kw
     with pkg.SGDEngine(20000, 100, 1000, 0.1, keep_residuals=True) as eng:
