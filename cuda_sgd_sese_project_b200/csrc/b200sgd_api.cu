@@ -692,8 +692,17 @@ int enqueue_device_shuffle(sgd_ctx* c, int stage_buf, int src, int dst, int* lau
   return SGD_OK;
 }
 
+// Pinned staging of host-side permutations: only the host shuffle and sgd_set_permutation need it, and
+// page-locking 8 bytes per row costs milliseconds, so it is allocated on first use.
+int ensure_host_stage(sgd_ctx* c) {
+  for (int i = 0; i < 2; ++i)
+    if (!c->h_stage[i]) CUDA_TRY(cudaMallocHost(&c->h_stage[i], sizeof(int32_t) * (size_t)c->R));
+  return SGD_OK;
+}
+
 int sync_host_ind(sgd_ctx* c) {  // bring h_ind up to date after device shuffles
   if (!c->host_ind_stale) return SGD_OK;
+  c->h_ind.resize((size_t)c->R);
   CUDA_TRY(cudaStreamSynchronize(c->shuf_stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   CUDA_TRY(cudaMemcpy(c->h_ind.data(), c->d_perm[c->cur], sizeof(int32_t) * (size_t)c->R, cudaMemcpyDeviceToHost));
@@ -910,6 +919,11 @@ int sgd_create(const sgd_config* cfg, const float* X, const float* y, sgd_ctx** 
     g_last_error = keep;
     return rc;
   };
+  const bool dbg_time = std::getenv("B200SGD_DEBUG") != nullptr;
+  const auto t_setup = clk::now();
+  auto stamp = [&](const char* what) {
+    if (dbg_time) std::fprintf(stderr, "[b200sgd] sgd_create %-28s %8.2f ms\n", what, ms_since(t_setup));
+  };
   auto setup = [&]() -> int {
     SGD_TRY(bind(c));
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -924,18 +938,20 @@ int sgd_create(const sgd_config* cfg, const float* X, const float* y, sgd_ctx** 
       CUDA_TRY(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
     }
     CUDA_TRY(cudaEventCreateWithFlags(&c->ev_done[2], cudaEventDisableTiming));
+    stamp("streams, events");
     SGD_TRY(configure_launch(c));
+    stamp("configure_launch");
     const size_t rec_bytes = sizeof(float) * (size_t)std::max<int64_t>(1, c->local_rows) * (size_t)c->ld;
     if (cudaMalloc(&c->d_rec, rec_bytes) != cudaSuccess) {
       cudaGetLastError();
       return fail(SGD_ERR_NOMEM, "cannot allocate " + std::to_string(rec_bytes >> 20) + " MiB of HBM for the data");
     }
+    stamp("record array");
     SGD_TRY(make_record_tensor_map(c));
     CUDA_TRY(cudaMalloc(&c->d_w, sizeof(float) * c->C));
     CUDA_TRY(cudaMalloc(&c->d_wtrue, sizeof(float) * c->C));
     for (int i = 0; i < 2; ++i) {
       CUDA_TRY(cudaMalloc(&c->d_perm[i], sizeof(int32_t) * (size_t)c->R));
-      CUDA_TRY(cudaMallocHost(&c->h_stage[i], sizeof(int32_t) * (size_t)c->R));
     }
     if (c->cfg.nranks > 1) {
       CUDA_TRY(cudaMalloc(&c->d_perm_local, sizeof(int32_t) * (size_t)std::max<int64_t>(1, c->local_rows)));
@@ -969,6 +985,7 @@ int sgd_create(const sgd_config* cfg, const float* X, const float* y, sgd_ctx** 
       CUDA_TRY(cudaMalloc(&c->d_rout, sizeof(float) * (size_t)std::max<int64_t>(1, c->rout_len)));
       CUDA_TRY(cudaMemset(c->d_rout, 0, sizeof(float) * (size_t)std::max<int64_t>(1, c->rout_len)));
     }
+    stamp("step buffers");
     // bit-exact permutation on the device for anything but tiny data sets
     c->device_shuffle = !(c->cfg.flags & SGD_FLAG_HOST_SHUFFLE) && c->R >= 32768;
     if (c->device_shuffle) {
@@ -991,6 +1008,7 @@ int sgd_create(const sgd_config* cfg, const float* X, const float* y, sgd_ctx** 
       CUDA_TRY(cudaMalloc(&c->d_states, sizeof(uint32_t) * 31 * (size_t)c->nchunks));
       for (int i = 0; i < 2; ++i) CUDA_TRY(cudaMallocHost(&c->h_states[i], sizeof(uint32_t) * 31 * (size_t)c->nchunks));
     }
+    stamp("shuffle buffers");
     c->mae_blocks = c->num_sms * 8;
     if (sizeof(float) * 4 * (size_t)c->C4 > (48u << 10))  // weights in shared memory: opt in above 48 KB
       CUDA_TRY(cudaFuncSetAttribute((const void*)b200sgd::sgd_mae_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1008,15 +1026,18 @@ int sgd_create(const sgd_config* cfg, const float* X, const float* y, sgd_ctx** 
       c->peer_block[c->cfg.rank] = c->d_xchg_block;
     }
     SGD_TRY(configure_cluster(c));
+    stamp("cluster configuration");
     // main.cu:389-395: weights ~ U(0, 0.01) from the Thrust minstd stream, drawn on the host
     std::vector<float> w0(c->C);
     b200sgd::thrust_minstd_weights(w0.data(), c->C);
     CUDA_TRY(cudaMemcpy(c->d_w, w0.data(), sizeof(float) * c->C, cudaMemcpyHostToDevice));
-    // main.cu:421-426: identity index vector, on host and device
-    c->h_ind.resize((size_t)c->R);
-    for (int64_t i = 0; i < c->R; ++i) c->h_ind[(size_t)i] = (int32_t)i;
-    CUDA_TRY(cudaMemcpy(c->d_perm[0], c->h_ind.data(), sizeof(int32_t) * (size_t)c->R, cudaMemcpyHostToDevice));
+    // main.cu:421-426: identity index vector; the host copy is materialised when somebody needs it
+    b200sgd::shuf_iota_kernel<<<std::max(1, std::min<int>(c->num_sms * 8, (int)((c->R + 255) / 256))), 256, 0, c->stream>>>(
+        c->d_perm[0], c->R);
+    CUDA_TRY(cudaGetLastError());
+    c->host_ind_stale = true;
     CUDA_TRY(cudaDeviceSynchronize());
+    stamp("weights, identity, sync");
     return SGD_OK;
   };
   int rc = setup();
@@ -1193,6 +1214,7 @@ int sgd_shuffle(sgd_ctx* c) {
     return SGD_OK;
   }
   SGD_TRY(sync_host_ind(c));
+  SGD_TRY(ensure_host_stage(c));
   // main.cu:90 / :207: std::random_shuffle(ind_vector.begin(), ind_vector.end()), cumulative
   b200sgd::exact_shuffle(c->rng, c->h_ind.data(), c->R);
   const int buf = c->cur ^ 1;
@@ -1212,6 +1234,8 @@ int sgd_set_permutation(sgd_ctx* c, const int32_t* perm) {
   for (int64_t i = 0; i < c->R; ++i)
     if (perm[i] < 0 || perm[i] >= c->R) return fail(SGD_ERR_ARG, "permutation entry out of range");
   SGD_TRY(bind(c));
+  SGD_TRY(ensure_host_stage(c));
+  c->h_ind.resize((size_t)c->R);
   std::memcpy(c->h_ind.data(), perm, sizeof(int32_t) * (size_t)c->R);
   c->host_ind_stale = false;
   const int buf = c->cur ^ 1;
@@ -1235,6 +1259,7 @@ int sgd_get_permutation(sgd_ctx* c, int32_t* perm) {
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     CUDA_TRY(cudaMemcpy(perm, c->d_perm[c->cur], sizeof(int32_t) * (size_t)c->R, cudaMemcpyDeviceToHost));
   } else {
+    SGD_TRY(sync_host_ind(c));  // before the first shuffle: the identity
     std::memcpy(perm, c->h_ind.data(), sizeof(int32_t) * (size_t)c->R);
   }
   return SGD_OK;
@@ -1305,6 +1330,7 @@ int sgd_run(sgd_ctx* c, int32_t first_epoch, int32_t num_epochs, sgd_timings* to
       return SGD_OK;
     }
     SGD_TRY(sync_host_ind(c));
+    SGD_TRY(ensure_host_stage(c));
     b200sgd::exact_shuffle(c->rng, c->h_ind.data(), c->R);
     const int buf = c->cur ^ 1;
     CUDA_TRY(cudaEventSynchronize(c->ev_perm[buf]));

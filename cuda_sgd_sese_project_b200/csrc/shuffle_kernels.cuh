@@ -64,6 +64,12 @@ __global__ void __launch_bounds__(128) shuf_targets_stream_kernel(const uint32_t
   }
 }
 
+// the reference's ind_vector before the first shuffle (main.cu:421-424), written on the device
+__global__ void __launch_bounds__(256) shuf_iota_kernel(int32_t* __restrict__ out, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = (int32_t)i;
+}
+
 constexpr int kScanBlock = 1024;
 constexpr int kScanPerThread = 4;
 constexpr int kScanTile = kScanBlock * kScanPerThread;
