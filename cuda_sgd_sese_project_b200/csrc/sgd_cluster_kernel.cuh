@@ -1,29 +1,33 @@
-// sgd_cluster_kernel.cuh -- the epoch kernel for SMALL steps of narrow rows (BASELINE config 2:
-// 4M x 100, B = 1000: a step moves 0.45 MB = 70 ns of HBM time; what it costs is the cross-SM
+// sgd_cluster_kernel.cuh -- the epoch kernel for small and mid-size steps of narrow rows (BASELINE
+// config 2: 4M x 100, B = 1000: a step moves 0.45 MB = 70 ns of HBM time; what it costs is the cross-SM
 // dependency "step k+1 needs the weights of step k, which need every row of step k").
 //
 // Same algorithm, record layout and summation discipline as sgd_epoch_kernel (sgd_kernels.cuh;
-// reference: cuda_iteration / cublas_iteration, main.cu:56-163 / :168-301), but the whole grid is ONE
-// thread-block cluster (8 or 16 CTAs) and the per-step gradient exchange never leaves the SMs:
+// reference: cuda_iteration / cublas_iteration, main.cu:56-163 / :168-301), but the CTAs that share a
+// step form ONE thread-block cluster (16 CTAs, or 8) and the per-step gradient exchange never leaves
+// the SMs:
 //
 //   * Through L2 (the generic kernel) a hop is "store, then poll": ~800 cycles SM to SM, quantised by
 //     the poll round trip and stretched by the slowest of 32 publishers -- measured 2400 + 2000
-//     cycles for the two hops of a 6500-cycle step.  Here every warp sends its 128 bytes of column
-//     sums straight into the shared memory of every CTA of the cluster with one bulk copy per
-//     destination (cp.async.bulk.shared::cluster.shared::cta), which completes bytes on the
+//     cycles for the two hops of a 6500-cycle step.  Here every warp sends its 16 column sums from
+//     registers straight into the shared memory of every CTA of the cluster (st.async, four columns
+//     per lane, one instruction per eight destination CTAs), each store completing its bytes on the
 //     RECEIVER's mbarrier: the receiver sleeps on a local mbarrier instead of polling L2, and there
-//     is no second hop at all -- every CTA adds the same 2*CS partials in the same order and updates
-//     its own copy of the weights (bit-identical in all CTAs, no atomics, reruns reproduce).
+//     is no second hop -- every CTA adds the same CS partials in the same order and updates its own
+//     copy of the weights (bit-identical in all CTAs, no atomics, reruns reproduce).
 //   * Column mapping of the gradient: phase A (8 lanes per row, 4 rows per warp, 8 warps = one 32-row
-//     ring tile) leaves the residuals in shared memory; after one CTA barrier thread (h, c) adds
-//     res[r] * x[r][c] over the rows 16h..16h+15 of the tile straight from the staged records.  A warp
-//     therefore ends the step with 32 finished column sums in 32 lanes -- exactly what it sends; the
-//     two row halves of a CTA travel as two sources.
-//   * Producer warp: TMA tile::gather4 (four rows per instruction) into the ring, running ahead of
+//     ring tile) leaves the residuals in shared memory; after one CTA barrier warp w adds
+//     res[r] * x[r][c] for its columns 16w .. 16w+15 straight from the staged records, one half warp
+//     over the even rows, the other over the odd rows; one shuffle folds the halves.  A warp therefore
+//     ends the step with 16 finished column sums -- exactly what it sends.
+//   * The rows of the next step are loaded into registers while the exchange is in flight.
+//   * Producer warps: TMA tile::gather4 (four rows per instruction) into the ring, running ahead of
 //     the consumers across step boundaries, as in the generic kernel.
+//   * Mid-size batches and several GPUs (MULTI): several clusters ("groups") take part in a step and
+//     meet in an inbox of tagged words in global memory (L2 on one GPU, NVLink between GPUs).
 //
 // Restrictions (the host falls back to sgd_epoch_kernel otherwise): C + 1 <= 128, tile::gather4
-// available, single GPU, persistent engine, dataflow reduction, no residual output.
+// available, persistent engine, dataflow reduction, no residual output, 48 .. 10240 rows per rank and step.
 #pragma once
 #include "sgd_kernels.cuh"
 
@@ -66,12 +70,6 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank
   uint32_t r;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
   return r;
-}
-// own shared memory -> shared memory of another CTA of the cluster; completes `bytes` on THAT CTA's mbarrier
-__device__ __forceinline__ void bulk_s2cluster(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t bar_cluster) {
-  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_cluster),
-               "r"(src_cta), "r"(bytes), "r"(bar_cluster)
-               : "memory");
 }
 // tagged 8-byte words {value, tag} through global memory (cross-GPU hop): see ll_store_f4
 __device__ __forceinline__ void ll_store_f1(uint2* dst, float v, uint32_t tag) {
