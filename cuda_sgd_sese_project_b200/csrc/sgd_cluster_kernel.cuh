@@ -263,12 +263,20 @@ __global__ void __launch_bounds__(32 * (kClNW + kClNP), 1) sgd_cluster_epoch_ker
     float y[CHUNK];
     bool live[CHUNK];
     auto load_block = [&](int t0, int nch, int n) {
+      // all probes of the block first, back to back (a probe takes ~100 cycles even when the tile has
+      // landed long ago), the retry loop only for tiles that are late
+      bool landed[CHUNK];
 #pragma unroll
       for (int u = 0; u < CHUNK; ++u) {
         const uint32_t q = tq + (uint32_t)u;
         const uint32_t tile = q & tile_mask;
         tb[u] = ring + (size_t)tile * tile_bytes;
-        if (u < nch) mbar_wait_guarded(full0 + 8u * tile, (q >> p.tile_log2) & 1u, p.err);
+        landed[u] = u >= nch || mbar_try_wait(full0 + 8u * tile, (q >> p.tile_log2) & 1u);
+      }
+#pragma unroll
+      for (int u = 0; u < CHUNK; ++u) {
+        const uint32_t q = tq + (uint32_t)u;
+        if (!landed[u]) mbar_wait_guarded(full0 + 8u * (q & tile_mask), (q >> p.tile_log2) & 1u, p.err);
       }
 #pragma unroll
       for (int u = 0; u < CHUNK; ++u) {
