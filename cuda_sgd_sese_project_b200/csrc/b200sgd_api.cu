@@ -294,19 +294,20 @@ int configure_launch(sgd_ctx* c) {
     const char* e = std::getenv("B200SGD_CLUSTER");
     const int want = e ? std::atoi(e) : b200sgd::kClMaxCS;
     const char* em = std::getenv("B200SGD_CLUSTER_MAX_ROWS");  // largest step (rows per rank) the cluster kernel takes
-    // measured at C = 100 (us per step, cluster / generic kernel): 4096 rows 2.95 / 3.87, 8192 4.05 / 4.4,
-    // 10000 4.42 / 4.6, 30000 7.4 / 6.2, 100000 15.7 / 12.7: beyond ~10k rows the per-warp streaming of
-    // the generic kernel wins over the per-tile CTA barrier of this one
+    // measured at C = 100 (us per step, cluster / generic kernel): 4096 rows 2.79 / 3.87, 8192 3.16 / 4.4,
+    // 10000 3.23 / 4.6, 16384 5.1 / 4.9, 30000 6.6 / 6.2, 100000 15.2 / 12.7: beyond ~12k rows the generic
+    // kernel wins (it streams on 128 SMs, 7 clusters are 112, and the per-SM TMA row rate is the limit)
     const int64_t max_rows = em ? std::atoll(em) : 10240;
     if ((want == 8 || want == 16) && c->ld <= 128 && c->cfg.engine != SGD_ENGINE_GRAPH &&
         (c->cfg.reduce == SGD_REDUCE_AUTO || c->cfg.reduce == SGD_REDUCE_DATAFLOW) &&
         !(c->cfg.flags & SGD_FLAG_RESIDUALS) && rows_step >= 48 && rows_step <= max_rows) {
-      // clusters: the L2 hop between clusters costs ~1.2 us per step, a ring tile of 32 rows ~0.3 us, so one
-      // cluster serves steps of up to 4095 rows; beyond, enough clusters for <= 64 rows per CTA and
-      // step, as far as they fit on the GPU at once (configure_cluster: 7 clusters of 16 CTAs on a
-      // B200).  Several GPUs: one cluster per GPU.
+      // clusters: the L2 hop between clusters costs ~1 us per step, a ring tile of 32 rows ~0.2-0.3 us
+      // (2000 rows: 1.93 us on one cluster, 2.61 on two; 3000 rows: 3.54 / 2.86), so one cluster serves
+      // steps of up to 2048 rows (one four-tile block per CTA); beyond, enough clusters for <= 64 rows
+      // per CTA and step, as far as they fit on the GPU at once (configure_cluster: 7 clusters of 16
+      // CTAs on a B200).  Several GPUs: one cluster per GPU.
       int ng = 1;
-      if (c->cfg.nranks == 1 && rows_step >= 4096)
+      if (c->cfg.nranks == 1 && rows_step > 2048)
         ng = (int)std::min<int64_t>(c->num_sms / want, (rows_step + 64 * want - 1) / (64 * want));
       if (const char* en = std::getenv("B200SGD_CLUSTERS")) ng = std::max(1, std::atoi(en));
       if (c->cfg.grid > 0 && c->cfg.grid % want == 0) ng = c->cfg.grid / want;  // explicit grid: that many clusters

@@ -439,28 +439,33 @@ __global__ void __launch_bounds__(32 * (kClNW + kClNP), 1) sgd_cluster_epoch_ker
                 if (NG > 1 || r != p.rank) ll_store_f1(reinterpret_cast<uint2*>(p.ll_inbox_peer[r]) + at, tot, tag);
             const uint2* inbox = reinterpret_cast<const uint2*>(p.ll_inbox_local) + (int64_t)par * TG * cpad + c;
             float all = 0.f;
-            for (int q0 = 0; q0 < TG; q0 += 8) {  // eight polls in flight
-              uint2 u[8];
-#pragma unroll
-              for (int k = 0; k < 8; ++k)
-                if (q0 + k < TG && q0 + k != me) u[k] = ld_volatile_u2(inbox + (int64_t)(q0 + k) * cpad);
+            for (int q0 = 0; q0 < TG; q0 += 8) {
+              // poll all missing groups of the batch together until the last one has arrived: after the
+              // last arrival one L2 round trip is left, not one per group
+              float vq[8];
+              uint32_t pending = 0;
 #pragma unroll
               for (int k = 0; k < 8; ++k) {
-                if (q0 + k < TG) {
-                  float vq = tot;
-                  if (q0 + k != me) {
-                    if (u[k].y != tag) {
-                      SpinGuard guard;
-                      do {
-                        if (guard.expired(p.err, 3u)) break;
-                        u[k] = ld_volatile_u2(inbox + (int64_t)(q0 + k) * cpad);
-                      } while (u[k].y != tag);
-                    }
-                    vq = __uint_as_float(u[k].x);
-                  }
-                  all += vq;
-                }
+                vq[k] = tot;
+                if (q0 + k < TG && q0 + k != me) pending |= 1u << k;
               }
+              SpinGuard guard;
+              while (pending != 0u) {
+                uint2 u[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                  if (pending & (1u << k)) u[k] = ld_volatile_u2(inbox + (int64_t)(q0 + k) * cpad);
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                  if ((pending & (1u << k)) && u[k].y == tag) {
+                    vq[k] = __uint_as_float(u[k].x);
+                    pending &= ~(1u << k);
+                  }
+                if (pending != 0u && guard.expired(p.err, 3u)) break;
+              }
+#pragma unroll
+              for (int k = 0; k < 8; ++k)
+                if (q0 + k < TG) all += vq[k];
             }
             tot = all;
           }
