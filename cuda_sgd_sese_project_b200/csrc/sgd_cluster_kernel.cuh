@@ -80,6 +80,15 @@ __device__ __forceinline__ uint2 ld_volatile_u2(const uint2* p) {
   asm volatile("ld.volatile.global.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
   return v;
 }
+// two fp32 FMAs in one instruction (SASS FFMA2; each half rounds exactly like fmaf)
+__device__ __forceinline__ float2 ffma2(float2 a, float s, float2 c) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2,%3};\n\tmov.b64 rb, {%4,%4};\n\tmov.b64 rc, {%5,%6};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0,%1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(s), "f"(c.x), "f"(c.y));
+  return d;
+}
 // mbarrier wait with the watchdog of the L2 spin loops: a lost message must not hang the GPU
 __device__ __forceinline__ void mbar_wait_guarded(uint32_t bar, uint32_t parity, unsigned int* err) {
   if (mbar_try_wait(bar, parity)) return;
@@ -230,14 +239,15 @@ __global__ void __launch_bounds__(32 * (kClNW + kClNP), 1) sgd_cluster_epoch_ker
     // ======================================= CONSUMERS =======================================
     const int ctid = tid - 32 * kClNP, cw = warp - kClNP;
     const int rg = lane >> 3, sl = lane & 7;  // phase A: row group of the warp, sub-lane within the row
-    const int hp = lane >> 4;                 // phase B: row parity of this half warp ...
-    const int colB = 16 * cw + (lane & 15);   // ... and its gradient column (16 columns per warp)
+    const int hp = lane >> 4;                 // sum phase: which half of the sources this half warp adds
+    const int cls = lane >> 3;                // phase B: my rows of a tile are cls, cls + 4, cls + 8, ...
+    const int colB = 16 * cw + 2 * (lane & 7);  // ... and my two gradient columns (16 columns per warp)
     const int C = p.C, ld = (int)p.ld, ld4 = ld >> 2;
     const float Bf = (float)p.B, a = p.a;
     const uint32_t expect = (uint32_t)CS * (((uint32_t)C * 4u + 15u) & ~15u);  // bytes every CTA receives per step
     const bool armer = ctid == kClCT - 1;  // arms the receive barriers (kept off warp 0's path)
     const int rowA = cw * 4 + rg;             // my row of every tile in phase A
-    const int rslot = (rowA & 1) * 16 + (rowA >> 1);  // residuals are stored even rows first, then odd rows
+    const int rslot = (rowA & 3) * 8 + (rowA >> 2);  // residuals are stored by row class (row mod 4)
     int n;                                    // my rows of the current step
     {
       int64_t off_unused;
@@ -307,7 +317,9 @@ __global__ void __launch_bounds__(32 * (kClNW + kClNP), 1) sgd_cluster_epoch_ker
       float4 wv[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) wv[k] = reinterpret_cast<const float4*>(w_s)[sl + 8 * k];
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};  // column colB over the rows of my parity
+      float2 acc[4];  // columns colB, colB + 1 over the rows of my class
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[j] = make_float2(0.f, 0.f);
       // the tiles of the step, CHUNK at a time: phase A of all of them as one straight-line block
       // (their latencies overlap), one CTA barrier, phase B of all of them.  The rows of the first
       // block are already in registers (fetched while the previous step's exchange was in flight).
@@ -345,22 +357,23 @@ __global__ void __launch_bounds__(32 * (kClNW + kClNP), 1) sgd_cluster_epoch_ker
         mark(1);  // phase A done
         consumer_bar<kClCT>();
         mark(2);  // residuals visible
-        // ---- phase B: res[r] * x[r][colB] over the 16 rows of my parity of every tile.  No row
-        // bound: rows beyond the slice have res = 0 and finite (stale or zero-initialised) records.
-        // (Adjacent rows are ld = 16 mod 32 floats apart for C = 100: the half warps hit disjoint banks.)
+        // ---- phase B: res[r] * x[r][colB, colB+1] over the 8 rows of my class of every tile, two columns
+        // per lane and instruction (FFMA2).  No row bound: rows beyond the slice have res = 0 and finite
+        // (stale or zero-initialised) records.  (Adjacent rows are ld = 16 mod 32 floats apart for C = 100:
+        // the two row classes of a half warp hit disjoint banks.)
         if (colB < ld) {
 #pragma unroll
           for (int u = 0; u < CHUNK; ++u) {
             if (u < nch) {
-              const float* col = reinterpret_cast<const float*>(tb[u]) + (size_t)hp * ld + colB;
-              const float4* r4 = reinterpret_cast<const float4*>(rr + u * 32 + 16 * hp);
+              const float* col = reinterpret_cast<const float*>(tb[u]) + (size_t)cls * ld + colB;
+              const float4* r4 = reinterpret_cast<const float4*>(rr + u * 32 + 8 * cls);
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float4 rv = r4[j];  // rows 2*(4j..4j+3) + hp
-                acc[0] = fmaf(rv.x, col[(size_t)(8 * j + 0) * ld], acc[0]);
-                acc[1] = fmaf(rv.y, col[(size_t)(8 * j + 2) * ld], acc[1]);
-                acc[2] = fmaf(rv.z, col[(size_t)(8 * j + 4) * ld], acc[2]);
-                acc[3] = fmaf(rv.w, col[(size_t)(8 * j + 6) * ld], acc[3]);
+              for (int j = 0; j < 2; ++j) {
+                const float4 rv = r4[j];  // rows 4*(4j..4j+3) + cls
+                acc[0] = ffma2(*reinterpret_cast<const float2*>(col + (size_t)(16 * j + 0) * ld), rv.x, acc[0]);
+                acc[1] = ffma2(*reinterpret_cast<const float2*>(col + (size_t)(16 * j + 4) * ld), rv.y, acc[1]);
+                acc[2] = ffma2(*reinterpret_cast<const float2*>(col + (size_t)(16 * j + 8) * ld), rv.z, acc[2]);
+                acc[3] = ffma2(*reinterpret_cast<const float2*>(col + (size_t)(16 * j + 12) * ld), rv.w, acc[3]);
               }
             }
           }
@@ -374,21 +387,24 @@ __global__ void __launch_bounds__(32 * (kClNW + kClNP), 1) sgd_cluster_epoch_ker
         tq += (uint32_t)nch;
       }
 
-      // ---- exchange: fold the two row parities (one shuffle); the warp's 16 column sums then go to
-      // slot [par][cta][16*cw ..] of EVERY CTA straight from registers: lane l carries the four columns
-      // 4*(l & 3) .. +3 to CTA (l >> 2) (+ 8 in the second pass), so ONE st.async.v4 serves 8 destination
-      // CTAs, each store completing its 16 bytes on its destination's barrier.  No staging, no proxy
-      // fence, no CTA barrier.  (Issuing costs a warp ~60 cycles per remote-store instruction or bulk
-      // copy whatever its size: 16 of them per warp were 1000 cycles per step.)
+      // ---- exchange: fold the four row classes (two shuffle levels on two columns); the warp's 16 column
+      // sums then go to slot [par][cta][16*cw ..] of EVERY CTA straight from registers: lane l carries
+      // the four columns 4*(l & 3) .. +3 to CTA (l >> 2) (+ 8 in the second pass), so ONE st.async.v4
+      // serves 8 destination CTAs, each store completing its 16 bytes on its destination's barrier.
+      // No staging, no proxy fence, no CTA barrier.  (Issuing costs a warp ~60 cycles per remote-store
+      // instruction or bulk copy whatever its size: 16 of them per warp were 1000 cycles per step.)
       {
-        float v = (acc[0] + acc[1]) + (acc[2] + acc[3]);
-        v += __shfl_xor_sync(0xffffffffu, v, 16);
-        const int q4 = 4 * (lane & 3);
+        float2 v = make_float2((acc[0].x + acc[1].x) + (acc[2].x + acc[3].x), (acc[0].y + acc[1].y) + (acc[2].y + acc[3].y));
+        v.x += __shfl_xor_sync(0xffffffffu, v.x, 8);
+        v.y += __shfl_xor_sync(0xffffffffu, v.y, 8);
+        v.x += __shfl_xor_sync(0xffffffffu, v.x, 16);
+        v.y += __shfl_xor_sync(0xffffffffu, v.y, 16);
+        const int q4 = 4 * (lane & 3);  // my four columns live in lanes q4/2 and q4/2 + 1
         float4 f;
-        f.x = __shfl_sync(0xffffffffu, v, q4 + 0);
-        f.y = __shfl_sync(0xffffffffu, v, q4 + 1);
-        f.z = __shfl_sync(0xffffffffu, v, q4 + 2);
-        f.w = __shfl_sync(0xffffffffu, v, q4 + 3);
+        f.x = __shfl_sync(0xffffffffu, v.x, (q4 >> 1) + 0);
+        f.y = __shfl_sync(0xffffffffu, v.y, (q4 >> 1) + 0);
+        f.z = __shfl_sync(0xffffffffu, v.x, (q4 >> 1) + 1);
+        f.w = __shfl_sync(0xffffffffu, v.y, (q4 >> 1) + 1);
         if (16 * cw + q4 < C) {  // whole 16-byte units up to C (the sum of these is `expect`)
           const uint32_t slot = smem0 + kClOffRecv + (uint32_t)(((par * kClMaxCS + cta) * kClSlot + 16 * cw + q4) * 4);
 #pragma unroll
