@@ -49,7 +49,10 @@ typedef enum {
   SGD_ENGINE_GRAPH = 2       /* one fused kernel per step, steps captured in a CUDA graph       */
 } sgd_engine;
 
-/* How the per-CTA partial gradients become the new weights (DESIGN.md "grid reduction"). */
+/* How the per-CTA partial gradients become the new weights (DESIGN.md "grid reduction").  AUTO (and
+ * DATAFLOW) lets narrow rows with small and mid-size steps run on the cluster kernel (DESIGN.md 3.2:
+ * the CTAs of a thread-block cluster exchange their partials through distributed shared memory);
+ * the other values pin the generic kernel to one scheme (A/B measurements). */
 typedef enum {
   SGD_REDUCE_AUTO = 0,
   SGD_REDUCE_ALLGATHER = 1, /* every CTA sums all partials itself: 1 grid barrier, G^2*C traffic */
@@ -69,7 +72,7 @@ typedef struct sgd_config {
   int32_t nranks;      /* number of row shards / GPUs (1 for single GPU)                       */
   int32_t engine;      /* sgd_engine                                                           */
   int32_t reduce;      /* sgd_reduce                                                           */
-  int32_t grid;        /* CTAs of the persistent kernel, 0 = auto                              */
+  int32_t grid;        /* CTAs of the persistent kernel, 0 = auto (cluster kernel: a multiple of 8 / 16) */
   uint32_t shuffle_seed; /* seed of the rand() stream; 0 or 1 = the reference's unseeded rand() */
   int32_t flags;       /* SGD_FLAG_*                                                           */
   int32_t reserved[7];
@@ -196,7 +199,8 @@ int sgd_get_local_schedule(sgd_ctx* ctx, int32_t* local_perm, int64_t local_cap,
 /* diagnostics: when the context was created with B200SGD_PHASE_PROFILE=1 in the environment, the
  * epoch kernel sums, per CTA, the SM cycles of the phases of a step (rows | CTA reduce | publish
  * partial | gather+update (1-hop) | owner work (2-hop) | wait for weights | CTA barrier | -) of
- * the LAST launch.  out gets 8 values per CTA; returns the number of CTAs written or < 0. */
+ * the LAST launch.  out gets 8 values per CTA; returns the number of CTAs written or < 0.  (The
+ * cluster kernel stores the SM clock at eight marks of its middle step instead) */
 int sgd_debug_phase_cycles(sgd_ctx* ctx, uint64_t* out, int32_t max_ctas);
 
 /* ---- multi-GPU (new functionality, BASELINE.json north_star; one process per GPU) -----------
