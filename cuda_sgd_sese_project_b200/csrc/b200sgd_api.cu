@@ -374,11 +374,6 @@ int configure_launch(sgd_ctx* c) {
 
 // Ring geometry, attributes and schedulability of the cluster kernel; falls back to the generic
 // kernel (cluster_cs = 0) when the tensor map or a free GPC for the cluster is missing.
-int configure_cluster(sgd_ctx* c);
-int configure_cluster_retry(sgd_ctx* c, int cs) {  // with a smaller number of clusters
-  c->cluster_cs = cs;
-  return configure_cluster(c);
-}
 int configure_cluster(sgd_ctx* c) {
   if (c->cluster_cs == 0) return SGD_OK;
   const int cs = c->cluster_cs;
@@ -393,54 +388,54 @@ int configure_cluster(sgd_ctx* c) {
   c->cluster_ntiles = ntiles;
   c->cluster_tile_log2 = lg;
   c->cluster_smem = b200sgd::kClFixedSmem + (size_t)ntiles * tile_bytes;
-  // tiles of one CTA per step -> phase-A block size
   const bool prof = c->d_dbg != nullptr;
-  const bool multi = c->cfg.nranks > 1 || c->cluster_ng > 1;
   const int64_t rows_rank = std::max<int64_t>(1, (int64_t)c->B / c->cfg.nranks);
-  const int64_t ctas = (int64_t)cs * c->cluster_ng;
-  const int tiles = (int)(((rows_rank + ctas - 1) / ctas + b200sgd::kClTileRows - 1) / b200sgd::kClTileRows);
-  const void* fn = nullptr;
-  using namespace b200sgd;
-  if (multi) {
-    fn = tiles <= 1 ? (const void*)sgd_cluster_epoch_kernel<1, false, true>
-       : tiles <= 2 ? (const void*)sgd_cluster_epoch_kernel<2, false, true>
-                    : (const void*)sgd_cluster_epoch_kernel<4, false, true>;
-  } else if (prof) {
-    fn = tiles <= 1 ? (const void*)sgd_cluster_epoch_kernel<1, true> : tiles <= 2 ? (const void*)sgd_cluster_epoch_kernel<2, true>
-                                                                                  : (const void*)sgd_cluster_epoch_kernel<4, true>;
-  } else {
-    fn = tiles <= 1 ? (const void*)sgd_cluster_epoch_kernel<1> : tiles <= 2 ? (const void*)sgd_cluster_epoch_kernel<2>
-                                                                            : (const void*)sgd_cluster_epoch_kernel<4>;
-  }
-  c->cluster_fn = fn;
-  CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->cluster_smem));
-  if (cs > 8) CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-  cudaLaunchConfig_t lc = {};
-  lc.gridDim = dim3(cs * c->cluster_ng);
-  lc.blockDim = dim3(32 * (b200sgd::kClNW + b200sgd::kClNP));
-  lc.dynamicSmemBytes = c->cluster_smem;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = cs;
-  at[0].val.clusterDim.y = 1;
-  at[0].val.clusterDim.z = 1;
-  lc.attrs = at;
-  lc.numAttrs = 1;
-  int nclusters = 0;
-  // every cluster of the launch must be resident at once: they wait for one another's sums
-  if (cudaOccupancyMaxActiveClusters(&nclusters, fn, &lc) != cudaSuccess || nclusters < 1) {
-    cudaGetLastError();
-    return SGD_OK;
-  }
-  if (std::getenv("B200SGD_DEBUG"))
-    std::fprintf(stderr, "[b200sgd] cluster size %d: at most %d clusters resident, %d wanted\n", cs, nclusters, c->cluster_ng);
-  if (nclusters < c->cluster_ng) {
+  for (;;) {  // until the wanted number of clusters is resident at once
+    // instantiation: tiles of one CTA per step -> phase-A block size; more than one group -> MULTI
+    using namespace b200sgd;
+    const bool multi = c->cfg.nranks > 1 || c->cluster_ng > 1;
+    const int64_t ctas = (int64_t)cs * c->cluster_ng;
+    const int tiles = (int)(((rows_rank + ctas - 1) / ctas + kClTileRows - 1) / kClTileRows);
+    const void* fn = nullptr;
+    if (multi) {
+      fn = tiles <= 1 ? (const void*)sgd_cluster_epoch_kernel<1, false, true>
+         : tiles <= 2 ? (const void*)sgd_cluster_epoch_kernel<2, false, true>
+                      : (const void*)sgd_cluster_epoch_kernel<4, false, true>;
+    } else if (prof) {
+      fn = tiles <= 1 ? (const void*)sgd_cluster_epoch_kernel<1, true> : tiles <= 2 ? (const void*)sgd_cluster_epoch_kernel<2, true>
+                                                                                    : (const void*)sgd_cluster_epoch_kernel<4, true>;
+    } else {
+      fn = tiles <= 1 ? (const void*)sgd_cluster_epoch_kernel<1> : tiles <= 2 ? (const void*)sgd_cluster_epoch_kernel<2>
+                                                                              : (const void*)sgd_cluster_epoch_kernel<4>;
+    }
+    c->cluster_fn = fn;
+    CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->cluster_smem));
+    if (cs > 8) CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(cs * c->cluster_ng);
+    lc.blockDim = dim3(32 * (kClNW + kClNP));
+    lc.dynamicSmemBytes = c->cluster_smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cs;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    lc.attrs = at;
+    lc.numAttrs = 1;
+    int nclusters = 0;
+    // every cluster of the launch must be resident at once: they wait for one another's sums
+    if (cudaOccupancyMaxActiveClusters(&nclusters, fn, &lc) != cudaSuccess || nclusters < 1) {
+      cudaGetLastError();
+      return SGD_OK;
+    }
+    if (std::getenv("B200SGD_DEBUG"))
+      std::fprintf(stderr, "[b200sgd] cluster size %d: at most %d clusters resident, %d wanted\n", cs, nclusters, c->cluster_ng);
+    if (nclusters >= c->cluster_ng) break;
     if (c->cfg.grid > 0) return SGD_OK;  // an explicit grid that does not fit: generic kernel
-    c->cluster_ng = nclusters;
+    c->cluster_ng = nclusters;           // as many as fit (a B200 keeps 7 clusters of 16 CTAs, 15 of 8)
     c->grid = cs * c->cluster_ng;
-    return configure_cluster_retry(c, cs);
   }
-  if (c->cluster_ng > 1 && c->cfg.nranks == 1) {
+  if (c->cluster_ng > 1 && c->cfg.nranks == 1) {  // the clusters of this GPU meet in a local inbox of tagged sums
     const size_t words = 2 * (size_t)c->cluster_ng * 4 * (((size_t)c->C4 + 3) & ~(size_t)3);
     CUDA_TRY(cudaMalloc(&c->d_cl_inbox, sizeof(uint2) * words));
     CUDA_TRY(cudaMemset(c->d_cl_inbox, 0, sizeof(uint2) * words));

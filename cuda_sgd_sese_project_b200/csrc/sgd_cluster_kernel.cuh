@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(32 * (kClNW + kClNP), 1) sgd_cluster_epoch_ker
     const int hp = lane >> 4;                 // sum phase: which half of the sources this half warp adds
     const int cls = lane >> 3;                // phase B: my rows of a tile are cls, cls + 4, cls + 8, ...
     const int colB = 16 * cw + 2 * (lane & 7);  // ... and my two gradient columns (16 columns per warp)
-    const int C = p.C, ld = (int)p.ld, ld4 = ld >> 2;
+    const int C = p.C, ld = (int)p.ld;
     const float Bf = (float)p.B, a = p.a;
     const uint32_t expect = (uint32_t)CS * (((uint32_t)C * 4u + 15u) & ~15u);  // bytes every CTA receives per step
     const bool armer = ctid == kClCT - 1;  // arms the receive barriers (kept off warp 0's path)
