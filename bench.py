@@ -47,6 +47,8 @@ WORKLOADS = {
     # name: (rows per GPU, cols, batch per GPU, lr)
     "c1": (10_000, 100, 1000, 0.1),
     "c2": (4_000_000, 100, 1000, 0.1),
+    # the report's own ~1.6 GB case (sese_report_tvas.tex:690-706, source of the README's "~5x"): 200k x 2k
+    "c2p": (200_000, 2000, 1000, 0.02),
     "c4": (16_777_216, 2048, 4096, 0.1),     # 137 GB: one GPU holds it
     "c4b": (16_777_216, 2048, 65536, 0.1),
     "c5": (8_388_608, 512, 8192, 0.1),       # x8 GPUs = 64M x 512, batch 65536
