@@ -17,6 +17,7 @@ SGD_ERR_ARG, SGD_ERR_IO, SGD_ERR_PARSE, SGD_ERR_CUDA, SGD_ERR_STATE, SGD_ERR_NOM
 SGD_PATH_CUBLAS, SGD_PATH_PLAIN_CUDA, SGD_PATH_LVL1 = 0, 1, 2
 SGD_ENGINE_AUTO, SGD_ENGINE_PERSISTENT, SGD_ENGINE_GRAPH = 0, 1, 2
 SGD_REDUCE_AUTO, SGD_REDUCE_ALLGATHER, SGD_REDUCE_SCATTER, SGD_REDUCE_DATAFLOW, SGD_REDUCE_DATAFLOW_1HOP = 0, 1, 2, 3, 4
+SGD_REDUCE_CLUSTER = 5
 SGD_FLAG_HOST_SHUFFLE, SGD_FLAG_RESIDUALS = 0x1, 0x2
 SGD_PEER_HANDLE_BYTES = 128
 

@@ -65,6 +65,7 @@ struct KernelChoice {
   bool wide = false, narrow8 = false;
   const void* fn = nullptr;
   const void* fn_lean = nullptr;  // same mapping with the run-time switches folded away, or nullptr
+  const void* fn_clt = nullptr;   // same mapping with the CLUSTER step tail (launched as thread-block clusters)
   size_t fixed_smem = 0;
 };
 
@@ -76,6 +77,7 @@ KernelChoice make_choice() {
   k.narrow8 = NARROW8;
   k.fn = (const void*)b200sgd::sgd_epoch_kernel<KC, U, NW, WIDE, NARROW8>;
   if constexpr (WITH_LEAN) k.fn_lean = (const void*)b200sgd::sgd_epoch_kernel<KC, U, NW, WIDE, NARROW8, true>;
+  k.fn_clt = (const void*)b200sgd::sgd_epoch_kernel<KC, U, NW, WIDE, NARROW8, false, true>;
   k.fixed_smem = b200sgd::EpochSmem<KC, NW, WIDE>::kFixed;
   return k;
 }
@@ -93,8 +95,6 @@ bool choose_kernel(int C4, int64_t rows_per_cta, KernelChoice* out) {
   if (C4 <= 32) {
     if (rows_per_cta <= 8) *out = make_choice<1, 1, 8>();
     else if (rows_per_cta <= 16) *out = make_choice<1, 2, 8>();
-    else if (variant_env() == 5) *out = rows_per_cta <= 32 ? make_choice<1, 4, 8>() : make_choice<1, 2, 16>();
-    else if (rows_per_cta > 32 && variant_env() == 6) *out = make_choice<1, 4, 16, false, true>();
     else *out = make_choice<1, 4, 8, false, true, true>();  // 8 lanes per row, 4 rows per warp
   } else if (C4 <= 64) {
     if (rows_per_cta <= 8) *out = make_choice<2, 1, 8>();
@@ -102,11 +102,9 @@ bool choose_kernel(int C4, int64_t rows_per_cta, KernelChoice* out) {
     else *out = make_choice<2, 2, 16>();
   } else if (C4 <= 128) {
     if (rows_per_cta <= 8) *out = make_choice<4, 1, 8>();
-    else if (variant_env() == 1) *out = make_choice<4, 1, 16>();
     else *out = make_choice<4, 2, 8>();
   } else if (C4 <= 256) {
-    if (rows_per_cta > 8 && variant_env() == 2) *out = make_choice<8, 2, 8>();
-    else *out = make_choice<8, 1, 8>();
+    *out = make_choice<8, 1, 8>();
   } else if (C4 <= 512) {
     if (variant_env() == 3) *out = make_choice<2, 1, 8, true>();  // column mapping, A/B
     else *out = make_choice<16, 1, 8>();
@@ -197,6 +195,12 @@ struct sgd_ctx {
   bool cluster_coop = true;        // pass the cooperative attribute with several clusters (dropped if refused)
   uint2* d_cl_inbox = nullptr;     // one GPU, several clusters: tagged cluster sums [2][clusters][4*C4p]
   size_t cluster_smem = 0;
+  // CLUSTER step tail of the generic kernel (sgd_kernels.cuh, CLT): clt_ng clusters of clt_cs CTAs
+  bool clt = false;
+  int clt_cs = 0, clt_ng = 0, clt_slice = 0;
+  size_t clt_extra = 0;          // shared memory of the exchange (before the ring)
+  uint4* d_clt_inbox = nullptr;  // one GPU: tagged slice sums of the clusters [2][clusters][C4p][2]
+  int inflight_tiles = 0;        // producers keep at most this many ring tiles in flight (0: the whole ring)
   int nprod = 1;  // producer warps
   int tile_rows = 0;
   size_t smem_bytes = 0;
@@ -247,7 +251,7 @@ void free_all(sgd_ctx* c) {
   cudaFree(c->d_tilesum); cudaFree(c->d_states);
   if (c->h_states[0]) cudaFreeHost(c->h_states[0]);
   if (c->h_states[1]) cudaFreeHost(c->h_states[1]);
-  cudaFree(c->d_mae); cudaFree(c->d_xchg_block); cudaFree(c->d_cl_inbox);
+  cudaFree(c->d_mae); cudaFree(c->d_xchg_block); cudaFree(c->d_cl_inbox); cudaFree(c->d_clt_inbox);
   if (c->h_stage[0]) cudaFreeHost(c->h_stage[0]);
   if (c->h_stage[1]) cudaFreeHost(c->h_stage[1]);
   cudaEvent_t evs[] = {c->ev0, c->ev1, c->ev_perm[0], c->ev_perm[1], c->ev_done[0], c->ev_done[1], c->ev_done[2]};
@@ -321,50 +325,115 @@ int configure_launch(sgd_ctx* c) {
     }
   }
   grid = std::max(1, std::min(grid, c->num_sms));
-  if (!choose_kernel(c->C4, (rows_step + grid - 1) / grid, &c->kc))
-    return fail(SGD_ERR_ARG, "unsupported row width");
   const size_t slot_bytes = (size_t)c->ld * 4;
-  // producer warps: one TMA bulk copy per row is issued lane by lane (~30-40 cycles each), so
-  // short rows need several issuing warps to keep up with HBM; long rows and tiny batches do not
-  {
-    const int64_t rows_cta = (rows_step + grid - 1) / grid;
+  // Kernel variant, producer warps and ring for `g` CTAs and `extra` bytes of exchange buffers in
+  // front of the ring.  The ring takes every tile that fits (any count >= 2, not only powers of two).
+  auto geometry = [&](int g, size_t extra) -> int {
+    if (!choose_kernel(c->C4, (rows_step + g - 1) / g, &c->kc)) return fail(SGD_ERR_ARG, "unsupported row width");
+    // producer warps: one TMA bulk copy per row is issued lane by lane (~30-40 cycles each), so
+    // short rows need several issuing warps to keep up with HBM; long rows and tiny batches do not
+    const int64_t rows_cta = (rows_step + g - 1) / g;
     int np = 1;
     if (slot_bytes <= 1024) np = rows_cta >= 64 ? 4 : 2;
     else if (slot_bytes <= 4096) np = rows_cta >= 32 ? 2 : 1;
     if (const char* e = std::getenv("B200SGD_PRODUCER_WARPS")) np = std::atoi(e);
     c->nprod = std::max(1, std::min(np, b200sgd::kMaxProducerWarps));
+    int tile_rows = c->kc.NW * c->kc.U;
+    const size_t avail = kMaxDynSmem - c->kc.fixed_smem - extra;
+    if (c->kc.wide) {
+      // column mapping: as many rows per tile as two tiles allow (<= 32, a multiple of NW if possible)
+      tile_rows = (int)std::min<size_t>(32, avail / (2 * slot_bytes));
+      if (tile_rows >= c->kc.NW) tile_rows -= tile_rows % c->kc.NW;
+      if (tile_rows < 1) return fail(SGD_ERR_ARG, "row too wide for the shared-memory ring");
+    }
+    c->tile_rows = tile_rows;
+    const size_t tile_bytes = (size_t)tile_rows * slot_bytes;
+    if (2 * tile_bytes > avail) return fail(SGD_ERR_ARG, "row too wide for the shared-memory ring");
+    int ntiles = (int)std::min<size_t>(b200sgd::kMaxTiles, avail / tile_bytes);
+    if (const char* e = std::getenv("B200SGD_RING_TILES")) ntiles = std::max(2, std::min(ntiles, std::atoi(e)));
+    c->nprod = std::min(c->nprod, ntiles);
+    c->ntiles = ntiles;
+    c->tile_log2 = 0;
+    c->smem_bytes = c->kc.fixed_smem + extra + (size_t)ntiles * tile_bytes;
+    // Bytes in flight per CTA (DESIGN.md "loaded latency"): requests beyond bandwidth x latency only
+    // lengthen the queue the step tail's polls wait in.  Default 64 KB per SM (~9 MB per GPU).
+    int64_t kb = 64;
+    if (const char* e = std::getenv("B200SGD_INFLIGHT_KB")) kb = std::atoll(e);
+    int infl = kb > 0 ? (int)std::max<int64_t>(1, (kb * 1024 + (int64_t)tile_bytes / 2) / (int64_t)tile_bytes) : 0;
+    if (infl >= ntiles) infl = 0;  // the ring itself is the bound
+    c->inflight_tiles = infl;
+    return SGD_OK;
+  };
+  // CLUSTER step tail (sgd_kernels.cuh, CLT) for everything the cluster kernel above does not take and
+  // that runs on at least two clusters' worth of CTAs: the grid becomes clt_ng clusters of clt_cs CTAs.
+  c->clt = false;
+  if (c->cluster_cs == 0 && c->cfg.engine != SGD_ENGINE_GRAPH &&
+      (c->cfg.reduce == SGD_REDUCE_AUTO || c->cfg.reduce == SGD_REDUCE_CLUSTER)) {
+    int cs = 8;
+    if (const char* e = std::getenv("B200SGD_CLT")) cs = std::atoi(e);  // 0 = off; 2, 4, 8, 16 = CTAs per cluster
+    const bool cs_ok = cs == 2 || cs == 4 || cs == 8 || cs == 16;
+    const bool grid_ok = c->cfg.grid <= 0 ? grid >= 2 * cs : (c->cfg.grid % cs == 0);
+    if (cs_ok && grid_ok && c->C4 <= 2048) {
+      const int slice = (c->C4 + cs - 1) / cs;
+      int g = c->cfg.grid > 0 ? c->cfg.grid : std::max(cs, grid / cs * cs);
+      for (int pass = 0; pass < 3; ++pass) {
+        // exchange region: 4 barriers | reduce-scatter buffers [2][cs][slice] | cross-cluster partials [consumer threads]
+        choose_kernel(c->C4, (rows_step + g - 1) / g, &c->kc);
+        const size_t extra = (128 + (size_t)32 * cs * slice + (size_t)16 * 32 * c->kc.NW + 127) / 128 * 128;
+        if (geometry(g, extra) != SGD_OK) break;
+        const void* fn = c->kc.fn_clt;
+        CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
+        if (cs > 8) CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        cudaLaunchConfig_t lc = {};
+        lc.gridDim = dim3(g);
+        lc.blockDim = dim3(32 * (c->kc.NW + c->nprod));
+        lc.dynamicSmemBytes = c->smem_bytes;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = cs;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        lc.attrs = at;
+        lc.numAttrs = 1;
+        int nclusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&nclusters, fn, &lc) != cudaSuccess || nclusters < 1) {
+          cudaGetLastError();
+          break;
+        }
+        if (std::getenv("B200SGD_DEBUG"))
+          std::fprintf(stderr, "[b200sgd] cluster tail: %d CTAs per cluster, at most %d clusters resident, %d CTAs wanted\n", cs,
+                       nclusters, g);
+        int want = g / cs;
+        if (c->cfg.grid <= 0 && grid >= c->num_sms - 20) want = nclusters;  // streaming steps: every cluster the GPU holds
+        if (const char* en = std::getenv("B200SGD_CLUSTERS")) want = std::max(1, std::atoi(en));
+        const int ng = std::min(want, nclusters);
+        if (c->cfg.grid > 0 && ng * cs != c->cfg.grid) break;  // an explicit grid that does not fit
+        if (ng * cs == g) {
+          c->clt = true;
+          c->clt_cs = cs;
+          c->clt_ng = ng;
+          c->clt_slice = slice;
+          c->clt_extra = extra;
+          grid = g;
+          break;
+        }
+        g = ng * cs;  // re-derive the per-CTA geometry for the grid that fits
+      }
+    }
   }
-  int tile_rows = c->kc.NW * c->kc.U;
-  if (c->kc.wide) {
-    // column mapping: as many rows per tile as two tiles allow (<= 32, a multiple of NW if possible)
-    const size_t avail = kMaxDynSmem - c->kc.fixed_smem;
-    tile_rows = (int)std::min<size_t>(32, avail / (2 * slot_bytes));
-    if (tile_rows >= c->kc.NW) tile_rows -= tile_rows % c->kc.NW;
-    if (tile_rows < 1) return fail(SGD_ERR_ARG, "row too wide for the shared-memory ring");
-  }
-  c->tile_rows = tile_rows;
-  const size_t tile_bytes = (size_t)tile_rows * slot_bytes;
-  if (c->kc.fixed_smem + 2 * tile_bytes > kMaxDynSmem)
-    return fail(SGD_ERR_ARG, "row too wide for the shared-memory ring");
-  int ntiles = 2, lg = 1;
-  while (ntiles * 2 <= b200sgd::kMaxTiles &&
-         c->kc.fixed_smem + (size_t)(ntiles * 2) * tile_bytes <= kMaxDynSmem) {
-    ntiles *= 2;
-    ++lg;
-  }
-  c->ntiles = ntiles;
-  c->tile_log2 = lg;
-  c->smem_bytes = c->kc.fixed_smem + (size_t)ntiles * tile_bytes;
+  if (!c->clt) SGD_TRY(geometry(grid, 0));
   CUDA_TRY(cudaFuncSetAttribute(c->kc.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
   if (c->kc.fn_lean)
     CUDA_TRY(cudaFuncSetAttribute(c->kc.fn_lean, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
   int occ = 0;
-  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, c->kc.fn, 32 * (c->kc.NW + c->nprod), c->smem_bytes));
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, c->clt ? c->kc.fn_clt : c->kc.fn, 32 * (c->kc.NW + c->nprod),
+                                                         c->smem_bytes));
   if (occ < 1) return fail(SGD_ERR_CUDA, "step kernel does not fit on an SM");
   c->grid = grid;
   int mode = c->cfg.reduce;
   if (c->cfg.nranks > 1) mode = SGD_REDUCE_DATAFLOW;  // the fused NVLink exchange lives there
   if (mode < SGD_REDUCE_ALLGATHER || mode > SGD_REDUCE_DATAFLOW_1HOP) mode = SGD_REDUCE_DATAFLOW;
+  if (c->clt) mode = SGD_REDUCE_CLUSTER;
   c->reduce_mode = mode;
   c->engine = (c->cfg.engine == SGD_ENGINE_GRAPH) ? SGD_ENGINE_GRAPH : SGD_ENGINE_PERSISTENT;
   if (c->engine == SGD_ENGINE_GRAPH && c->cfg.nranks > 1)
@@ -513,6 +582,20 @@ void fill_params(sgd_ctx* c, b200sgd::EpochParams* p, int32_t epoch, int buf) {
   p->nranks = c->cfg.nranks;
   p->ctl = nullptr;
   p->dbg = c->d_dbg;
+  p->inflight_tiles = c->inflight_tiles;
+  if (c->clt) {
+    p->cl_cs = c->clt_cs;
+    p->cl_ng = c->clt_ng;
+    p->cl_slice = c->clt_slice;
+    p->cl_extra = (uint32_t)c->clt_extra;
+    if (c->cfg.nranks == 1) {
+      p->cl_inbox_local = c->d_clt_inbox;
+      p->cl_inbox_peer[0] = c->d_clt_inbox;
+    } else {
+      p->cl_inbox_local = (uint4*)c->d_xchg_block;
+      for (int r = 0; r < c->cfg.nranks; ++r) p->cl_inbox_peer[r] = (uint4*)c->peer_block[r];
+    }
+  }
 }
 
 int upload_perm(sgd_ctx* c, int buf) {
@@ -633,6 +716,32 @@ int launch_epoch(sgd_ctx* c, int32_t epoch, int buf, int* launches) {
       c->cluster_coop = false;
       lc.numAttrs = 1;
       e = cudaLaunchKernelExC(&lc, c->cluster_fn, args);
+    }
+    CUDA_TRY(e);
+    *launches += 1;
+    return SGD_OK;
+  }
+  if (c->clt) {  // generic kernel, cluster step tail: clusters wait for one another, so cooperative as well
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(c->grid);
+    lc.blockDim = dim3(32 * (c->kc.NW + c->nprod));
+    lc.dynamicSmemBytes = c->smem_bytes;
+    lc.stream = c->stream;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = c->clt_cs;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeCooperative;
+    at[1].val.cooperative = 1;
+    lc.attrs = at;
+    lc.numAttrs = (c->clt_ng > 1 && c->cluster_coop) ? 2 : 1;
+    cudaError_t e = cudaLaunchKernelExC(&lc, c->kc.fn_clt, args);
+    if (e != cudaSuccess && lc.numAttrs == 2) {  // cooperative + cluster refused: the occupancy check stands in
+      cudaGetLastError();
+      c->cluster_coop = false;
+      lc.numAttrs = 1;
+      e = cudaLaunchKernelExC(&lc, c->kc.fn_clt, args);
     }
     CUDA_TRY(e);
     *launches += 1;
@@ -1015,12 +1124,19 @@ int sgd_create(const sgd_config* cfg, const float* X, const float* y, sgd_ctx** 
       c->xchg_bytes = sizeof(uint4) * 2 * 2 * (size_t)c->cfg.nranks * (((size_t)c->C4 + 3) & ~(size_t)3);
       // direct push of the partials when the NVLink traffic per step stays small (narrow rows)
       const size_t push_bytes = (size_t)(c->cfg.nranks - 1) * c->grid * c->C4 * 32;
-      c->direct = (c->grid % 4 == 0) && push_bytes <= (1u << 20) && !std::getenv("B200SGD_NO_DIRECT");
+      c->direct = !c->clt && (c->grid % 4 == 0) && push_bytes <= (1u << 20) && !std::getenv("B200SGD_NO_DIRECT");
       c->xpart_off = (c->xchg_bytes + 255) / 256 * 256;
       if (c->direct) c->xchg_bytes = c->xpart_off + sizeof(uint4) * 2 * 2 * (size_t)c->C4 * c->cfg.nranks * c->grid;
+      // cluster tail: tagged slice sums of every cluster of every rank, [2][nranks * clusters][C4p] float4
+      if (c->clt) c->xchg_bytes = sizeof(uint4) * 2 * 2 * (size_t)c->cfg.nranks * c->clt_ng * (((size_t)c->C4 + 3) & ~(size_t)3);
       CUDA_TRY(cudaMalloc(&c->d_xchg_block, c->xchg_bytes));
       CUDA_TRY(cudaMemset(c->d_xchg_block, 0, c->xchg_bytes));
       c->peer_block[c->cfg.rank] = c->d_xchg_block;
+    }
+    if (c->clt && c->cfg.nranks == 1 && c->clt_ng > 1) {
+      const size_t bytes = sizeof(uint4) * 2 * 2 * (size_t)c->clt_ng * (((size_t)c->C4 + 3) & ~(size_t)3);
+      CUDA_TRY(cudaMalloc(&c->d_clt_inbox, bytes));
+      CUDA_TRY(cudaMemset(c->d_clt_inbox, 0, bytes));
     }
     SGD_TRY(configure_cluster(c));
     stamp("cluster configuration");

@@ -52,25 +52,6 @@ constexpr uint32_t kClOffRing = kClOffRecv + 2 * kClMaxCS * kClSlot * 4;  // 204
 constexpr uint32_t kClRingSlack = 512;  // the last row's unpredicated 128-float read may run past the ring
 constexpr size_t kClFixedSmem = kClOffRing + kClRingSlack;
 
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ uint32_t cluster_nctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// address of `smem_addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
-__device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
-  return r;
-}
 // tagged 8-byte words {value, tag} through global memory (cross-GPU hop): see ll_store_f4
 __device__ __forceinline__ void ll_store_f1(uint2* dst, float v, uint32_t tag) {
   asm volatile("st.volatile.global.v2.u32 [%0], {%1,%2};" ::"l"(dst), "r"(__float_as_uint(v)), "r"(tag) : "memory");
@@ -89,25 +70,6 @@ __device__ __forceinline__ float2 ffma2(float2 a, float s, float2 c) {
       : "f"(a.x), "f"(a.y), "f"(s), "f"(c.x), "f"(c.y));
   return d;
 }
-// mbarrier wait with the watchdog of the L2 spin loops: a lost message must not hang the GPU
-__device__ __forceinline__ void mbar_wait_guarded(uint32_t bar, uint32_t parity, unsigned int* err) {
-  if (mbar_try_wait(bar, parity)) return;
-  SpinGuard guard;
-  while (!mbar_try_wait(bar, parity)) {
-    if (guard.expired(err, 4u)) break;
-  }
-}
-// remote 16-byte store into another CTA's shared memory; completes 16 bytes on THAT CTA's mbarrier
-__device__ __forceinline__ void st_async_f4(uint32_t dst_cluster, float4 v, uint32_t bar_cluster) {
-  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1,%2,%3,%4}, [%5];" ::"r"(dst_cluster),
-               "r"(__float_as_uint(v.x)), "r"(__float_as_uint(v.y)), "r"(__float_as_uint(v.z)), "r"(__float_as_uint(v.w)),
-               "r"(bar_cluster)
-               : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async_smem() {
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-
 // EpochParams fields used: rec_map, ld, C, perm, B, nb, first_step, a, w, g_last, ntiles, tile_log2,
 // slot_bytes, loss, err.  gridDim.x == cluster size (one cluster).
 //   CHUNK = ring tiles per phase-A block (1, 2 or 4: the host takes the tiles of a step, capped at 4)

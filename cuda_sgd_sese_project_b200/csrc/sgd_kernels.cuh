@@ -89,6 +89,13 @@ struct EpochParams {
   int32_t direct;
   uint4* ll_xpart_local;
   uint4* ll_xpart_peer[8];
+  // CLUSTER reduction (reduce_mode 5, template flag CLT): the grid is cl_ng thread-block clusters of
+  // cl_cs CTAs; CTA j of a cluster owns the float4 columns [j*cl_slice, (j+1)*cl_slice)
+  int32_t cl_cs, cl_ng, cl_slice;
+  uint32_t cl_extra;        // bytes of the exchange region in dynamic shared memory (before the ring)
+  uint4* cl_inbox_local;    // [2][nranks*cl_ng][C4p][2] tagged slice sums of every cluster of every rank
+  uint4* cl_inbox_peer[8];  // the same buffer of every rank (own rank: the local one)
+  int32_t inflight_tiles;   // producers keep at most this many ring tiles in flight (0 = whole ring)
   StepCtl* ctl;             // GRAPH engine only (nullptr for the persistent engine)
   unsigned long long* dbg;  // optional [grid][8] per-phase cycle sums (sgd_debug_phase_cycles)
   double* loss;             // [grid][2] per-CTA sums of |r| and r*r over the launch (running loss)
@@ -251,6 +258,50 @@ struct SpinGuard {
     return false;
   }
 };
+// ---- thread-block clusters / distributed shared memory ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of `smem_addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+// mbarrier wait with the watchdog of the L2 spin loops: a lost message must not hang the GPU
+__device__ __forceinline__ void mbar_wait_guarded(uint32_t bar, uint32_t parity, unsigned int* err) {
+  if (mbar_try_wait(bar, parity)) return;
+  SpinGuard guard;
+  while (!mbar_try_wait(bar, parity)) {
+    if (guard.expired(err, 4u)) break;
+  }
+}
+// remote 16-byte store into another CTA's shared memory; completes 16 bytes on THAT CTA's mbarrier
+__device__ __forceinline__ void st_async_f4(uint32_t dst_cluster, float4 v, uint32_t bar_cluster) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1,%2,%3,%4}, [%5];" ::"r"(dst_cluster),
+               "r"(__float_as_uint(v.x)), "r"(__float_as_uint(v.y)), "r"(__float_as_uint(v.z)), "r"(__float_as_uint(v.w)),
+               "r"(bar_cluster)
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// the same barrier for code in which the warps of a CTA arrive from different places (producer
+// warps leave their loop, consumer warps theirs): the non-aligned forms
+__device__ __forceinline__ void cluster_sync_unaligned() {
+  asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");
+}
 // Blocks until the float4 at `src` carries `tag`.  Narrow rows (few column owners) probe both
 // 16-byte words at once: one L2 round trip less on the critical path.  Wide rows (~100 column
 // owners each polling 148 sources, 148 CTAs polling their mailboxes) probe ONE word and fetch the
@@ -343,6 +394,48 @@ __device__ __forceinline__ float4 ll_gather(const uint4* base0, int64_t stride, 
   return acc;
 }
 
+// CLUSTER tail: sum of the tagged float4 of sources q, q+Q, ... < nsrc of ONE column; source i sits
+// `stride` uint4 after source i-1.  Up to four sources in flight, consumed in order (fixed order:
+// every cluster of every GPU gets the same bits).
+__device__ __forceinline__ float4 cl_gather(const uint4* base, int64_t stride, int nsrc, int q, int Q, uint32_t tag,
+                                            unsigned int* err, unsigned one_word) {
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  int i = q;
+  for (; i + 3 * Q < nsrc; i += 4 * Q) {
+    const uint4* s0 = base + (int64_t)i * stride;
+    const uint4* s1 = base + (int64_t)(i + Q) * stride;
+    const uint4* s2 = base + (int64_t)(i + 2 * Q) * stride;
+    const uint4* s3 = base + (int64_t)(i + 3 * Q) * stride;
+    const uint4 a0 = ld_volatile_u4(s0), b0 = ld_volatile_u4(s0 + 1);
+    const uint4 a1 = ld_volatile_u4(s1), b1 = ld_volatile_u4(s1 + 1);
+    const uint4 a2 = ld_volatile_u4(s2), b2 = ld_volatile_u4(s2 + 1);
+    const uint4 a3 = ld_volatile_u4(s3), b3 = ld_volatile_u4(s3 + 1);
+    float4 v0, v1, v2, v3;
+    if (!ll_unpack(a0, b0, tag, &v0)) v0 = ll_wait_f4(s0, tag, err, one_word);
+    if (!ll_unpack(a1, b1, tag, &v1)) v1 = ll_wait_f4(s1, tag, err, one_word);
+    if (!ll_unpack(a2, b2, tag, &v2)) v2 = ll_wait_f4(s2, tag, err, one_word);
+    if (!ll_unpack(a3, b3, tag, &v3)) v3 = ll_wait_f4(s3, tag, err, one_word);
+    acc = f4_add(acc, v0);
+    acc = f4_add(acc, v1);
+    acc = f4_add(acc, v2);
+    acc = f4_add(acc, v3);
+  }
+  if (i + Q < nsrc) {
+    const uint4* s0 = base + (int64_t)i * stride;
+    const uint4* s1 = base + (int64_t)(i + Q) * stride;
+    const uint4 a0 = ld_volatile_u4(s0), b0 = ld_volatile_u4(s0 + 1);
+    const uint4 a1 = ld_volatile_u4(s1), b1 = ld_volatile_u4(s1 + 1);
+    float4 v0, v1;
+    if (!ll_unpack(a0, b0, tag, &v0)) v0 = ll_wait_f4(s0, tag, err, one_word);
+    if (!ll_unpack(a1, b1, tag, &v1)) v1 = ll_wait_f4(s1, tag, err, one_word);
+    acc = f4_add(acc, v0);
+    acc = f4_add(acc, v1);
+    i += 2 * Q;
+  }
+  for (; i < nsrc; i += Q) acc = f4_add(acc, ll_wait_f4(base + (int64_t)i * stride, tag, err, one_word));
+  return acc;
+}
+
 template <int kThreads>
 __device__ __forceinline__ void grid_barrier(unsigned int* ctr, unsigned int target, int ctid,
                                              unsigned int* err) {
@@ -430,9 +523,19 @@ struct EpochSmem {
 //          output, no profiling: every run-time switch below folds to a constant.  The latency-
 //          bound shapes (config 2) execute a few hundred instructions per step per warp exactly
 //          once, so the size of the loop body (instruction-cache misses) is part of the step time.
-template <int KC, int U, int NW, bool WIDE = false, bool NARROW8 = false, bool LEAN = false>
+//   CLT:  CLUSTER step tail (reduce_mode 5).  The grid is a set of thread-block clusters; a step's
+//          gradient is (1) reduce-scattered inside every cluster through distributed shared memory
+//          (st.async, bytes counted on the receiver's mbarrier: CTA j ends up with the cluster's sum
+//          of ITS column slice), (2) exchanged between the clusters of this GPU and of all GPUs as
+//          tagged words -- one store-then-poll hop through L2 / NVLink, every cluster gathering the
+//          same sums in the same order --, (3) applied (w = a*(g/B) + w) by the slice owner and
+//          (4) all-gathered inside the cluster, again through distributed shared memory.  One L2
+//          hop per step instead of two, <= 18 sources per poll instead of 128-148, and no CTA ever
+//          polls for the weights.
+template <int KC, int U, int NW, bool WIDE = false, bool NARROW8 = false, bool LEAN = false, bool CLT = false>
 __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1)
     sgd_epoch_kernel(const __grid_constant__ EpochParams p) {
+  static_assert(!(CLT && LEAN), "the cluster tail keeps its run-time switches");
   static_assert(!NARROW8 || (KC == 1 && U == 4 && !WIDE), "NARROW8 is the <1,4,NW> row mapping");
   // run-time switches, constant-folded in the LEAN instantiations
   StepCtl* const o_ctl = LEAN ? nullptr : p.ctl;
@@ -450,7 +553,9 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1)
   uint64_t* empty_bar = full_bar + kMaxTiles;
   float4* w_s = reinterpret_cast<float4*>(smem_raw + EpochSmem<KC, NW, WIDE>::kBarBytes);
   float4* gred = w_s + (WIDE ? 32 * NW * KC : 32 * KC);  // WIDE: float r_s[2][32] lives here instead
-  unsigned char* ring = smem_raw + EpochSmem<KC, NW, WIDE>::kFixed;
+  // CLT: [kFixed, kFixed + cl_extra) holds the exchange barriers and buffers (see the step tail)
+  unsigned char* const cl_base = smem_raw + EpochSmem<KC, NW, WIDE>::kFixed;
+  unsigned char* ring = cl_base + (CLT ? p.cl_extra : 0u);
   __shared__ float4 xred[NW];  // cross-warp scratch of ll_gather
   __shared__ volatile int steps_done;  // experiment switch (prefetch_steps): consumer progress
 
@@ -466,8 +571,7 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1)
   static_assert(TRc <= 128, "a gather4 round is one warp instruction: at most 4 * 32 rows per tile");
   constexpr int IH = WIDE ? 1 : (TRc + 31) / 32;  // permutation indices a producer lane holds per round
   const int TR = WIDE ? p.tile_rows : TRc;
-  const int ntiles = p.ntiles;
-  const uint32_t tile_mask = (uint32_t)ntiles - 1u;
+  const int ntiles = p.ntiles;  // any number >= 2 (and >= the producer warps): tiles are walked, not masked
   const uint32_t tile_bytes = (uint32_t)TR * p.slot_bytes;
   const uint32_t full0 = smem_u32(full_bar);
   const uint32_t empty0 = smem_u32(empty_bar);
@@ -494,12 +598,17 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1)
       mbar_init(full0 + 8u * i, 1);    // the producer's arrive.expect_tx; the rows complete the bytes
       mbar_init(empty0 + 8u * i, NW);  // every consumer warp releases every tile once
     }
+    if constexpr (CLT) {  // reduce-scatter and weight all-gather barriers, double-buffered by step parity
+      const uint32_t cb = smem_u32(cl_base);
+      for (int i = 0; i < 4; ++i) mbar_init(cb + 8u * i, 1);
+    }
     fence_barrier_init();
   }
   // weights -> shared (zero beyond C so that the label / pad columns never contribute)
   for (int c = tid; c < (WIDE ? 128 * NW * KC : 128 * KC); c += kThreads)
     reinterpret_cast<float*>(w_s)[c] = (c < p.C) ? p.w[c] : 0.0f;
   __syncthreads();
+  if constexpr (CLT) cluster_sync_unaligned();  // every CTA's barriers exist before anybody sends
 
   auto step_begin = [&](int s) -> int64_t {
     const int64_t sa = (int64_t)first_step + s;
@@ -580,12 +689,26 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1)
       }
     };
     load_indices();
+    // ring position of my current round: round q lives in tile q % ntiles, use q / ntiles (NP <= ntiles)
+    uint32_t ptile = (uint32_t)warp, puse = 0, pseq = (uint32_t)warp;
+    const uint32_t infl = (uint32_t)p.inflight_tiles;
+    // Flow control of one round (lane 0): the tile is free again, and at most `infl` tiles are in
+    // flight.  Every byte requested from HBM queues in front of the step tail's small L2 polls: with
+    // the whole ring (~200 KB per SM, ~30 MB per GPU) outstanding a poll waits ~4.5 us behind the row
+    // stream; ~48-64 KB per SM keep HBM busy (bandwidth x latency ~ 6 MB) and the queues short.
+    auto acquire_tile = [&](uint32_t tile, uint32_t use, uint32_t seq) {
+      mbar_wait_relaxed(empty0 + 8u * tile, (use & 1u) ^ 1u);  // passes at once on the first use
+      if (infl > 0u && seq >= infl) {                          // round seq - infl has landed
+        uint32_t t = tile + (uint32_t)ntiles - infl, u = use - 1u;
+        if (t >= (uint32_t)ntiles) { t -= (uint32_t)ntiles; u += 1u; }
+        mbar_wait_relaxed(full0 + 8u * t, u & 1u);
+      }
+    };
     while (cnt > 0) {
       const int cur_cnt = cnt;
       int32_t cur_idx[IH];
 #pragma unroll
       for (int h = 0; h < IH; ++h) cur_idx[h] = idx[h];
-      const uint32_t cur_tq = tq;
       const int cur_s = s;
       // move to my next round and get its indices in flight
       for (int k = 0; k < NP; ++k) advance();
@@ -597,15 +720,17 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1)
         }
       }
       // issue the current round: wait for the tile, arm its barrier, one TMA bulk copy per row
-      const uint32_t tile = cur_tq & tile_mask;
-      const uint32_t use = cur_tq >> p.tile_log2;
+      const uint32_t tile = ptile, use = puse, seq = pseq;
+      ptile += (uint32_t)NP;
+      pseq += (uint32_t)NP;
+      if (ptile >= (uint32_t)ntiles) { ptile -= (uint32_t)ntiles; ++puse; }
       const uint32_t fb = full0 + 8u * tile;
       if (o_use_gather4) {
         // narrow rows: one tile::gather4 per four rows (lane l takes rows 4l..4l+3 of the round; a
         // short last group repeats its first row into slots that nobody reads)
         const int groups = (cur_cnt + 3) >> 2;
         if (lane == 0) {
-          mbar_wait_relaxed(empty0 + 8u * tile, (use & 1u) ^ 1u);
+          acquire_tile(tile, use, seq);
           mbar_arrive_expect_tx(fb, (uint32_t)groups * 4u * p.slot_bytes);
         }
         const int b4 = (lane << 2) & 31;
@@ -625,7 +750,7 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1)
           tma_gather4_g2s(ring0 + tile * tile_bytes + (uint32_t)(4 * lane) * p.slot_bytes, &p.rec_map, r0, r1, r2, r3, fb);
       } else {
         if (lane == 0) {
-          mbar_wait_relaxed(empty0 + 8u * tile, (use & 1u) ^ 1u);  // passes at once on the first use
+          acquire_tile(tile, use, seq);
           mbar_arrive_expect_tx(fb, (uint32_t)cur_cnt * p.slot_bytes);
         }
         __syncwarp();
@@ -637,6 +762,7 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1)
       }
       __syncwarp();
     }
+    if constexpr (CLT) cluster_sync_unaligned();  // nobody leaves while a peer may still write into its shared memory
     return;
   }
 
@@ -648,6 +774,7 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1)
   const int C4 = p.C4;
   unsigned int bar_count = 0;  // grid barriers passed so far
   uint32_t tqbase = 0;         // sequence number of the first round of the current step
+  uint32_t ctile = 0, cuse = 0;  // ring tile and use count of the next round to consume
   float4 g[KC];
   // running training loss of the epoch (extension; the reference's squared_errors kernel,
   // sgd_thrust.cu:56-74, is dead code): every residual is already in a register
@@ -733,8 +860,8 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1)
       const int ntw = (n32w + TR - 1) / TR;
       for (int ti = 0; ti < ntw; ++ti) {
         const uint32_t tq = tqbase + (uint32_t)ti;
-        const uint32_t tile = tq & tile_mask;
-        const uint32_t use = tq >> p.tile_log2;
+        const uint32_t tile = ctile, use = cuse;
+        if (++ctile == (uint32_t)ntiles) { ctile = 0; ++cuse; }
         const int cnt = (n32w - ti * TR) < TR ? (n32w - ti * TR) : TR;
         const unsigned char* tbase = ring + (size_t)tile * tile_bytes;
         float* rbuf = r_s + (tq & 1u) * 32;
@@ -797,9 +924,8 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1)
       const int n32 = (int)n;
       const int nt = (n32 + TR - 1) / TR;
       for (int ti = 0; ti < nt; ++ti) {
-        const uint32_t tq = tqbase + (uint32_t)ti;
-        const uint32_t tile = tq & tile_mask;
-        const uint32_t use = tq >> p.tile_log2;
+        const uint32_t tile = ctile, use = cuse;
+        if (++ctile == (uint32_t)ntiles) { ctile = 0; ++cuse; }
         const int cnt = (n32 - ti * TR) < TR ? (n32 - ti * TR) : TR;
         const int r = cw * 4 + rg;  // my row of the tile
         const bool live = r < cnt;
@@ -857,9 +983,8 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1)
       const int n32 = (int)n;  // rows of one CTA in one step always fit 32 bits
       const int nt = (n32 + TR - 1) / TR;
       for (int ti = 0; ti < nt; ++ti) {
-        const uint32_t tq = tqbase + (uint32_t)ti;
-        const uint32_t tile = tq & tile_mask;
-        const uint32_t use = tq >> p.tile_log2;
+        const uint32_t tile = ctile, use = cuse;
+        if (++ctile == (uint32_t)ntiles) { ctile = 0; ++cuse; }
         const int cnt = (n32 - ti * TR) < TR ? (n32 - ti * TR) : TR;
         const unsigned char* tbase = ring + (size_t)tile * tile_bytes;
         float4 x[U][KC];
@@ -949,6 +1074,84 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1)
         return acc;
       }
     };
+    if constexpr (CLT) {
+      // ================= CLUSTER: reduce-scatter in distributed shared memory, ONE tagged hop between
+      // the clusters of all GPUs, update by the slice owner, all-gather in distributed shared memory
+      const int cs = p.cl_cs, SL = p.cl_slice;
+      const int crank = (int)cluster_ctarank();
+      const int TG = o_nranks * p.cl_ng;           // clusters that take part in a step, all GPUs
+      const int me = p.rank * p.cl_ng + cta / cs;  // mine
+      const int myf0 = crank * SL;                 // my slice of the float4 columns: [myf0, myf0 + mynf)
+      const int mynf = max(0, min(SL, C4 - myf0));
+      const int parc = s & 1;                              // buffers and barriers alternate by step
+      const uint32_t ph = (uint32_t)(s >> 1) & 1u;         // phase parity of this step's barrier pair
+      const uint32_t cb = smem_u32(cl_base);
+      const uint32_t rsbar = cb + 8u * (uint32_t)parc, wbbar = cb + 16u + 8u * (uint32_t)parc;
+      float4* rsbuf = reinterpret_cast<float4*>(cl_base + 128);  // [2][cs][SL] partials of my slice, by source CTA
+      float4* xpart = rsbuf + 2 * cs * SL;                       // [kCT] partial sums over the clusters
+      const uint32_t tag = tag_base + (uint32_t)s + 1u;
+      // Arm this step's two phases: my slice from every CTA of the cluster; every slice of the new
+      // weights.  (Bytes that arrive before the arming just run the transaction count negative.  The
+      // previous phase of these barriers, step s-2, is over in every local thread: this thread has
+      // the weights of step s-1, which needed the step s-1 partial of every thread of this CTA.)
+      if (ctid == kCT - 1) {
+        mbar_arrive_expect_tx(rsbar, (uint32_t)(cs * mynf) * 16u);
+        mbar_arrive_expect_tx(wbbar, (uint32_t)C4 * 16u);
+      }
+      {  // (1) reduce-scatter: column f of my partial goes to its owner, slot [parity][me][f - owner's first]
+        const uint32_t slot0 = smem_u32(rsbuf + (size_t)(parc * cs + crank) * SL);
+        for (int f = ctid; f < C4; f += kCT) {
+          const int j = f / SL;
+          st_async_f4(map_to_cta(slot0 + (uint32_t)(f - j * SL) * 16u, (uint32_t)j), cta_partial(f),
+                      map_to_cta(rsbar, (uint32_t)j));
+        }
+      }
+      mark(2);  // partial sent
+      mbar_wait_guarded(rsbar, ph, p.err);
+      mark(3);  // the cluster's partials of my slice have arrived
+      for (int cb0 = 0; cb0 < SL; cb0 += kCT) {  // (one pass unless a slice has more than kCT float4 columns)
+        const int ncol = min(kCT, SL - cb0);
+        const int Qn = kCT / ncol;                // threads per column
+        const int cl = ctid % ncol, q = ctid / ncol;
+        const int col = cb0 + cl;
+        const bool active = q < Qn && col < mynf;
+        const int f = myf0 + col;
+        const int Qe = TG > 1 ? min(Qn, TG) : 1;  // of which poll sources
+        float4 w_old = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (active) w_old = w_s[f];               // before anybody can send the new one
+        if (active && q == 0) {  // (2) the cluster's sum of column f, sources in CTA order
+          const float4* src = rsbuf + (size_t)parc * cs * SL + col;
+          float4 tot = src[0];
+          for (int k = 1; k < cs; ++k) tot = f4_add(tot, src[(size_t)k * SL]);
+          if (TG > 1) {  // to slot [parity][me] of every rank's inbox: L2 on this GPU, NVLink to the peers
+            const int64_t at = (((int64_t)parc * TG + me) * C4p + f) * 2;
+            for (int r = 0; r < o_nranks; ++r) ll_store_f4(p.cl_inbox_peer[r] + at, tot, tag);
+          } else {
+            xpart[cl] = tot;
+          }
+        }
+        if (TG > 1 && active && q < Qe) {  // (3) thread q adds clusters q, q + Qe, ... (all GPUs), fixed order
+          const uint4* base = p.cl_inbox_local + (((int64_t)parc * TG) * C4p + f) * 2;
+          xpart[q * ncol + cl] = cl_gather(base, (int64_t)C4p * 2, TG, q, Qe, tag, p.err, poll_one_word);
+        }
+        consumer_bar<kCT>();
+        mark(4);  // all clusters' sums gathered
+        if (active) {  // (4) update, then the new weights of column f into every CTA of the cluster
+          float4 tot = xpart[cl];
+          for (int k = 1; k < Qe; ++k) tot = f4_add(tot, xpart[k * ncol + cl]);
+          float4 gs;
+          const float4 wv = updated(f, w_old, tot, &gs);
+          const uint32_t waddr = smem_u32(w_s + f);
+          for (int dst = q; dst < cs; dst += Qn) st_async_f4(map_to_cta(waddr, (uint32_t)dst), wv, map_to_cta(wbbar, (uint32_t)dst));
+          if (q == 0 && cta < cs) reinterpret_cast<float4*>(p.g_last)[f] = gs;
+        }
+        if (cb0 + kCT < SL) consumer_bar<kCT>();  // xpart is reused by the next pass
+      }
+      mark(5);  // my slice published
+      mbar_wait_guarded(wbbar, ph, p.err);
+      mark(6);  // new weights complete in my shared memory
+      continue;
+    }
     if (G == 1 && o_nranks == 1) {
       // single CTA (tiny batches): the CTA partial is the gradient; nothing leaves the SM
       for (int f = ctid; f < C4; f += kCT) {
@@ -1120,6 +1323,7 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1)
       o_ctl->tag_base = tag_base + (uint32_t)p.nb;
     }
   }
+  if constexpr (CLT) cluster_sync_unaligned();  // nobody leaves while a peer may still write into its shared memory
 }
 
 // ------------------------------------------------------------------------------------------------

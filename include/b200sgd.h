@@ -58,7 +58,10 @@ typedef enum {
   SGD_REDUCE_ALLGATHER = 1, /* every CTA sums all partials itself: 1 grid barrier, G^2*C traffic */
   SGD_REDUCE_SCATTER = 2,   /* column-sliced reduce + broadcast: 2 grid barriers, 2*G*C traffic  */
   SGD_REDUCE_DATAFLOW = 3,  /* column-sliced, tagged words instead of barriers: 2 one-way hops   */
-  SGD_REDUCE_DATAFLOW_1HOP = 4 /* every CTA gathers all tagged partials itself: 1 hop, small grids */
+  SGD_REDUCE_DATAFLOW_1HOP = 4, /* every CTA gathers all tagged partials itself: 1 hop, small grids */
+  SGD_REDUCE_CLUSTER = 5    /* reduce-scatter and all-gather inside thread-block clusters (distributed
+                               shared memory), one tagged hop between clusters / GPUs: what AUTO picks
+                               for everything the cluster kernel does not take                        */
 } sgd_reduce;
 
 typedef struct sgd_config {

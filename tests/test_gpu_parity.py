@@ -249,6 +249,53 @@ def test_cluster_kernel_is_not_used_where_it_does_not_apply():
         assert eng.kernel_shape[0] != 0
 
 
+# ------------------------------------------------------------------ the cluster step tail of the generic kernel
+@pytest.mark.parametrize("R,C,B,cs,clusters", [
+    (6000, 512, 2048, 8, 0),      # BASELINE config 5 row width: 16 float4 columns per CTA slice
+    (3000, 2048, 600, 8, 0),      # config 4 row width, ~5 rows per CTA and step
+    (3000, 2048, 600, 16, 0),     # 16 CTAs per cluster (non-portable size)
+    (4000, 300, 1000, 4, 3),      # three clusters of four
+    (4000, 300, 1000, 2, 5),      # pairs
+    (5000, 129, 777, 8, 2),       # 33 float4 columns: ragged slices (5 per CTA, the last CTA gets none... 33 = 6*5 + 3)
+    (9000, 100, 4500, 8, 4),      # narrow rows (8 lanes per row) beyond the cluster kernel's reach
+    (1200, 5000, 100, 8, 0),      # column mapping (C > 2048)
+    (600, 8192, 33, 4, 2),        # slices of 512 float4 columns: two passes of 256 threads
+    (2000, 1000, 2000, 8, 1),     # ONE cluster: nothing goes through L2
+])
+def test_cluster_tail_shapes(R, C, B, cs, clusters, monkeypatch):
+    monkeypatch.setenv("B200SGD_CLUSTER", "0")     # keep narrow rows off sgd_cluster_epoch_kernel
+    monkeypatch.setenv("B200SGD_CLT", str(cs))
+    if clusters:
+        monkeypatch.setenv("B200SGD_CLUSTERS", str(clusters))
+    X, y, _ = make_regression(R, C, seed=R + C + B)
+    grid = clusters * cs if clusters else 0
+    with pkg.SGDEngine(R, C, B, 0.01, grid=grid) as probe:
+        assert probe.reduce == _lib.SGD_REDUCE_CLUSTER and probe.grid % cs == 0, (probe.reduce, probe.grid)
+        if clusters:
+            assert probe.grid == clusters * cs
+    check_run(X, y, B, 0.01, 3, grid=grid)
+
+
+def test_cluster_tail_agrees_with_the_dataflow_reduction(monkeypatch):
+    X, y, _ = make_regression(8000, 512, seed=3)
+    w_c, mae_c = check_run(X, y, 2000, 0.02, 3)
+    with pkg.SGDEngine(8000, 512, 2000, 0.02) as probe:
+        assert probe.reduce == _lib.SGD_REDUCE_CLUSTER
+    w_d, mae_d = check_run(X, y, 2000, 0.02, 3, reduce=_lib.SGD_REDUCE_DATAFLOW)
+    assert rel_l2(w_c, w_d) < 1e-5
+
+
+@pytest.mark.parametrize("kb", [0, 16, 48, 1000])
+def test_producers_in_flight_cap(kb, monkeypatch):
+    # the cap only changes WHEN rows are requested, never the result
+    monkeypatch.setenv("B200SGD_INFLIGHT_KB", str(kb))
+    X, y, _ = make_regression(6000, 512, seed=8)
+    w, _ = check_run(X, y, 3000, 0.02, 2)
+    monkeypatch.setenv("B200SGD_INFLIGHT_KB", "64")
+    w2, _ = check_run(X, y, 3000, 0.02, 2)
+    assert np.array_equal(w, w2)
+
+
 def test_graph_engine_many_steps_reuses_graph():
     X, y, _ = make_regression(9000, 20, seed=4)
     check_run(X, y, 10, 0.005, 2, engine=_lib.SGD_ENGINE_GRAPH)   # 900 steps > one graph chunk
