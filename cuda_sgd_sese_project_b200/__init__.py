@@ -10,7 +10,7 @@ torchrun launcher.  Importing it never triggers a CPU fallback: if the library i
 from . import _lib
 from ._lib import SgdError
 from .engine import (SGDEngine, batch_geometry, device_count, get_filename_from_path, host_bucket,
-                     host_shuffle, init_weights, read_csv, shard_range, write_experiment_output)
+                     host_shuffle, init_weights, read_csv, shard_range, write_csv, write_experiment_output)
 
 __all__ = ["SGDEngine", "SgdError", "batch_geometry", "device_count", "get_filename_from_path",
-           "host_bucket", "host_shuffle", "init_weights", "read_csv", "shard_range", "write_experiment_output", "_lib"]
+           "host_bucket", "host_shuffle", "init_weights", "read_csv", "shard_range", "write_csv", "write_experiment_output", "_lib"]

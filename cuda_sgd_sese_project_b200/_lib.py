@@ -23,7 +23,7 @@ SGD_PEER_HANDLE_BYTES = 128
 
 # every symbol include/b200sgd.h declares (tests/test_abi.py checks the header against this list)
 EXPORTS = [
-    "sgd_abi_version", "sgd_last_error", "sgd_device_count", "sgd_read_csv",
+    "sgd_abi_version", "sgd_last_error", "sgd_device_count", "sgd_read_csv", "sgd_write_csv",
     "sgd_get_filename_from_path", "sgd_write_experiment_output", "sgd_init_weights",
     "sgd_batch_geometry", "sgd_host_shuffle", "sgd_shard_range", "sgd_host_bucket", "sgd_get_local_schedule", "sgd_get_loss_curve",
     "sgd_create", "sgd_destroy", "sgd_load_rows",
@@ -81,6 +81,7 @@ def load() -> C.CDLL:
         "sgd_last_error": ([], C.c_char_p),
         "sgd_device_count": ([], C.c_int),
         "sgd_read_csv": ([C.c_char_p, i64, i32, vp, vp], C.c_int),
+        "sgd_write_csv": ([C.c_char_p, i64, i32, vp, vp], C.c_int),
         "sgd_get_filename_from_path": ([C.c_char_p, C.c_char_p, C.c_size_t], C.c_int),
         "sgd_write_experiment_output": ([C.c_char_p, f32, f32, f32, f32, f32], C.c_int),
         "sgd_init_weights": ([vp, i32], C.c_int),

@@ -62,23 +62,29 @@ constexpr int kLossSlots = 64;          // epochs whose running loss can be in f
 
 struct KernelChoice {
   int KC = 0, U = 0, NW = 0;
+  int cw = 0;  // COLSPLIT: consumer warps along the columns (0: row / column / narrow mapping)
+  int npmax = b200sgd::kMaxProducerWarps;  // producer warps the variant is compiled for
   bool wide = false, narrow8 = false;
   const void* fn = nullptr;
   const void* fn_lean = nullptr;  // same mapping with the run-time switches folded away, or nullptr
   const void* fn_clt = nullptr;   // same mapping with the CLUSTER step tail (launched as thread-block clusters)
   size_t fixed_smem = 0;
+  int tile_rows() const { return cw > 0 ? (NW / cw) * U : NW * U; }
 };
 
-template <int KC, int U, int NW, bool WIDE = false, bool NARROW8 = false, bool WITH_LEAN = false>
+template <int KC, int U, int NW, bool WIDE = false, bool NARROW8 = false, bool WITH_LEAN = false, int CW = 0,
+          int NPMAX = b200sgd::kMaxProducerWarps>
 KernelChoice make_choice() {
   KernelChoice k;
   k.KC = KC; k.U = U; k.NW = NW;
+  k.cw = CW;
+  k.npmax = NPMAX;
   k.wide = WIDE;
   k.narrow8 = NARROW8;
-  k.fn = (const void*)b200sgd::sgd_epoch_kernel<KC, U, NW, WIDE, NARROW8>;
-  if constexpr (WITH_LEAN) k.fn_lean = (const void*)b200sgd::sgd_epoch_kernel<KC, U, NW, WIDE, NARROW8, true>;
-  k.fn_clt = (const void*)b200sgd::sgd_epoch_kernel<KC, U, NW, WIDE, NARROW8, false, true>;
-  k.fixed_smem = b200sgd::EpochSmem<KC, NW, WIDE>::kFixed;
+  k.fn = (const void*)b200sgd::sgd_epoch_kernel<KC, U, NW, WIDE, NARROW8, false, false, CW, NPMAX>;
+  if constexpr (WITH_LEAN) k.fn_lean = (const void*)b200sgd::sgd_epoch_kernel<KC, U, NW, WIDE, NARROW8, true, false, CW, NPMAX>;
+  k.fn_clt = (const void*)b200sgd::sgd_epoch_kernel<KC, U, NW, WIDE, NARROW8, false, true, CW, NPMAX>;
+  k.fixed_smem = b200sgd::EpochSmem<KC, NW, WIDE, U, CW>::kFixed;
   return k;
 }
 
@@ -87,33 +93,39 @@ int variant_env() {  // B200SGD_VARIANT: A/B switch for tuning runs
   return e ? std::atoi(e) : 0;
 }
 
-// Kernel variant by row width (KC) and by how many rows one CTA handles per step: few rows ->
-// fewer consumer warps and no row unrolling, so the latency-critical step tail is not slowed down
-// by warps that only execute control code (the tail is issue-bound).
+// Kernel variant by row width and, for narrow rows, by how many rows one CTA handles per step (few
+// rows -> no row unrolling, so the latency-critical step tail is not slowed down by warps that only
+// execute control code).  Rows of 129 .. 8192 features run the COLSPLIT mapping (sgd_kernels.cuh):
+// CW warps along the columns, KC float4 columns per lane, U rows per warp and tile in registers.
+// B200SGD_VARIANT=3 / 9 select the round-1 column / row mappings where they exist (A/B runs).
 bool choose_kernel(int C4, int64_t rows_per_cta, KernelChoice* out) {
-  // a ring tile holds NW*U <= 32 rows (one producer round)
+  const int v = variant_env();
   if (C4 <= 32) {
     if (rows_per_cta <= 8) *out = make_choice<1, 1, 8>();
     else if (rows_per_cta <= 16) *out = make_choice<1, 2, 8>();
     else *out = make_choice<1, 4, 8, false, true, true>();  // 8 lanes per row, 4 rows per warp
   } else if (C4 <= 64) {
-    if (rows_per_cta <= 8) *out = make_choice<2, 1, 8>();
-    else if (rows_per_cta <= 16) *out = make_choice<2, 2, 8>();
-    else *out = make_choice<2, 2, 16>();
+    if (v == 8) *out = make_choice<1, 8, 8, false, false, false, 2>();   // COLSPLIT 2 x 4 warps (A/B)
+    else *out = make_choice<2, 4, 8>();                                  // rows: 4 per warp in flight, tiles of 32
   } else if (C4 <= 128) {
-    if (rows_per_cta <= 8) *out = make_choice<4, 1, 8>();
-    else *out = make_choice<4, 2, 8>();
+    if (v == 8) *out = make_choice<1, 8, 8, false, false, false, 4>();   // COLSPLIT 4 x 2 warps, tiles of 16 rows (A/B)
+    else if (v == 7) *out = make_choice<4, 1, 8>();                      // tiles of 8 rows (A/B)
+    else *out = make_choice<4, 2, 8>();                                  // rows: 2 per warp in flight, tiles of 16
   } else if (C4 <= 256) {
-    *out = make_choice<8, 1, 8>();
+    if (v == 8) *out = make_choice<1, 8, 8, false, false, false, 8>();   // COLSPLIT 8 x 1 warps (A/B)
+    else *out = make_choice<8, 1, 8>();                                  // tiles of 8 rows
   } else if (C4 <= 512) {
-    if (variant_env() == 3) *out = make_choice<2, 1, 8, true>();  // column mapping, A/B
-    else *out = make_choice<16, 1, 8>();
+    if (v == 3) *out = make_choice<2, 1, 8, true>();                     // round-1 column mapping (A/B)
+    else if (v == 7) *out = make_choice<2, 4, 8, false, false, false, 8>();  // COLSPLIT, tiles of 4 rows (A/B)
+    else *out = make_choice<2, 8, 8, false, false, false, 8>();          // COLSPLIT, tiles of 8 rows
   } else if (C4 <= 1024) {
-    *out = make_choice<4, 1, 8, true>();   // column mapping: C <= 4096
+    if (v == 3) *out = make_choice<4, 1, 8, true>();
+    else *out = make_choice<4, 2, 8, false, false, false, 8>();          // tiles of 2 rows
   } else if (C4 <= 2048) {
-    *out = make_choice<8, 1, 8, true>();   // C <= 8192
+    if (v == 3) *out = make_choice<8, 1, 8, true>();
+    else *out = make_choice<8, 1, 8, false, false, false, 8>();          // one row per tile
   } else if (C4 <= 4096) {
-    *out = make_choice<16, 1, 8, true>();  // C <= 16384
+    *out = make_choice<16, 1, 8, true>();  // column mapping: C <= 16384
   } else {
     return false;
   }
@@ -228,10 +240,17 @@ int bind(const sgd_ctx* c) {
   return SGD_OK;
 }
 
-// main.cu:343-344
+// main.cu:343-344: num_batches = (int)floor(R / (float)B).  The float division rounds up for some
+// R > 2^24 (R = 99,999,999, B = 1000 gives 100,000 batches = R + 1 rows), where the reference reads
+// past its index vector; the integer quotient is the same value wherever the reference is well
+// defined, so the result is clamped to it.
 void batch_geometry(int64_t R, int32_t batch_arg, int32_t* B, int32_t* nb) {
   *B = batch_arg == 0 ? (int32_t)R : batch_arg;
-  *nb = (*B > 0) ? (int32_t)std::floor((float)R / (float)(*B)) : 0;
+  *nb = 0;
+  if (*B > 0) {
+    const int64_t f = (int64_t)std::floor((float)R / (float)(*B));
+    *nb = (int32_t)std::min<int64_t>(f, R / *B);
+  }
 }
 
 void free_all(sgd_ctx* c) {
@@ -337,8 +356,8 @@ int configure_launch(sgd_ctx* c) {
     if (slot_bytes <= 1024) np = rows_cta >= 64 ? 4 : 2;
     else if (slot_bytes <= 4096) np = rows_cta >= 32 ? 2 : 1;
     if (const char* e = std::getenv("B200SGD_PRODUCER_WARPS")) np = std::atoi(e);
-    c->nprod = std::max(1, std::min(np, b200sgd::kMaxProducerWarps));
-    int tile_rows = c->kc.NW * c->kc.U;
+    c->nprod = std::max(1, std::min(np, c->kc.npmax));
+    int tile_rows = c->kc.tile_rows();
     const size_t avail = kMaxDynSmem - c->kc.fixed_smem - extra;
     if (c->kc.wide) {
       // column mapping: as many rows per tile as two tiles allow (<= 32, a multiple of NW if possible)
@@ -355,9 +374,9 @@ int configure_launch(sgd_ctx* c) {
     c->ntiles = ntiles;
     c->tile_log2 = 0;
     c->smem_bytes = c->kc.fixed_smem + extra + (size_t)ntiles * tile_bytes;
-    // Bytes in flight per CTA (DESIGN.md "loaded latency"): requests beyond bandwidth x latency only
-    // lengthen the queue the step tail's polls wait in.  Default 64 KB per SM (~9 MB per GPU).
-    int64_t kb = 64;
+    // Experiment switch: cap the bytes in flight per CTA.  Measured (profiles/r2_tail_matrix.md): no
+    // effect on the step tail down to 64 KB per SM, bandwidth lost below that -> off by default.
+    int64_t kb = 0;
     if (const char* e = std::getenv("B200SGD_INFLIGHT_KB")) kb = std::atoll(e);
     int infl = kb > 0 ? (int)std::max<int64_t>(1, (kb * 1024 + (int64_t)tile_bytes / 2) / (int64_t)tile_bytes) : 0;
     if (infl >= ntiles) infl = 0;  // the ring itself is the bound
@@ -369,7 +388,12 @@ int configure_launch(sgd_ctx* c) {
   c->clt = false;
   if (c->cluster_cs == 0 && c->cfg.engine != SGD_ENGINE_GRAPH &&
       (c->cfg.reduce == SGD_REDUCE_AUTO || c->cfg.reduce == SGD_REDUCE_CLUSTER)) {
-    int cs = 8;
+    // CTAs per cluster: 16 (7 clusters = 112 SMs on a B200) while the step tail matters -- fewer clusters
+    // meet in L2: C = 2048, B = 4096: 8.9 us per step against 9.9 with 8 --, 8 (15 clusters = 120 SMs)
+    // once a step streams >= 64 MB and the number of SMs counts (C = 512, B = 65536: 0.82 vs 0.79 of peak)
+    int cs = rows_step * c->ld * 4 >= (64ll << 20) ? 8 : 16;
+    if (cs == 16 && c->cfg.grid <= 0 && grid < 32) cs = 8;  // small grids: two clusters of 8 rather than none
+    if (c->cfg.grid > 0 && c->cfg.grid % 16 != 0) cs = 8;
     if (const char* e = std::getenv("B200SGD_CLT")) cs = std::atoi(e);  // 0 = off; 2, 4, 8, 16 = CTAs per cluster
     const bool cs_ok = cs == 2 || cs == 4 || cs == 8 || cs == 16;
     const bool grid_ok = c->cfg.grid <= 0 ? grid >= 2 * cs : (c->cfg.grid % cs == 0);
@@ -446,6 +470,7 @@ int configure_launch(sgd_ctx* c) {
 int configure_cluster(sgd_ctx* c) {
   if (c->cluster_cs == 0) return SGD_OK;
   const int cs = c->cluster_cs;
+  const int grid0 = c->grid;  // what the generic kernel's buffers and geometry were derived for
   c->cluster_cs = 0;
   if (!c->have_rec_map) return SGD_OK;
   const size_t tile_bytes = (size_t)b200sgd::kClTileRows * c->ld * 4;
@@ -495,12 +520,16 @@ int configure_cluster(sgd_ctx* c) {
     // every cluster of the launch must be resident at once: they wait for one another's sums
     if (cudaOccupancyMaxActiveClusters(&nclusters, fn, &lc) != cudaSuccess || nclusters < 1) {
       cudaGetLastError();
+      c->grid = grid0;  // generic kernel with the geometry configure_launch derived
       return SGD_OK;
     }
     if (std::getenv("B200SGD_DEBUG"))
       std::fprintf(stderr, "[b200sgd] cluster size %d: at most %d clusters resident, %d wanted\n", cs, nclusters, c->cluster_ng);
     if (nclusters >= c->cluster_ng) break;
-    if (c->cfg.grid > 0) return SGD_OK;  // an explicit grid that does not fit: generic kernel
+    if (c->cfg.grid > 0) {  // an explicit grid that does not fit: generic kernel
+      c->grid = grid0;
+      return SGD_OK;
+    }
     c->cluster_ng = nclusters;           // as many as fit (a B200 keeps 7 clusters of 16 CTAs, 15 of 8)
     c->grid = cs * c->cluster_ng;
   }
@@ -538,7 +567,7 @@ int make_record_tensor_map(sgd_ctx* c) {
                                      CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   c->have_rec_map = (r == CUDA_SUCCESS);
   // the generic kernel issues gather4 when its ring tile is a whole number of four-row groups
-  c->use_gather4 = c->have_rec_map && (c->kc.NW * c->kc.U) % 4 == 0 && !c->kc.wide;
+  c->use_gather4 = c->have_rec_map && c->kc.tile_rows() % 4 == 0 && !c->kc.wide;
   return SGD_OK;
 }
 
@@ -583,6 +612,7 @@ void fill_params(sgd_ctx* c, b200sgd::EpochParams* p, int32_t epoch, int buf) {
   p->ctl = nullptr;
   p->dbg = c->d_dbg;
   p->inflight_tiles = c->inflight_tiles;
+  if (const char* e = std::getenv("B200SGD_DBGSKIP")) p->dbg_skip = std::atoi(e);
   if (c->clt) {
     p->cl_cs = c->clt_cs;
     p->cl_ng = c->clt_ng;
@@ -899,6 +929,12 @@ int sgd_read_csv(const char* path, int64_t rows, int32_t cols, float* X, float* 
   return SGD_OK;
 }
 
+int sgd_write_csv(const char* path, int64_t rows, int32_t cols, const float* X, const float* y) {
+  if (!path || !X || !y || rows < 0 || cols < 0) return fail(SGD_ERR_ARG, "sgd_write_csv: bad argument");
+  if (b200sgd::write_csv(path, rows, cols, X, y) != 0) return fail(SGD_ERR_IO, std::string("cannot write ") + path);
+  return SGD_OK;
+}
+
 int sgd_get_filename_from_path(const char* path, char* out, size_t out_cap) {
   if (!path || !out || out_cap == 0) return fail(SGD_ERR_ARG, "sgd_get_filename_from_path: bad argument");
   const std::string s = b200sgd::filename_from_path(path);
@@ -984,7 +1020,7 @@ int sgd_create(const sgd_config* cfg, const float* X, const float* y, sgd_ctx** 
   *out = nullptr;
   if (cfg->rows <= 0 || cfg->rows > 2147483647ll) return fail(SGD_ERR_ARG, "rows must be in [1, 2^31-1]");
   if (cfg->cols <= 0) return fail(SGD_ERR_ARG, "cols must be positive");
-  if (cfg->batch < 0 || cfg->batch > cfg->rows) return fail(SGD_ERR_ARG, "batch must be in [0, rows]");
+  if (cfg->batch < 0) return fail(SGD_ERR_ARG, "batch must not be negative");  // batch > rows: 0 steps, as main.cu:344
   if (cfg->nranks < 1 || cfg->nranks > 8 || cfg->rank < 0 || cfg->rank >= cfg->nranks)
     return fail(SGD_ERR_ARG, "need 1 <= nranks <= 8 and 0 <= rank < nranks");
   if ((X == nullptr) != (y == nullptr)) return fail(SGD_ERR_ARG, "X and y must both be given or both be NULL");
@@ -1044,6 +1080,11 @@ int sgd_create(const sgd_config* cfg, const float* X, const float* y, sgd_ctx** 
       CUDA_TRY(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
     }
     CUDA_TRY(cudaEventCreateWithFlags(&c->ev_done[2], cudaEventDisableTiming));
+    {  // watchdog of the in-kernel waits (sgd_kernels.cuh, SpinGuard)
+      unsigned long long ns = c->cfg.nranks > 1 ? 30000000000ull : 4000000000ull;
+      if (const char* e = std::getenv("B200SGD_WATCHDOG_MS")) ns = 1000000ull * (unsigned long long)std::max(1ll, std::atoll(e));
+      CUDA_TRY(cudaMemcpyToSymbol(b200sgd::c_spin_timeout_ns, &ns, sizeof(ns)));
+    }
     stamp("streams, events");
     SGD_TRY(configure_launch(c));
     stamp("configure_launch");
@@ -1116,9 +1157,9 @@ int sgd_create(const sgd_config* cfg, const float* X, const float* y, sgd_ctx** 
     }
     stamp("shuffle buffers");
     c->mae_blocks = c->num_sms * 8;
-    if (sizeof(float) * 4 * (size_t)c->C4 > (48u << 10))  // weights in shared memory: opt in above 48 KB
+    if (sizeof(float) * (size_t)c->ld > (48u << 10))  // weights in shared memory: opt in above 48 KB
       CUDA_TRY(cudaFuncSetAttribute((const void*)b200sgd::sgd_mae_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)(sizeof(float) * 4 * (size_t)c->C4)));
+                                    (int)(sizeof(float) * (size_t)c->ld)));
     CUDA_TRY(cudaMalloc(&c->d_mae, sizeof(double) * c->mae_blocks));
     if (c->cfg.nranks > 1) {
       c->xchg_bytes = sizeof(uint4) * 2 * 2 * (size_t)c->cfg.nranks * (((size_t)c->C4 + 3) & ~(size_t)3);
@@ -1299,7 +1340,7 @@ int sgd_get_config(const sgd_ctx* c, sgd_config* out) {
   // KC: negative = column mapping; 0 = cluster kernel (then U = CTAs of the cluster)
   out->reserved[3] = c->cluster_cs > 0 ? 0 : c->kc.wide ? -c->kc.KC : c->kc.KC;
   out->reserved[4] = c->cluster_cs > 0 ? c->cluster_cs : c->kc.narrow8 ? -c->kc.U : c->kc.U;  // negative: 8 lanes per row
-  out->reserved[5] = c->kc.NW;
+  out->reserved[5] = c->kc.NW | (c->kc.cw << 8);  // bits 8..: COLSPLIT warps along the columns
   out->reserved[6] = (int32_t)c->ld;
   return SGD_OK;
 }
@@ -1344,8 +1385,17 @@ int sgd_shuffle(sgd_ctx* c) {
 int sgd_set_permutation(sgd_ctx* c, const int32_t* perm) {
   SGD_TRY(check_ctx(c));
   if (!perm) return fail(SGD_ERR_ARG, "null permutation");
-  for (int64_t i = 0; i < c->R; ++i)
-    if (perm[i] < 0 || perm[i] >= c->R) return fail(SGD_ERR_ARG, "permutation entry out of range");
+  {  // a permutation of 0..R-1: the bucketed row lists of nranks > 1 are sized for exactly that
+    std::vector<uint64_t> seen(((size_t)c->R + 63) / 64, 0);
+    for (int64_t i = 0; i < c->R; ++i) {
+      const int64_t v = perm[i];
+      if (v < 0 || v >= c->R) return fail(SGD_ERR_ARG, "permutation entry out of range");
+      uint64_t& wd = seen[(size_t)v >> 6];
+      const uint64_t bit = 1ull << (v & 63);
+      if (wd & bit) return fail(SGD_ERR_ARG, "not a permutation: row " + std::to_string(v) + " appears twice");
+      wd |= bit;
+    }
+  }
   SGD_TRY(bind(c));
   SGD_TRY(ensure_host_stage(c));
   c->h_ind.resize((size_t)c->R);
@@ -1520,9 +1570,13 @@ int sgd_mean_abs_error(sgd_ctx* c, float* mae_out, double* sum_out) {
   SGD_TRY(bind(c));
   double total = 0.0;
   if (c->local_rows > 0) {
-    const int blocks = (int)std::min<int64_t>(c->mae_blocks, (c->local_rows + 7) / 8);
-    b200sgd::sgd_mae_kernel<<<blocks, 256, sizeof(float) * 4 * c->C4, c->stream>>>(
-        c->d_rec, c->ld, c->C, c->local_rows, c->d_w, c->d_mae);
+    // lanes per row: the power of two that leaves a lane about four float4 of the record
+    int L = 1;
+    while (L < 32 && (int64_t)L * 4 < c->ld / 4) L *= 2;
+    const int64_t rows_per_block = (int64_t)8 * (32 / L) * 2;  // 8 warps, 32/L groups, two rows per pass
+    const int blocks = (int)std::min<int64_t>(c->mae_blocks, (c->local_rows + rows_per_block - 1) / rows_per_block);
+    b200sgd::sgd_mae_kernel<<<blocks, 256, sizeof(float) * (size_t)c->ld, c->stream>>>(
+        c->d_rec, c->ld, c->C, c->local_rows, c->d_w, L, c->d_mae);
     CUDA_TRY(cudaGetLastError());
     std::vector<double> h((size_t)blocks);
     CUDA_TRY(cudaMemcpyAsync(h.data(), c->d_mae, sizeof(double) * blocks, cudaMemcpyDeviceToHost, c->stream));

@@ -11,12 +11,15 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <atomic>
+#include <cerrno>
 #include <charconv>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <string>
 #include <thread>
 #include <vector>
 
@@ -25,23 +28,34 @@ namespace b200sgd {
 namespace {
 
 // One cell -> float with std::stof's semantics (strtof: leading blanks, optional sign, longest
-// valid prefix, trailing junk ignored).  from_chars is the fast path; anything it does not take
-// verbatim goes through strtof so that odd spellings ("+2", " .5", "1e3", "inf") agree with stof.
+// valid prefix, trailing junk ignored).  from_chars is the fast path when it consumes the WHOLE
+// cell; anything else ("+2", " .5", "0x1p3", "inf", "1.5abc") goes through strtof on a NUL-terminated
+// copy of the whole cell, so that the value agrees with stof.  Where stof would throw
+// (std::invalid_argument: no number; std::out_of_range: strtof sets ERANGE) the cell is rejected.
 inline bool parse_cell(const char* b, const char* e, float* out) {
   while (b < e && (*b == ' ' || *b == '\t')) ++b;
   if (b == e) return false;
   if (*b != '+') {
     auto res = std::from_chars(b, e, *out);
-    if (res.ec == std::errc()) return true;
+    if (res.ec == std::errc() && res.ptr == e) return true;
   }
   char tmp[64];
-  size_t n = (size_t)(e - b);
-  if (n >= sizeof(tmp)) n = sizeof(tmp) - 1;
-  std::memcpy(tmp, b, n);
-  tmp[n] = 0;
-  char* end = tmp;
-  float v = std::strtof(tmp, &end);
-  if (end == tmp) return false;  // std::stof would throw std::invalid_argument
+  std::string big;
+  const size_t n = (size_t)(e - b);
+  const char* z;
+  if (n < sizeof(tmp)) {
+    std::memcpy(tmp, b, n);
+    tmp[n] = 0;
+    z = tmp;
+  } else {
+    big.assign(b, n);
+    z = big.c_str();
+  }
+  char* end = nullptr;
+  errno = 0;
+  const float v = std::strtof(z, &end);
+  if (end == z) return false;       // std::stof would throw std::invalid_argument
+  if (errno == ERANGE) return false;  // std::stof would throw std::out_of_range
   *out = v;
   return true;
 }
@@ -142,6 +156,42 @@ int read_csv(const char* path, int64_t R, int32_t C, float* X, float* y, std::st
   if (rc.load() != 0 && err)
     *err = std::string("CSV has more rows/columns than announced or an unparsable cell: ") + path;
   return rc.load();
+}
+
+// The reference's data_set_creation scripts write `f1,...,fC,label` lines with csv.writer; this is the
+// same format with the shortest text that parses back to the same float (std::to_chars), written by
+// all cores: the benchmark's reference arm and the ingestion measurements need GB-size files.
+int write_csv(const char* path, int64_t R, int32_t C, const float* X, const float* y) {
+  FILE* f = std::fopen(path, "wb");
+  if (!f) return -2;
+  unsigned hw = std::thread::hardware_concurrency();
+  const size_t T = hw ? (hw > 32 ? 32 : hw) : 4;
+  const int64_t rows_per_task = std::max<int64_t>(1, (int64_t)(4 << 20) / (12 * ((int64_t)C + 1)));  // ~4 MB of text
+  std::vector<std::string> out(T);
+  int rc = 0;
+  for (int64_t r0 = 0; r0 < R && rc == 0; r0 += rows_per_task * (int64_t)T) {
+    std::vector<std::thread> th;
+    for (size_t k = 0; k < T; ++k)
+      th.emplace_back([&, k] {
+        std::string& s = out[k];
+        s.clear();
+        const int64_t b = r0 + (int64_t)k * rows_per_task, e = std::min(R, b + rows_per_task);
+        char buf[32];
+        for (int64_t r = b; r < e; ++r) {
+          for (int32_t c = 0; c <= C; ++c) {
+            const float v = c < C ? X[r * (int64_t)C + c] : y[r];
+            auto res = std::to_chars(buf, buf + sizeof(buf), v);
+            s.append(buf, (size_t)(res.ptr - buf));
+            s.push_back(c < C ? ',' : '\n');
+          }
+        }
+      });
+    for (auto& t : th) t.join();
+    for (size_t k = 0; k < T; ++k)
+      if (!out[k].empty() && std::fwrite(out[k].data(), 1, out[k].size(), f) != out[k].size()) rc = -2;
+  }
+  if (std::fclose(f) != 0) rc = -2;
+  return rc;
 }
 
 std::string filename_from_path(const std::string& filepath) {

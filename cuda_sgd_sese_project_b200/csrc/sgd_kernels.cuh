@@ -96,6 +96,7 @@ struct EpochParams {
   uint4* cl_inbox_local;    // [2][nranks*cl_ng][C4p][2] tagged slice sums of every cluster of every rank
   uint4* cl_inbox_peer[8];  // the same buffer of every rank (own rank: the local one)
   int32_t inflight_tiles;   // producers keep at most this many ring tiles in flight (0 = whole ring)
+  int32_t dbg_skip;         // experiment (B200SGD_DBGSKIP, row mapping only): 1 no running loss, 2 no shuffles, 4 no g FMAs
   StepCtl* ctl;             // GRAPH engine only (nullptr for the persistent engine)
   unsigned long long* dbg;  // optional [grid][8] per-phase cycle sums (sgd_debug_phase_cycles)
   double* loss;             // [grid][2] per-CTA sums of |r| and r*r over the launch (running loss)
@@ -163,6 +164,15 @@ __device__ __forceinline__ void tma_gather4_g2s(uint32_t dst, const CUtensorMap*
       " [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(dst),
       "l"(reinterpret_cast<uint64_t>(map)), "r"(0), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(bar)
       : "memory");
+}
+// 4 bytes global -> shared without a register in between (LDGSTS); completion by group
+__device__ __forceinline__ void cp_async_4(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -243,9 +253,11 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
   return t;
 }
 // Watchdog for the inter-CTA / inter-GPU spin loops: a kernel that can never finish would take the
-// whole GPU box down with it.  After kSpinTimeoutNs the waiter records an error code in *err and
+// whole GPU box down with it.  After c_spin_timeout_ns the waiter records an error code in *err and
 // gives up (so does every later wait, at once); the host turns that into SGD_ERR_CUDA/COMM.
-constexpr unsigned long long kSpinTimeoutNs = 4000000000ull;
+// The host sets it at sgd_create: 4 s on one GPU; 30 s with several ranks, where it is also the
+// skew the ranks may have when they enter an epoch (B200SGD_WATCHDOG_MS overrides both).
+__constant__ unsigned long long c_spin_timeout_ns = 4000000000ull;
 struct SpinGuard {
   unsigned int spins = 0;
   unsigned long long t0 = 0;
@@ -254,7 +266,7 @@ struct SpinGuard {
     if (*reinterpret_cast<volatile unsigned int*>(err) != 0u) return true;
     const unsigned long long now = global_timer_ns();
     if (t0 == 0) { t0 = now; return false; }
-    if (now - t0 > kSpinTimeoutNs) { atomicCAS(err, 0u, code); return true; }
+    if (now - t0 > c_spin_timeout_ns) { atomicCAS(err, 0u, code); return true; }
     return false;
   }
 };
@@ -395,44 +407,41 @@ __device__ __forceinline__ float4 ll_gather(const uint4* base0, int64_t stride, 
 }
 
 // CLUSTER tail: sum of the tagged float4 of sources q, q+Q, ... < nsrc of ONE column; source i sits
-// `stride` uint4 after source i-1.  Up to four sources in flight, consumed in order (fixed order:
-// every cluster of every GPU gets the same bits).
+// `stride` uint4 after source i-1.  Four sources at a time: ALL that are still missing are probed in
+// every round, so one L2 round trip is left after the last arrival (probing them one after the other
+// cost a round trip per late source: 15 clusters took twice as long as 7).  The values are added in
+// source order whatever the order of arrival: every cluster of every GPU gets the same bits.
 __device__ __forceinline__ float4 cl_gather(const uint4* base, int64_t stride, int nsrc, int q, int Q, uint32_t tag,
-                                            unsigned int* err, unsigned one_word) {
+                                            unsigned int* err) {
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  int i = q;
-  for (; i + 3 * Q < nsrc; i += 4 * Q) {
-    const uint4* s0 = base + (int64_t)i * stride;
-    const uint4* s1 = base + (int64_t)(i + Q) * stride;
-    const uint4* s2 = base + (int64_t)(i + 2 * Q) * stride;
-    const uint4* s3 = base + (int64_t)(i + 3 * Q) * stride;
-    const uint4 a0 = ld_volatile_u4(s0), b0 = ld_volatile_u4(s0 + 1);
-    const uint4 a1 = ld_volatile_u4(s1), b1 = ld_volatile_u4(s1 + 1);
-    const uint4 a2 = ld_volatile_u4(s2), b2 = ld_volatile_u4(s2 + 1);
-    const uint4 a3 = ld_volatile_u4(s3), b3 = ld_volatile_u4(s3 + 1);
-    float4 v0, v1, v2, v3;
-    if (!ll_unpack(a0, b0, tag, &v0)) v0 = ll_wait_f4(s0, tag, err, one_word);
-    if (!ll_unpack(a1, b1, tag, &v1)) v1 = ll_wait_f4(s1, tag, err, one_word);
-    if (!ll_unpack(a2, b2, tag, &v2)) v2 = ll_wait_f4(s2, tag, err, one_word);
-    if (!ll_unpack(a3, b3, tag, &v3)) v3 = ll_wait_f4(s3, tag, err, one_word);
-    acc = f4_add(acc, v0);
-    acc = f4_add(acc, v1);
-    acc = f4_add(acc, v2);
-    acc = f4_add(acc, v3);
+  for (int i0 = q; i0 < nsrc; i0 += 4 * Q) {
+    float4 v[4];
+    uint32_t pending = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i0 + k * Q < nsrc) pending |= 1u << k;
+    }
+    const uint32_t want = pending;
+    SpinGuard guard;
+    while (pending != 0u) {
+      uint4 a[4], b[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (pending & (1u << k)) {
+          const uint4* sp = base + (int64_t)(i0 + k * Q) * stride;
+          a[k] = ld_volatile_u4(sp);
+          b[k] = ld_volatile_u4(sp + 1);
+        }
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if ((pending & (1u << k)) && ll_unpack(a[k], b[k], tag, &v[k])) pending &= ~(1u << k);
+      if (pending != 0u && guard.expired(err, 3u)) break;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (want & (1u << k)) acc = f4_add(acc, v[k]);
   }
-  if (i + Q < nsrc) {
-    const uint4* s0 = base + (int64_t)i * stride;
-    const uint4* s1 = base + (int64_t)(i + Q) * stride;
-    const uint4 a0 = ld_volatile_u4(s0), b0 = ld_volatile_u4(s0 + 1);
-    const uint4 a1 = ld_volatile_u4(s1), b1 = ld_volatile_u4(s1 + 1);
-    float4 v0, v1;
-    if (!ll_unpack(a0, b0, tag, &v0)) v0 = ll_wait_f4(s0, tag, err, one_word);
-    if (!ll_unpack(a1, b1, tag, &v1)) v1 = ll_wait_f4(s1, tag, err, one_word);
-    acc = f4_add(acc, v0);
-    acc = f4_add(acc, v1);
-    i += 2 * Q;
-  }
-  for (; i < nsrc; i += Q) acc = f4_add(acc, ll_wait_f4(base + (int64_t)i * stride, tag, err, one_word));
   return acc;
 }
 
@@ -507,11 +516,23 @@ __device__ __forceinline__ float4 tree_sum_sources(const float4* src, int64_t st
 //          thread t accumulates r * x for ITS float4 columns t, t+kCT, ... over all rows of the tile
 //          (KC float4 of gradient per thread).  No cross-warp gradient scratch, so the ring is
 //          deeper; the staged row is read from shared memory twice instead of once.
-template <int KC, int NW, bool WIDE>
+constexpr int kIdxStages = 4;  // rounds of permutation indices in flight per producer warp
+// Software pipeline of the consumers over the tiles of a step (rows of tile t+1 fetched into a second
+// register set before tile t is computed).  Measured in round 2: 2x SLOWER than the plain loop on every
+// shape (C = 512: 1475 vs 807 cycles per 16-row tile; spills and a 6000-instruction kernel), so off.
+constexpr bool kPipelineTiles = false;
+template <int KC, int NW, bool WIDE, int U = 1, int CW = 0>
 struct EpochSmem {
-  static constexpr size_t kBarBytes = 2 * kMaxTiles * sizeof(uint64_t);
-  static constexpr size_t kWBytes = (WIDE ? (size_t)32 * NW * KC : (size_t)32 * KC) * sizeof(float4);
-  static constexpr size_t kGredBytes = WIDE ? 2 * 32 * sizeof(float) : (size_t)NW * 32 * KC * sizeof(float4);
+  static constexpr int kRW = CW > 0 ? NW / CW : 1;                  // COLSPLIT: warps along the rows
+  static constexpr int kTileRows = CW > 0 ? kRW * U : NW * U;       // rows of a ring tile (row / COLSPLIT mappings)
+  // index staging of the producers: [producer warp][stage][rows of a round, padded to 32]
+  static constexpr size_t kIdxBytes = (size_t)kMaxProducerWarps * kIdxStages * (WIDE ? 32 : ((kTileRows + 31) / 32) * 32) * sizeof(int32_t);
+  static constexpr size_t kBarBytes = 2 * kMaxTiles * sizeof(uint64_t) + kIdxBytes;
+  static constexpr size_t kWBytes = (CW > 0 ? (size_t)32 * CW * KC : WIDE ? (size_t)32 * NW * KC : (size_t)32 * KC) * sizeof(float4);
+  // cross-warp scratch: row mapping: the warps' gradients [NW][KC][32]; column mapping: residuals [2][32];
+  // COLSPLIT: partial dots [2][CW][tile rows] (2 KB) + the row groups' gradients [RW][KC][32*CW] when RW > 1
+  static constexpr size_t kGredBytes = CW > 0 ? (size_t)2048 + (kRW > 1 ? (size_t)kRW * KC * 32 * CW * sizeof(float4) : 0)
+                                       : WIDE ? 2 * 32 * sizeof(float) : (size_t)NW * 32 * KC * sizeof(float4);
   static constexpr size_t kFixed = kBarBytes + kWBytes + kGredBytes;
 };
 
@@ -532,10 +553,28 @@ struct EpochSmem {
 //          (4) all-gathered inside the cluster, again through distributed shared memory.  One L2
 //          hop per step instead of two, <= 18 sources per poll instead of 128-148, and no CTA ever
 //          polls for the weights.
-template <int KC, int U, int NW, bool WIDE = false, bool NARROW8 = false, bool LEAN = false, bool CLT = false>
-__global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1)
+//   CW > 0: COLSPLIT mapping (rows of 129 .. 8192 features).  The consumer warps form a CW x RW grid
+//          (RW = NW / CW): warp (cg, rg) owns the float4 columns cg*32 + lane + k*32*CW, k < KC, of
+//          the U rows rg*U .. rg*U+U-1 of every ring tile (tile = RW*U rows).  Its weights and its
+//          gradient columns live in registers for the whole step (KC float4 each) and so do the U x KC
+//          float4 of the tile it is working on: every staged byte is read from shared memory ONCE
+//          (the row mapping re-reads the weights per row: 2x the shared-memory traffic, and at
+//          C = 2048 it was the consumers, not HBM, that bounded the step: 30 bytes per clock and SM).
+//          Per tile: partial dot products of the own columns for U rows, a transposing butterfly
+//          (U values over 32 lanes in U-1 + log2(32/U) shuffles instead of 5 per row), the CW partial
+//          sums of a row meet in shared memory (one CTA barrier per tile), r = x.w - y, then
+//          g += r * x from the registers.
+//   NPMAX: most producer warps the host may launch (block = 32 * (NW + producer warps) threads).  (A row
+//          mapping that keeps 16 float4 of weights, row and gradient per lane -- 192 registers -- does not
+//          exist: the register file is 16 K per SM sub-partition, so 224 registers allow two warps per
+//          sub-partition, eight per CTA, producers included.)
+template <int KC, int U, int NW, bool WIDE = false, bool NARROW8 = false, bool LEAN = false, bool CLT = false, int CW = 0,
+          int NPMAX = kMaxProducerWarps>
+__global__ void __launch_bounds__(32 * (NW + NPMAX), 1)
     sgd_epoch_kernel(const __grid_constant__ EpochParams p) {
   static_assert(!(CLT && LEAN), "the cluster tail keeps its run-time switches");
+  static_assert(CW == 0 || (!WIDE && !NARROW8 && NW % CW == 0 && (U == 1 || U == 2 || U == 4 || U == 8)), "COLSPLIT geometry");
+  using Smem = EpochSmem<KC, NW, WIDE, U, CW>;
   static_assert(!NARROW8 || (KC == 1 && U == 4 && !WIDE), "NARROW8 is the <1,4,NW> row mapping");
   // run-time switches, constant-folded in the LEAN instantiations
   StepCtl* const o_ctl = LEAN ? nullptr : p.ctl;
@@ -551,10 +590,11 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw);
   uint64_t* empty_bar = full_bar + kMaxTiles;
-  float4* w_s = reinterpret_cast<float4*>(smem_raw + EpochSmem<KC, NW, WIDE>::kBarBytes);
-  float4* gred = w_s + (WIDE ? 32 * NW * KC : 32 * KC);  // WIDE: float r_s[2][32] lives here instead
+  int32_t* idx_s = reinterpret_cast<int32_t*>(empty_bar + kMaxTiles);  // producers' index staging
+  float4* w_s = reinterpret_cast<float4*>(smem_raw + Smem::kBarBytes);
+  float4* gred = w_s + Smem::kWBytes / sizeof(float4);  // WIDE: float r_s[2][32] lives here instead; COLSPLIT: see Smem
   // CLT: [kFixed, kFixed + cl_extra) holds the exchange barriers and buffers (see the step tail)
-  unsigned char* const cl_base = smem_raw + EpochSmem<KC, NW, WIDE>::kFixed;
+  unsigned char* const cl_base = smem_raw + Smem::kFixed;
   unsigned char* ring = cl_base + (CLT ? p.cl_extra : 0u);
   __shared__ float4 xred[NW];  // cross-warp scratch of ll_gather
   __shared__ volatile int steps_done;  // experiment switch (prefetch_steps): consumer progress
@@ -566,7 +606,7 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1)
   const int G = gridDim.x;
   // rows per ring tile = rows of one producer round: NW*U in the row mapping, chosen by the host
   // (as many as fit, rows can be tens of KB) in the column mapping
-  constexpr int TRc = NW * U;
+  constexpr int TRc = Smem::kTileRows;
   static_assert(TRc <= 32 || NARROW8, "only the narrow-row mapping uses tiles of more than 32 rows");
   static_assert(TRc <= 128, "a gather4 round is one warp instruction: at most 4 * 32 rows per tile");
   constexpr int IH = WIDE ? 1 : (TRc + 31) / 32;  // permutation indices a producer lane holds per round
@@ -605,7 +645,7 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1)
     fence_barrier_init();
   }
   // weights -> shared (zero beyond C so that the label / pad columns never contribute)
-  for (int c = tid; c < (WIDE ? 128 * NW * KC : 128 * KC); c += kThreads)
+  for (int c = tid; c < (int)(Smem::kWBytes / sizeof(float)); c += kThreads)
     reinterpret_cast<float*>(w_s)[c] = (c < p.C) ? p.w[c] : 0.0f;
   __syncthreads();
   if constexpr (CLT) cluster_sync_unaligned();  // every CTA's barriers exist before anybody sends
@@ -679,23 +719,38 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1)
     load_step();
     settle();
     for (int k = 0; k < warp; ++k) advance();  // my first round
-    int cnt = round_cnt();
-    int32_t idx[IH];
-    auto load_indices = [&]() {  // lane l holds rows l, l+32, ... of the round
+    // The permutation indices of my next kIdxStages rounds are in flight at any time, fetched with
+    // cp.async straight into shared memory (no register waits for them).  An index comes from HBM
+    // under full load (1-2 us): with one round of look-ahead a producer warp managed one round per
+    // that latency, i.e. the row stream ran at about the HBM rate but could never get AHEAD of the
+    // consumers, and the step tail was not overlapped at all (rows of a step took the step's whole
+    // HBM time after every tail).
+    constexpr int PD = kIdxStages;
+    constexpr int TRP = 32 * IH;
+    const uint32_t ibuf0 = smem_u32(idx_s) + (uint32_t)(warp * PD * TRP) * 4u;
+    const int32_t* ibuf = idx_s + warp * PD * TRP;
+    int cntq[PD], sq[PD];
+    auto fetch_indices = [&](int stage, int c) {  // lane l fetches rows l, l+32, ... of the generator's round
 #pragma unroll
-      for (int h = 0; h < IH; ++h) {
-        idx[h] = 0;
-        if (h * 32 + lane < cnt) idx[h] = __ldg(perm + off + lo + j0 + h * 32 + lane);
-      }
+      for (int h = 0; h < IH; ++h)
+        if (h * 32 + lane < c) cp_async_4(ibuf0 + (uint32_t)(stage * TRP + h * 32 + lane) * 4u, perm + off + lo + j0 + h * 32 + lane);
+      cp_async_commit();  // one group per round, also when it is empty
     };
-    load_indices();
+#pragma unroll
+    for (int d = 0; d < PD; ++d) {
+      cntq[d] = round_cnt();
+      sq[d] = s;
+      fetch_indices(d, cntq[d]);
+      for (int k = 0; k < NP; ++k) advance();
+    }
+    int stage = 0;
     // ring position of my current round: round q lives in tile q % ntiles, use q / ntiles (NP <= ntiles)
     uint32_t ptile = (uint32_t)warp, puse = 0, pseq = (uint32_t)warp;
     const uint32_t infl = (uint32_t)p.inflight_tiles;
-    // Flow control of one round (lane 0): the tile is free again, and at most `infl` tiles are in
-    // flight.  Every byte requested from HBM queues in front of the step tail's small L2 polls: with
-    // the whole ring (~200 KB per SM, ~30 MB per GPU) outstanding a poll waits ~4.5 us behind the row
-    // stream; ~48-64 KB per SM keep HBM busy (bandwidth x latency ~ 6 MB) and the queues short.
+    // Flow control of one round (lane 0): the tile is free again and -- experiment switch
+    // B200SGD_INFLIGHT_KB, off by default -- at most `infl` tiles are in flight.  (Hypothesis tested in
+    // round 2: the tail's L2 polls queue behind the outstanding row requests.  They do not: capping
+    // the bytes in flight changed nothing down to 64 KB per SM and cost bandwidth below that.)
     auto acquire_tile = [&](uint32_t tile, uint32_t use, uint32_t seq) {
       mbar_wait_relaxed(empty0 + 8u * tile, (use & 1u) ^ 1u);  // passes at once on the first use
       if (infl > 0u && seq >= infl) {                          // round seq - infl has landed
@@ -704,16 +759,25 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1)
         mbar_wait_relaxed(full0 + 8u * t, u & 1u);
       }
     };
-    while (cnt > 0) {
-      const int cur_cnt = cnt;
+    while (cntq[0] > 0) {
+      const int cur_cnt = cntq[0];
+      const int cur_s = sq[0];
+      cp_async_wait_group<PD - 1>();  // the oldest round's indices have landed
       int32_t cur_idx[IH];
 #pragma unroll
-      for (int h = 0; h < IH; ++h) cur_idx[h] = idx[h];
-      const int cur_s = s;
-      // move to my next round and get its indices in flight
+      for (int h = 0; h < IH; ++h) cur_idx[h] = (h * 32 + lane < cur_cnt) ? ibuf[stage * TRP + h * 32 + lane] : 0;
+      // the queue moves up; the generator stands PD rounds ahead: fetch that round into the freed stage
+#pragma unroll
+      for (int d = 0; d + 1 < PD; ++d) {
+        cntq[d] = cntq[d + 1];
+        sq[d] = sq[d + 1];
+      }
+      cntq[PD - 1] = round_cnt();
+      sq[PD - 1] = s;
+      __syncwarp();
+      fetch_indices(stage, cntq[PD - 1]);
       for (int k = 0; k < NP; ++k) advance();
-      cnt = round_cnt();
-      load_indices();
+      stage = (stage + 1 == PD) ? 0 : stage + 1;
       // experiment: cap how many steps the producer may run ahead of the consumers (0 = unlimited)
       if (o_prefetch_steps > 0) {
         while (cur_s - steps_done >= o_prefetch_steps) {
@@ -866,6 +930,7 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1)
         const unsigned char* tbase = ring + (size_t)tile * tile_bytes;
         float* rbuf = r_s + (tq & 1u) * 32;
         mbar_wait(full0 + 8u * tile, use & 1u);
+        mark(7);
         // phase A: warp cw takes rows cw, cw+NW, ... of the tile
         for (int r = cw; r < cnt; r += NW) {
           {
@@ -909,8 +974,148 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1)
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(empty0 + 8u * tile);  // this warp is done with the tile
+        mark(0);
       }
       tqbase += (uint32_t)ntw;
+    } else if constexpr (CW > 0) {
+      // ---- COLSPLIT: my columns of my U rows of every tile, everything in registers ----
+      constexpr int RPW = U, LB = (RPW == 1 ? 0 : RPW == 2 ? 1 : RPW == 4 ? 2 : 3), LG = 5 - LB;
+      constexpr int CT = 32 * CW;  // threads along the columns
+      const int cg = cw % CW, rg = cw / CW;
+      const int ccid = cg * 32 + lane;
+      float* pd_s = reinterpret_cast<float*>(gred);  // [2][CW][TRc] partial dot products
+      float4 wv[KC];
+#pragma unroll
+      for (int k = 0; k < KC; ++k) wv[k] = w_s[ccid + k * CT];  // zero beyond C
+      const int row0 = rg * RPW;       // my rows of a tile: row0 .. row0 + RPW - 1
+      const int ridx = lane >> LG;     // the one whose dot product ends up in this lane
+      const int n32 = (int)n;
+      const int nt = (n32 + TR - 1) / TR;
+      // Software pipeline over the tiles (see the row mapping): my part of tile t+1 is fetched into
+      // a second register set -- if the tile has landed -- before tile t is reduced, exchanged
+      // (CTA barrier) and accumulated.
+      constexpr bool kPipe = kPipelineTiles && (RPW * KC <= 8);
+      float4 xa[RPW][KC], xb[kPipe ? RPW : 1][kPipe ? KC : 1];
+      float ya = 0.f, yb = 0.f;
+      auto take_tile = [&](uint32_t* tile, uint32_t* use) {
+        *tile = ctile;
+        *use = cuse;
+        if (++ctile == (uint32_t)ntiles) { ctile = 0; ++cuse; }
+      };
+      auto tile_cnt = [&](int ti) -> int { return (n32 - ti * TR) < TR ? (n32 - ti * TR) : TR; };
+      auto load_part = [&](auto& x, float& yv, uint32_t tile, int cnt) {
+        const unsigned char* tbase = ring + (size_t)tile * tile_bytes + (size_t)row0 * p.slot_bytes;
+#pragma unroll
+        for (int i = 0; i < RPW; ++i) {
+          const float4* row = reinterpret_cast<const float4*>(tbase + (size_t)i * p.slot_bytes);
+          const bool live = row0 + i < cnt;  // warp-uniform
+#pragma unroll
+          for (int k = 0; k < KC; ++k) {
+            const int f = ccid + k * CT;
+            x[i][k] = (live && f < C4) ? row[f] : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+        yv = (row0 + ridx < cnt) ? reinterpret_cast<const float*>(tbase + (size_t)ridx * p.slot_bytes)[p.C] : 0.f;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty0 + 8u * tile);  // my part of the tile is in registers
+      };
+      auto compute_part = [&](auto& x, float yv, int cnt, int ti) {
+        const bool my_live = row0 + ridx < cnt;
+        float v[RPW];
+#pragma unroll
+        for (int i = 0; i < RPW; ++i) {
+          float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+          for (int k = 0; k < KC; ++k) {
+            d0 = fmaf(x[i][k].x, wv[k].x, d0);
+            d1 = fmaf(x[i][k].y, wv[k].y, d1);
+            d0 = fmaf(x[i][k].z, wv[k].z, d0);
+            d1 = fmaf(x[i][k].w, wv[k].w, d1);
+          }
+          v[i] = d0 + d1;
+        }
+        // transposing butterfly: RPW values x 32 lanes -> one value per lane (row ridx), fixed order
+#pragma unroll
+        for (int b = 0; b < LB; ++b) {
+          const int m = 16 >> b, half = RPW >> (b + 1);
+          const bool up = (lane & m) != 0;
+#pragma unroll
+          for (int jx = 0; jx < half; ++jx) {
+            const float keep = up ? v[jx + half] : v[jx];
+            const float send = up ? v[jx] : v[jx + half];
+            v[jx] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+          }
+        }
+#pragma unroll
+        for (int m = 16 >> LB; m >= 1; m >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], m);
+        float* pd = pd_s + ((tqbase + (uint32_t)ti) & 1u) * (CW * TRc);
+        if ((lane & ((1 << LG) - 1)) == 0) pd[cg * TRc + row0 + ridx] = v[0];
+        consumer_bar<kCT>();
+        float dsum = pd[row0 + ridx];
+#pragma unroll
+        for (int c2 = 1; c2 < CW; ++c2) dsum += pd[c2 * TRc + row0 + ridx];
+        const float res = my_live ? dsum - yv : 0.f;  // r = x.w - y (sgd_thrust.cu:43-48 / :352-364); rows beyond the slice: 0
+        if (cg == 0 && (lane & ((1 << LG) - 1)) == 0) {  // one lane per row keeps the running loss and the residual
+          loss_abs += (double)fabsf(res);
+          loss_sq += (double)res * (double)res;
+          if (o_r_out != nullptr && my_live) o_r_out[off + lo + (int64_t)ti * TR + row0 + ridx] = res;
+        }
+#pragma unroll
+        for (int i = 0; i < RPW; ++i) {
+          const float ri = __shfl_sync(0xffffffffu, res, i << LG);
+#pragma unroll
+          for (int k = 0; k < KC; ++k) {
+            g[k].x = fmaf(ri, x[i][k].x, g[k].x);
+            g[k].y = fmaf(ri, x[i][k].y, g[k].y);
+            g[k].z = fmaf(ri, x[i][k].z, g[k].z);
+            g[k].w = fmaf(ri, x[i][k].w, g[k].w);
+          }
+        }
+      };
+      if constexpr (kPipe) {
+        uint32_t tile, use;
+        if (nt > 0) {
+          take_tile(&tile, &use);
+          mbar_wait(full0 + 8u * tile, use & 1u);
+          mark(7);  // (profile) time spent waiting for the rows to land
+          load_part(xa, ya, tile, tile_cnt(0));
+        }
+        for (int ti = 0; ti < nt; ++ti) {
+          const bool more = ti + 1 < nt;
+          bool early = false;
+          if (more) {
+            take_tile(&tile, &use);
+            early = __all_sync(0xffffffffu, mbar_try_wait(full0 + 8u * tile, use & 1u));
+            if (early) load_part(xb, yb, tile, tile_cnt(ti + 1));
+          }
+          compute_part(xa, ya, tile_cnt(ti), ti);
+          mark(0);  // (profile) rows of the tile processed
+          if (more) {
+            if (!early) {
+              mbar_wait(full0 + 8u * tile, use & 1u);
+              mark(7);
+              load_part(xb, yb, tile, tile_cnt(ti + 1));
+            }
+            ya = yb;
+#pragma unroll
+            for (int i = 0; i < RPW; ++i) {
+#pragma unroll
+              for (int k = 0; k < KC; ++k) xa[i][k] = xb[i][k];
+            }
+          }
+        }
+      } else {
+        for (int ti = 0; ti < nt; ++ti) {
+          uint32_t tile, use;
+          take_tile(&tile, &use);
+          mbar_wait(full0 + 8u * tile, use & 1u);
+          mark(7);
+          load_part(xa, ya, tile, tile_cnt(ti));
+          compute_part(xa, ya, tile_cnt(ti), ti);
+          mark(0);
+        }
+      }
+      tqbase += (uint32_t)nt;
     } else if constexpr (NARROW8) {
       // ---- narrow rows: 8 lanes per row, 4 rows per warp and tile pass ----
       const int rg = lane >> 3, sl = lane & 7;  // row group within the warp, sub-lane within the row
@@ -982,18 +1187,29 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1)
       // takes rows cw, cw+NW, ... of the tile, all U of them concurrently ----
       const int n32 = (int)n;  // rows of one CTA in one step always fit 32 bits
       const int nt = (n32 + TR - 1) / TR;
-      for (int ti = 0; ti < nt; ++ti) {
-        const uint32_t tile = ctile, use = cuse;
+      // the weights of my columns stay in registers for the whole step: the staged rows are the only
+      // shared-memory traffic of the row phase (re-reading w per tile pass doubled it at U = 1 and made
+      // the consumers, not HBM, the bound of 2048-feature rows: 30 bytes per clock and SM)
+      float4 wv[KC];
+#pragma unroll
+      for (int k = 0; k < KC; ++k) wv[k] = w_s[k * 32 + lane];
+      // Software pipeline over the tiles of the step (kPipe: where two tiles' rows fit the registers):
+      // all warps wait for the same tile, so without it they load together (the shared-memory pipe is
+      // the only busy unit, ~530 cycles for a 67 KB tile) and then compute together (the pipe idles).
+      // With it the rows of tile t+1 are fetched -- if they have landed -- before tile t is computed.
+      constexpr bool kPipe = kPipelineTiles && (U * KC <= 8);
+      float4 xa[U][KC], xb[kPipe ? U : 1][kPipe ? KC : 1];
+      float ya[U], yb[kPipe ? U : 1];
+      auto take_tile = [&](uint32_t* tile, uint32_t* use) {  // the next ring tile of my sequence
+        *tile = ctile;
+        *use = cuse;
         if (++ctile == (uint32_t)ntiles) { ctile = 0; ++cuse; }
-        const int cnt = (n32 - ti * TR) < TR ? (n32 - ti * TR) : TR;
+      };
+      auto load_rows = [&](auto& x, auto& y, uint32_t tile, int cnt) {
         const unsigned char* tbase = ring + (size_t)tile * tile_bytes;
-        float4 x[U][KC];
-        float dot[U], y[U];
-        mbar_wait(full0 + 8u * tile, use & 1u);  // all rows of the tile have landed
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const int r = cw + u * NW;
-          dot[u] = 0.f;
           y[u] = 0.f;
           if (r < cnt) {  // warp-uniform
             const float4* row = reinterpret_cast<const float4*>(tbase + (size_t)r * p.slot_bytes);
@@ -1010,29 +1226,40 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1)
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(empty0 + 8u * tile);  // my rows are in registers
+      };
+      auto compute_rows = [&](auto& x, auto& y, int cnt, int ti) {
+        float dot[U], dot2[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) dot[u] = dot2[u] = 0.f;
 #pragma unroll
         for (int k = 0; k < KC; ++k) {
-          const float4 wv = w_s[k * 32 + lane];
 #pragma unroll
-          for (int u = 0; u < U; ++u) {
-            dot[u] = fmaf(x[u][k].x, wv.x, dot[u]);
-            dot[u] = fmaf(x[u][k].y, wv.y, dot[u]);
-            dot[u] = fmaf(x[u][k].z, wv.z, dot[u]);
-            dot[u] = fmaf(x[u][k].w, wv.w, dot[u]);
+          for (int u = 0; u < U; ++u) {  // two chains per row
+            dot[u] = fmaf(x[u][k].x, wv[k].x, dot[u]);
+            dot2[u] = fmaf(x[u][k].y, wv[k].y, dot2[u]);
+            dot[u] = fmaf(x[u][k].z, wv[k].z, dot[u]);
+            dot2[u] = fmaf(x[u][k].w, wv[k].w, dot2[u]);
           }
         }
 #pragma unroll
-        for (int m = 16; m >= 1; m >>= 1) {
+        for (int u = 0; u < U; ++u) dot[u] += dot2[u];
+        if (!(p.dbg_skip & 2)) {
 #pragma unroll
-          for (int u = 0; u < U; ++u) dot[u] += __shfl_xor_sync(0xffffffffu, dot[u], m);
+          for (int m = 16; m >= 1; m >>= 1) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) dot[u] += __shfl_xor_sync(0xffffffffu, dot[u], m);
+          }
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           // r = x.w - y   (sgd_thrust.cu:43-48; Sgemv with beta = -1, sgd_thrust.cu:352-364);
           // rows beyond the tile have x = 0, y = 0 -> r = 0 and contribute nothing
           const float r = dot[u] - y[u];
-          loss_abs += (double)fabsf(r);  // rows beyond the tile have r = 0
-          loss_sq += (double)r * (double)r;
+          if (!(p.dbg_skip & 1)) {
+            loss_abs += (double)fabsf(r);
+            loss_sq += (double)r * (double)r;
+          }
+          if (p.dbg_skip & 4) { g[0].x += r; continue; }
 #pragma unroll
           for (int k = 0; k < KC; ++k) {
             g[k].x = fmaf(r, x[u][k].x, g[k].x);
@@ -1045,6 +1272,50 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1)
             if (rr < cnt) o_r_out[off + lo + (int64_t)ti * TR + rr] = r;
           }
         }
+      };
+      auto tile_cnt = [&](int ti) -> int { return (n32 - ti * TR) < TR ? (n32 - ti * TR) : TR; };
+      if constexpr (kPipe) {
+        uint32_t tile, use;
+        if (nt > 0) {
+          take_tile(&tile, &use);
+          mbar_wait(full0 + 8u * tile, use & 1u);  // all rows of the tile have landed
+          mark(7);  // (profile) time spent waiting for the rows to land
+          load_rows(xa, ya, tile, tile_cnt(0));
+        }
+        for (int ti = 0; ti < nt; ++ti) {
+          const bool more = ti + 1 < nt;
+          bool early = false;
+          if (more) {
+            take_tile(&tile, &use);
+            early = __all_sync(0xffffffffu, mbar_try_wait(full0 + 8u * tile, use & 1u));
+            if (early) load_rows(xb, yb, tile, tile_cnt(ti + 1));
+          }
+          compute_rows(xa, ya, tile_cnt(ti), ti);
+          mark(0);  // (profile) rows of the tile processed
+          if (more) {
+            if (!early) {
+              mbar_wait(full0 + 8u * tile, use & 1u);
+              mark(7);
+              load_rows(xb, yb, tile, tile_cnt(ti + 1));
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              ya[u] = yb[u];
+#pragma unroll
+              for (int k = 0; k < KC; ++k) xa[u][k] = xb[u][k];
+            }
+          }
+        }
+      } else {
+        for (int ti = 0; ti < nt; ++ti) {
+          uint32_t tile, use;
+          take_tile(&tile, &use);
+          mbar_wait(full0 + 8u * tile, use & 1u);
+          mark(7);
+          load_rows(xa, ya, tile, tile_cnt(ti));
+          compute_rows(xa, ya, tile_cnt(ti), ti);
+          mark(0);
+        }
       }
       tqbase += (uint32_t)nt;
     }
@@ -1052,7 +1323,14 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1)
 
     // ---- CTA partial: fixed-order sum over the warps (row mapping); already per thread and
     // per column in the column mapping: thread ctid holds float4 columns ctid + k*kCT ----
-    if constexpr (!WIDE) {
+    if constexpr (CW > 0) {
+      if constexpr (Smem::kRW > 1) {  // the row groups' gradients of a column meet in shared memory: [rg][k][column thread]
+        float4* gred2 = gred + 2048 / sizeof(float4);
+#pragma unroll
+        for (int k = 0; k < KC; ++k) gred2[((cw / CW) * KC + k) * (32 * CW) + (cw % CW) * 32 + lane] = g[k];
+        consumer_bar<kCT>();
+      }
+    } else if constexpr (!WIDE) {
 #pragma unroll
       for (int k = 0; k < KC; ++k) gred[(cw * KC + k) * 32 + lane] = g[k];
       consumer_bar<kCT>();
@@ -1060,7 +1338,14 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1)
     mark(1);  // all warps of the CTA done
     const int par = (first_step + s) & 1;
     auto cta_partial = [&](int f) -> float4 {
-      if constexpr (WIDE) {
+      if constexpr (CW > 0 && Smem::kRW > 1) {
+        const float4* gred2 = gred + 2048 / sizeof(float4);
+        const int k = f / (32 * CW), cc = f % (32 * CW);
+        float4 acc = gred2[k * (32 * CW) + cc];
+#pragma unroll
+        for (int r2 = 1; r2 < Smem::kRW; ++r2) acc = f4_add(acc, gred2[(r2 * KC + k) * (32 * CW) + cc]);
+        return acc;
+      } else if constexpr (WIDE || CW > 0) {  // (COLSPLIT with CW == NW: thread ctid owns columns ctid + k*kCT, as WIDE)
         float4 acc = g[0];  // f == ctid + k*kCT for the calling thread (publish loops stride by kCT)
 #pragma unroll
         for (int k = 1; k < KC; ++k)
@@ -1132,7 +1417,7 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1)
         }
         if (TG > 1 && active && q < Qe) {  // (3) thread q adds clusters q, q + Qe, ... (all GPUs), fixed order
           const uint4* base = p.cl_inbox_local + (((int64_t)parc * TG) * C4p + f) * 2;
-          xpart[q * ncol + cl] = cl_gather(base, (int64_t)C4p * 2, TG, q, Qe, tag, p.err, poll_one_word);
+          xpart[q * ncol + cl] = cl_gather(base, (int64_t)C4p * 2, TG, q, Qe, tag, p.err);
         }
         consumer_bar<kCT>();
         mark(4);  // all clusters' sums gathered
@@ -1290,6 +1575,13 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1)
     for (int i = 0; i < 8; ++i) o_dbg[(int64_t)cta * 8 + i] = ph[i];
   }
   double* const loss_out = (o_ctl != nullptr) ? o_ctl->loss : p.loss;
+  if constexpr (CW > 0) {  // the loss lives in one lane per row of the cg == 0 warps
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+      loss_abs += __shfl_xor_sync(0xffffffffu, loss_abs, m);
+      loss_sq += __shfl_xor_sync(0xffffffffu, loss_sq, m);
+    }
+  }
   if constexpr (NARROW8) {  // the loss lives in the sl == 0 lane of every row group
     loss_abs += __shfl_xor_sync(0xffffffffu, loss_abs, 8);
     loss_abs += __shfl_xor_sync(0xffffffffu, loss_abs, 16);
@@ -1328,39 +1620,79 @@ __global__ void __launch_bounds__(32 * (NW + kMaxProducerWarps), 1)
 
 // ------------------------------------------------------------------------------------------------
 // Mean absolute error over the data in ORIGINAL order (replaces calculate_mean_abs_error_cublas,
-// sgd_thrust.cu:79-135: Scopy + Sgemv + Sasum).  One streaming pass, warp per row, float4 loads.
+// sgd_thrust.cu:79-135: Scopy + Sgemv + Sasum).  One streaming pass over the record array -- a pure
+// HBM-roofline kernel: 4 * rows * ld bytes, nothing else.
+//   * L lanes share a row (L = 8 for C = 100, 32 from C = 512 on; the host picks the power of two
+//     that gives a lane about four float4), so narrow rows keep all 32 lanes busy (the first
+//     version gave a whole warp to a 448-byte row: 28 of 32 lanes, 5 shuffle levels per row);
+//   * two rows per group and four float4 per row are in flight per lane (8 independent 16-byte
+//     streaming loads) before anything is consumed;
+//   * the label is element C of the record: the lane that loaded that float4 subtracts it, no
+//     second (dependent, 4-byte) read per row.
 // Per-block partial sums in double; the host adds the few hundred block sums.
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float f4_dot(float4 a, float4 b, float acc) {
+  acc = fmaf(a.x, b.x, acc);
+  acc = fmaf(a.y, b.y, acc);
+  acc = fmaf(a.z, b.z, acc);
+  return fmaf(a.w, b.w, acc);
+}
+__device__ __forceinline__ float f4_pick(float4 a, int e) { return e == 0 ? a.x : e == 1 ? a.y : e == 2 ? a.z : a.w; }
+
 __global__ void __launch_bounds__(256) sgd_mae_kernel(const float* __restrict__ rec, int64_t ld,
                                                       int32_t C, int64_t rows,
-                                                      const float* __restrict__ w,
+                                                      const float* __restrict__ w, int32_t L,
                                                       double* __restrict__ block_sums) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  float* w_s = reinterpret_cast<float*>(smem_raw);
-  const int C4 = (C + 3) >> 2;
-  for (int c = threadIdx.x; c < C4 * 4; c += blockDim.x) w_s[c] = (c < C) ? w[c] : 0.f;
+  float* w_s = reinterpret_cast<float*>(smem_raw);  // [ld]: the weights, 0 for the label and the padding
+  for (int c = threadIdx.x; c < (int)ld; c += blockDim.x) w_s[c] = (c < C) ? w[c] : 0.f;
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
+  const int ld4 = (int)(ld >> 2), cy = C >> 2, ey = C & 3;
+  const int G = 32 / L;                     // rows a warp treats side by side
+  const int j = lane & (L - 1), g = lane / L;
   const int64_t gwarp = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
-  const int64_t nwarps = (int64_t)gridDim.x * warps_per_block;
+  const int64_t stride = (int64_t)gridDim.x * warps_per_block * G;
   const float4* w4 = reinterpret_cast<const float4*>(w_s);
+  const float4* rec4 = reinterpret_cast<const float4*>(rec);
   double acc = 0.0;
-  for (int64_t row = gwarp; row < rows; row += nwarps) {
-    const float4* x4 = reinterpret_cast<const float4*>(rec + row * ld);
-    float dot = 0.f;
-    for (int f = lane; f < C4; f += 32) {
-      const float4 xv = __ldcs(x4 + f);
-      const float4 wv = w4[f];
-      dot = fmaf(xv.x, wv.x, dot);
-      dot = fmaf(xv.y, wv.y, dot);
-      dot = fmaf(xv.z, wv.z, dot);
-      dot = fmaf(xv.w, wv.w, dot);
-    }
+  for (int64_t rb = gwarp * G; rb < rows; rb += 2 * stride) {  // warp-uniform trip count
+    const int64_t r0 = rb + g, r1 = rb + stride + g;
+    const bool v0 = r0 < rows, v1 = r1 < rows;
+    const float4* x0 = rec4 + r0 * ld4;
+    const float4* x1 = rec4 + r1 * ld4;
+    float d0 = 0.f, d1 = 0.f;
+    for (int f = j; f < ld4; f += 4 * L) {
+      float4 a[4], b[4];
 #pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, m);
-    if (lane == 0) acc += (double)fabsf(dot - __ldcs(rec + row * ld + C));
+      for (int u = 0; u < 4; ++u) {
+        const int ff = f + u * L;
+        a[u] = (v0 && ff < ld4) ? __ldcs(x0 + ff) : make_float4(0.f, 0.f, 0.f, 0.f);
+        b[u] = (v1 && ff < ld4) ? __ldcs(x1 + ff) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int ff = f + u * L;
+        if (ff < ld4) {
+          const float4 wv = w4[ff];
+          d0 = f4_dot(a[u], wv, d0);
+          d1 = f4_dot(b[u], wv, d1);
+          if (ff == cy) {  // x.w - y   (sgd_thrust.cu:94-126: Sgemv with beta = -1 on a copy of the labels)
+            d0 -= f4_pick(a[u], ey);
+            d1 -= f4_pick(b[u], ey);
+          }
+        }
+      }
+    }
+    for (int m = L >> 1; m >= 1; m >>= 1) {
+      d0 += __shfl_xor_sync(0xffffffffu, d0, m);
+      d1 += __shfl_xor_sync(0xffffffffu, d1, m);
+    }
+    if (j == 0) acc += (double)fabsf(d0) + (double)fabsf(d1);  // rows beyond the end contribute |0|
   }
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
   __shared__ double red[32];
   if (lane == 0) red[threadIdx.x >> 5] = acc;
   __syncthreads();

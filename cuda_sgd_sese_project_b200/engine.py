@@ -42,6 +42,14 @@ def read_csv(filename: str, R: int, C_: int):
     return True, X, y
 
 
+def write_csv(filename: str, data, labels) -> None:
+    """`f1,...,fC,label` lines (the format of data_set_creation/generate_data.py:52-59), multi-threaded."""
+    X = _f32(data)
+    y = _f32(labels).reshape(-1)
+    X = X.reshape(y.shape[0], -1)
+    L.check(L.load().sgd_write_csv(os.fsencode(filename), X.shape[0], X.shape[1], _ptr(X), _ptr(y)))
+
+
 def get_filename_from_path(filepath: str) -> str:
     """sgd_io.cu:107-113."""
     buf = C.create_string_buffer(4096)
@@ -131,7 +139,8 @@ class SGDEngine:
         self.num_batches = out.reserved[0]
         self.grid, self.reduce, self.engine = out.grid, out.reduce, out.engine
         self.nslots, self.smem_bytes = out.reserved[1], out.reserved[2]
-        self.kernel_shape = (out.reserved[3], out.reserved[4], out.reserved[5])  # KC, U, NW; KC = 0: cluster kernel (U = cluster size)
+        self.kernel_shape = (out.reserved[3], out.reserved[4], out.reserved[5] & 0xff)  # KC, U, NW; KC = 0: cluster kernel (U = cluster size)
+        self.colsplit = out.reserved[5] >> 8   # COLSPLIT mapping: consumer warps along the columns (0: other mappings)
         self.cluster_size = out.reserved[4] if out.reserved[3] == 0 else 0             # CTAs of the one cluster, or 0
         self.ld = out.reserved[6]
         self.rank, self.nranks = rank, nranks
@@ -278,7 +287,9 @@ class SGDEngine:
         if kc == 0 and u > 0:
             return "sgd_cluster_epoch_kernel (%d cluster%s of %d CTAs, %d consumer warps)" % (
                 self.grid // u, "" if self.grid == u else "s", u, nw)
-        return "sgd_epoch_kernel<KC=%d,U=%d,NW=%d%s%s>" % (abs(kc), abs(u), nw, ",WIDE" if kc < 0 else "", ",NARROW8" if u < 0 else "")
+        return "sgd_epoch_kernel<KC=%d,U=%d,NW=%d%s%s%s%s>" % (
+            abs(kc), abs(u), nw, ",WIDE" if kc < 0 else "", ",NARROW8" if u < 0 else "",
+            ",CW=%d" % self.colsplit if self.colsplit else "", ",CLT" if self.reduce == L.SGD_REDUCE_CLUSTER else "")
 
     def debug_phase_cycles(self) -> np.ndarray:
         """[grid, 8] cycle sums per phase of the last launch (needs B200SGD_PHASE_PROFILE=1)."""

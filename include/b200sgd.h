@@ -110,6 +110,10 @@ int sgd_device_count(void);
  * SGD_ERR_IO when the file cannot be opened (reference: returns false, main.cu:366-370);
  * SGD_ERR_PARSE where the reference would write outside the buffers (sgd_io.cu:57-68). */
 int sgd_read_csv(const char* path, int64_t rows, int32_t cols, float* X, float* y);
+/* the inverse of read_csv: the file format of data_set_creation/generate_data.py:52-59 (csv.writer
+ * rows `f1,...,fC,label`), every value as the shortest text that parses back to the same float;
+ * written with all host cores (GB-size inputs of the benchmark's reference arm). */
+int sgd_write_csv(const char* path, int64_t rows, int32_t cols, const float* X, const float* y);
 /* replaces std::string get_filename_from_path(std::string) (sgd_io.cu:107-113) */
 int sgd_get_filename_from_path(const char* path, char* out, size_t out_cap);
 /* replaces ExperimentOutput + write_experiment_output + write_json (sgd_io.cuh:28-60,

@@ -79,7 +79,7 @@ def test_argument_validation():
     cfg = _lib.SgdConfig()
     cfg.rows, cfg.cols, cfg.batch, cfg.nranks = 0, 3, 0, 1
     assert lib.sgd_create(ctypes.byref(cfg), None, None, ctypes.byref(h)) == _lib.SGD_ERR_ARG
-    cfg.rows, cfg.batch = 10, 11
+    cfg.rows, cfg.batch = 10, -1      # (batch > rows is legal: zero steps, as main.cu:344)
     assert lib.sgd_create(ctypes.byref(cfg), None, None, ctypes.byref(h)) == _lib.SGD_ERR_ARG
     cfg.batch, cfg.nranks, cfg.rank = 5, 2, 2
     assert lib.sgd_create(ctypes.byref(cfg), None, None, ctypes.byref(h)) == _lib.SGD_ERR_ARG

@@ -18,6 +18,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EXE = os.path.join(ROOT, "cuda_sgd_sese_project_b200", "main")
 
 
+def test_cli_binary_is_not_stale():
+    # the binary is a build artefact (git-ignored): build() must have produced it after the sources
+    src = os.path.join(ROOT, "cuda_sgd_sese_project_b200", "csrc", "main.cpp")
+    lib = os.path.join(ROOT, "cuda_sgd_sese_project_b200", "libb200sgd.so")
+    assert os.path.exists(EXE), "run __graft_entry__.build() first"
+    assert os.path.getmtime(EXE) >= os.path.getmtime(src)
+    assert os.path.getmtime(EXE) >= os.path.getmtime(lib) - 1.0   # linked against the library it ships with
+
+
 def write_csv(path, X, y):
     with open(path, "w") as f:
         for row, lab in zip(X, y):

@@ -170,11 +170,31 @@ def test_batch_shapes(R, B):
     check_run(X, y, B, 0.01, 2)
 
 
-def test_batch_larger_than_rows_is_rejected():
+def test_batch_larger_than_rows_runs_zero_steps():
+    # main.cu:344: floor(R / (float)B) = 0 batches; the reference still shuffles and reports the
+    # error of the initial weights
     X, y, _ = make_regression(10, 3)
+    with pkg.SGDEngine(10, 3, 11, 0.1, data=X, labels=y) as eng:
+        assert eng.num_batches == 0
+        t = eng.iteration(1)
+        assert t["steps"] == 0 and t["samples"] == 0
+        assert np.array_equal(eng.weights, orc.init_weights(3))
+        perm = np.arange(10, dtype=np.int32)
+        orc.Rand().shuffle(perm)
+        assert np.array_equal(eng.permutation(), perm)
+        assert eng.calculate_mean_abs_error() == pytest.approx(orc.mean_abs_error(X, y, orc.init_weights(3)), rel=1e-5)
     with pytest.raises(pkg.SgdError) as ei:
-        pkg.SGDEngine(10, 3, 11, 0.1, data=X, labels=y)
+        pkg.SGDEngine(10, 3, -1, 0.1, data=X, labels=y)
     assert ei.value.code == _lib.SGD_ERR_ARG
+
+
+def test_set_permutation_rejects_duplicates():
+    with pkg.SGDEngine(100, 3, 10, 0.1) as eng:
+        bad = np.arange(100, dtype=np.int32)
+        bad[7] = 8
+        with pytest.raises(pkg.SgdError) as ei:
+            eng.set_permutation(bad)
+        assert ei.value.code == _lib.SGD_ERR_ARG
 
 
 @pytest.mark.parametrize("reduce", [_lib.SGD_REDUCE_ALLGATHER, _lib.SGD_REDUCE_SCATTER, _lib.SGD_REDUCE_DATAFLOW, _lib.SGD_REDUCE_DATAFLOW_1HOP])
@@ -188,8 +208,8 @@ def test_reduction_modes_and_grids(reduce, grid):
 def test_graph_engine(C, B, monkeypatch):
     monkeypatch.setenv("B200SGD_CLUSTER", "0")   # the persistent engine on the same (generic) kernel
     X, y, _ = make_regression(3000, C, seed=C + 1)
-    w_p, _ = check_run(X, y, B, 0.02, 2, engine=_lib.SGD_ENGINE_PERSISTENT)
-    w_g, _ = check_run(X, y, B, 0.02, 2, engine=_lib.SGD_ENGINE_GRAPH)
+    w_p, _ = check_run(X, y, B, 0.02, 2, engine=_lib.SGD_ENGINE_PERSISTENT, reduce=_lib.SGD_REDUCE_DATAFLOW)
+    w_g, _ = check_run(X, y, B, 0.02, 2, engine=_lib.SGD_ENGINE_GRAPH, reduce=_lib.SGD_REDUCE_DATAFLOW)
     assert np.array_equal(w_p, w_g)     # same kernel, same order of operations
 
 
@@ -258,7 +278,7 @@ def test_cluster_kernel_is_not_used_where_it_does_not_apply():
     (4000, 300, 1000, 2, 5),      # pairs
     (5000, 129, 777, 8, 2),       # 33 float4 columns: ragged slices (5 per CTA, the last CTA gets none... 33 = 6*5 + 3)
     (9000, 100, 4500, 8, 4),      # narrow rows (8 lanes per row) beyond the cluster kernel's reach
-    (1200, 5000, 100, 8, 0),      # column mapping (C > 2048)
+    (1200, 5000, 200, 8, 0),      # column mapping (C > 2048)
     (600, 8192, 33, 4, 2),        # slices of 512 float4 columns: two passes of 256 threads
     (2000, 1000, 2000, 8, 1),     # ONE cluster: nothing goes through L2
 ])

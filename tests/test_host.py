@@ -103,6 +103,40 @@ def test_read_csv_large_parallel_equals_oracle(tmp_path):
     assert np.array_equal(X, a[:, :C]) and np.array_equal(y, a[:, C])
 
 
+def test_write_csv_round_trips_and_special_cells(tmp_path):
+    rng = np.random.default_rng(3)
+    X = rng.standard_normal((1234, 7)).astype(np.float32)
+    X[0, 0], X[1, 1], X[2, 2] = 0.0, -0.0, 1e-30
+    X[3, 3], X[4, 4] = np.float32(3.4e38), np.float32(1.17549435e-38)
+    y = (100 * rng.standard_normal(1234)).astype(np.float32)
+    p = tmp_path / "rt.csv"
+    pkg.write_csv(str(p), X, y)
+    ok, X2, y2 = pkg.read_csv(str(p), 1234, 7)
+    assert ok and np.array_equal(X2.view(np.uint32), X.view(np.uint32)) and np.array_equal(y2, y)
+    rc, Xo, yo = orc.read_csv(str(p), 1234, 7)     # the oracle's getline / stof restatement reads the same file
+    assert rc and np.array_equal(Xo, X) and np.array_equal(yo, y)
+    # spellings std::stof accepts and from_chars alone would not: hex floats, a leading '+',
+    # trailing junk, cells longer than 63 characters; out-of-range values are rejected (stof throws)
+    q = tmp_path / "odd.csv"
+    q.write_text("0x1p3,+2.5,1.5abc," + "0." + "0" * 80 + "1,7\n")
+    ok, X3, y3 = pkg.read_csv(str(q), 1, 4)
+    assert ok and X3[0].tolist() == [8.0, 2.5, 1.5, np.float32(1e-81)] and y3[0] == 7.0
+    q.write_text("1e50,1\n")
+    with pytest.raises(pkg.SgdError):
+        pkg.read_csv(str(q), 1, 1)
+
+
+def test_batch_geometry_is_clamped_where_the_float_division_rounds_up():
+    # main.cu:344 computes floor(R / (float)B) in float: for these R it exceeds R // B
+    for R, B in ((99_999_999, 1000), (33_554_431, 4096), (2**31 - 1, 65536)):
+        f = int(np.floor(np.float32(R) / np.float32(B)))
+        assert f * B > R                                   # the reference would index past its vector
+        b, nb = pkg.batch_geometry(R, B)
+        assert (b, nb) == (B, R // B) and nb * B <= R
+    for R, B in ((10_000, 1000), (4_000_000, 1000), (67_108_864, 65536), (16_777_216, 4096), (1000, 3)):
+        assert pkg.batch_geometry(R, B) == orc.num_batches(R, B)
+
+
 def test_get_filename_from_path():
     # sgd_io.cuh docstring example: "/path/to/file.csv" -> "file"
     assert pkg.get_filename_from_path("/path/to/file.csv") == "file"

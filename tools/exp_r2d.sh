@@ -1,0 +1,7 @@
+#!/usr/bin/env bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/r2f_pytest.log 2>&1
+echo "pytest rc=$?" >> gpurun_out/r2f_pytest.log
+tail -3 gpurun_out/r2f_pytest.log
+timeout 900 python tools/sweep2.py tail > gpurun_out/r2f_tail.jsonl 2> gpurun_out/r2f_tail.err
+echo "sweep rc=$?"

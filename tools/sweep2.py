@@ -25,7 +25,7 @@ except Exception:
 
 ENV_KEYS = {"CLT": "B200SGD_CLT", "INFLIGHT_KB": "B200SGD_INFLIGHT_KB", "CLUSTERS": "B200SGD_CLUSTERS",
             "RING_TILES": "B200SGD_RING_TILES", "PROFILE": "B200SGD_PHASE_PROFILE", "CLUSTER": "B200SGD_CLUSTER",
-            "PRODUCER_WARPS": "B200SGD_PRODUCER_WARPS"}
+            "PRODUCER_WARPS": "B200SGD_PRODUCER_WARPS", "VARIANT": "B200SGD_VARIANT", "DBGSKIP": "B200SGD_DBGSKIP"}
 
 
 def run(R, C, B, lr=0.01, epochs=2, warm=1, reduce=0, grid=0, **env):
@@ -87,16 +87,20 @@ def main():
     if what == "tail":
         quick = "--quick" in sys.argv
         for (R, C, B) in SHAPES[:3] if quick else SHAPES:
-            run(R, C, B, reduce=3, INFLIGHT_KB=0, CLUSTER=0)                 # round-1 tail, whole ring in flight
-            for kb in (32, 64, 128):
-                run(R, C, B, reduce=3, INFLIGHT_KB=kb, CLUSTER=0)
-            for cs in (8, 16, 4):
-                for kb in ((0, 32, 64, 96, 128) if cs == 8 else (64,)):
-                    run(R, C, B, CLT=cs, INFLIGHT_KB=kb, CLUSTER=0)
+            run(R, C, B, reduce=3, CLUSTER=0)                 # round-1 tail (two hops through L2)
+            for cs in (8, 16):
+                run(R, C, B, CLT=cs, CLUSTER=0)
+                if C > 128:
+                    run(R, C, B, CLT=cs, CLUSTER=0, VARIANT=8)    # COLSPLIT mapping
         # where the time goes: marks of the cluster tail
         for (R, C, B) in SHAPES[:2]:
-            run(R, C, B, CLT=8, INFLIGHT_KB=64, CLUSTER=0, PROFILE=1)
-            run(R, C, B, reduce=3, INFLIGHT_KB=64, CLUSTER=0, PROFILE=1)
+            for cs in (8, 16):
+                run(R, C, B, CLT=cs, CLUSTER=0, PROFILE=1)
+                run(R, C, B, CLT=cs, CLUSTER=0, PROFILE=1, VARIANT=8)
+    elif what == "inflight":   # the round-2 negative result: bytes in flight vs step time
+        for (R, C, B) in SHAPES[:5]:
+            for kb in (0, 32, 64, 96, 128):
+                run(R, C, B, CLT=8, INFLIGHT_KB=kb, CLUSTER=0)
     elif what == "one":
         a = [int(v) for v in sys.argv[2:5]]
         kv = dict(x.split("=") for x in sys.argv[5:])
