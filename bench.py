@@ -1,31 +1,37 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the B200-native SGD engine (contract: see the task brief).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c2|c1|c4|c5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c5|c4|c4b|c2|c2p|c1]
 
 A bench "step" is ONE SGD EPOCH of the workload (BASELINE.json's metric is quoted per epoch): the
-exact per-epoch permutation + floor(R/B) fused mini-batch steps.  At N = 1 the workload is BASELINE
-configs[1] (c2: 4,000,000 x 100 fp32, batch 1000, ~1.6 GB).  At N > 1 it is weak-scaled: every GPU
-keeps 4,000,000 rows and the global batch is 1000*N, so each GPU processes ~1000 rows per step and
-the d-float gradient is exchanged over NVLink inside the step kernel.
+bit-exact per-epoch permutation + floor(R/B) fused mini-batch steps.  The default workload is
+BASELINE configs[4], the 128 GB data-parallel configuration: 67,108,864 x 512 fp32 rows, batch 65536
+(1024 steps per epoch).  It fits ONE B200 (141.7 GB of records), so every N runs the SAME total
+problem ("scaling": "strong"): N = 1 keeps all rows on one GPU and a step streams 65536 rows; at N
+GPUs the rows are sharded, each GPU processes its ~65536/N rows of every step and the d-float
+gradient is exchanged over NVLink inside the step kernel.
 
 One JSON line on stdout (rank 0):
   value      samples/s over K epochs with the data resident in HBM, INCLUDING whatever part of the
              bit-exact permutation is not hidden behind the previous epoch (what the reference's
              gpu_time covers, main.cu:444-514); wall clock between barriers + synchronize, max over ranks
   steploop   samples/s and GB/s of the step loop alone (CUDA events around the epoch kernels)
-  roofline   the dominant kernel (sgd_epoch_kernel): algorithmic bytes / CUDA-event time vs the
-             measured HBM copy peak (MEASURED_PEAKS.json)
-  e2e        same metric through the C-ABI from HOST buffers: sgd_create (H2D of the data set from
-             pinned memory) + K epochs (H2D of each permutation) + weights/MAE read-back; one warm
-             pass, then the median of three timed passes (all three are listed)
-  roofline   (c2: the dominant kernel is sgd_cluster_epoch_kernel, see config.kernel)
-  cpu_baseline  OpenMP port of the reference's plain-CUDA path (oracle/, kind "port") on the host cores
+  roofline   the dominant kernel (sgd_epoch_kernel, one launch per epoch): algorithmic bytes /
+             CUDA-event time vs the measured HBM copy peak (MEASURED_PEAKS.json)
+  e2e        the same metric through the C-ABI from pinned HOST buffers on a bounded slice of the
+             workload (same C and B; the host cannot hold 142 GB): sgd_create + H2D of the rows +
+             K epochs + weights / MAE read-back; median of three timed passes
+  sweep      (N = 1) CUDA-event us per SGD step, GB/s and fraction of the HBM peak for BASELINE
+             configs[1..3]: c2 (4M x 100, B = 1000), c3 (B = 10 .. 100k), c4 (16.7M x 2048, B = 4096 and 65536)
+  quality    MAE, distance to the generating weights, the golden permutation checksum (real glibc +
+             libstdc++ run, tests/golden/thirdparty_kat.json) and, at N > 1, a small sharded problem
+             against the CPU oracle inside the same job (rel-L2 of the weights, replicas bit-identical)
+  cpu_baseline  (N = 1) OpenMP port of the reference's plain-CUDA path (oracle/, kind "port") on the host cores
 
---impl reference times the UNMODIFIED reference binary (oracle/_ref/main, its cuBLAS code path,
-cudaRun = 0) on the same B200 on a bounded sample of the workload (same C and B, fewer rows; its
-per-step cost does not depend on R).  The reference is a CUDA program and has no CPU path; if the
-binary is missing or fails, the OpenMP port is timed instead and the line says so.
+--impl reference times the UNMODIFIED reference binary (oracle/_ref/main) on the same B200 on a
+bounded sample of the workload (same C and B, fewer rows), BOTH of its code paths, three
+repetitions each (median); `value` is the faster path.  The reference is a CUDA program and has no
+CPU path; if the binary is missing or fails, the OpenMP port is timed instead and the line says so.
 """
 from __future__ import annotations
 
@@ -46,16 +52,18 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (rows per GPU, cols, batch per GPU, lr)
-    "c1": (10_000, 100, 1000, 0.1),
-    "c2": (4_000_000, 100, 1000, 0.1),
+    # name: (rows of the WHOLE job, cols, batch, lr, BASELINE config)
+    "c1": (10_000, 100, 1000, 0.1, "configs[0]"),
+    "c2": (4_000_000, 100, 1000, 0.1, "configs[1]"),
     # the report's own ~1.6 GB case (sese_report_tvas.tex:690-706, source of the README's "~5x"): 200k x 2k
-    "c2p": (200_000, 2000, 1000, 0.02),
-    "c4": (16_777_216, 2048, 4096, 0.1),     # 137 GB: one GPU holds it
-    "c4b": (16_777_216, 2048, 65536, 0.1),
-    "c5": (8_388_608, 512, 8192, 0.1),       # x8 GPUs = 64M x 512, batch 65536
+    "c2p": (200_000, 2000, 1000, 0.02, "report table"),
+    "c4": (16_777_216, 2048, 4096, 0.1, "configs[3]"),     # 138.5 GB: one GPU holds it
+    "c4b": (16_777_216, 2048, 65536, 0.1, "configs[3]"),
+    "c5": (67_108_864, 512, 65536, 0.1, "configs[4]"),      # 141.7 GB: one GPU holds it
 }
 FALLBACK_HBM_GBS = 6650.0  # B200_PROFILING.md fallback
+REDUCE_NAMES = {1: "allgather", 2: "scatter", 3: "dataflow-2hop", 4: "dataflow-1hop",
+                5: "cluster (DSMEM reduce-scatter + one tagged L2/NVLink hop + DSMEM all-gather)"}
 
 
 def measured_peaks():
@@ -102,7 +110,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.02)
+            self._stop.wait(0.01)
 
     def start(self):
         if self.nv is not None:
@@ -118,13 +126,40 @@ class ClockSampler:
                 "samples": len(self.samples)}
 
 
-def profile_traffic(workload: str):
-    """dram bytes per launch of the epoch kernel from the committed ncu --set full capture."""
+def profile_traffic(key: str):
+    """dram bytes per launch of the epoch kernel from the committed ncu --set full capture of THIS
+    shape (profiles/roofline_traffic.json), or None when the shape has no capture."""
     try:
         with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
-            return json.load(f).get(workload)
+            return json.load(f).get(key)
     except Exception:
         return None
+
+
+def perm_checksum(perm: np.ndarray) -> int:
+    """sum_i (i+1) * perm[i] mod 2^64: the checksum of tests/golden/thirdparty_kat.json."""
+    i = np.arange(1, perm.shape[0] + 1, dtype=np.uint64)
+    return int((i * perm.astype(np.uint64)).sum(dtype=np.uint64))
+
+
+def golden_perm(R: int, epoch: int):
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", "thirdparty_kat.json")) as f:
+            for r in json.load(f)["shuffle_kat"]:
+                if r["R"] == R and r["epoch"] == epoch:
+                    return r
+    except Exception:
+        pass
+    return None
+
+
+def synth(R, C, seed):
+    """The distribution of data_set_creation/generate_data.py:22-39 (X ~ N(0,1), w* ~ 100 U(0,1), y = X w*)."""
+    rng = np.random.default_rng(seed)
+    X = rng.standard_normal((R, C)).astype(np.float32)
+    w_true = (100.0 * rng.random(C)).astype(np.float32)
+    y = (X.astype(np.float64) @ w_true.astype(np.float64)).astype(np.float32)
+    return X, y
 
 
 # ------------------------------------------------------------------------------- CPU baseline
@@ -139,8 +174,8 @@ def cpu_port_baseline(X, y, B, lr, epochs):
     ind = np.arange(R, dtype=np.int32)
     g = orc.Rand()
     g.shuffle(ind)
-    orc.epoch(X[: min(R, 50 * B)], y[: min(R, 50 * B)], B, np.arange(min(R, 50 * B), dtype=np.int32), w.copy(), lr, 1,
-              threads=threads)  # warm the thread pool
+    nw = min(R, max(B, 50_000) // B * B if B <= R else R)
+    orc.epoch(X[:nw], y[:nw], B, np.arange(nw, dtype=np.int32), w.copy(), lr, 1, threads=threads)  # warm the thread pool
     t0 = time.perf_counter()
     for e in range(1, epochs + 1):
         g.shuffle(ind)
@@ -150,68 +185,64 @@ def cpu_port_baseline(X, y, B, lr, epochs):
 
 
 # ------------------------------------------------------------------------------- reference arm
-def reference_arm(args, cols, batch, lr):
+def reference_arm(args, name, cols, batch, lr):
     import torch
     ref = os.path.join(ROOT, "oracle", "_ref", "main")
     K, W = args.steps, args.warmup
-    sample_rows = args.ref_rows
-    rng = np.random.default_rng(42)
-    X = rng.standard_normal((sample_rows, cols)).astype(np.float32)
-    w_true = (100.0 * rng.random(cols)).astype(np.float32)
-    y = (X @ w_true).astype(np.float32)
+    sample_rows = args.ref_rows or max(2 * batch, min(262_144, (100_000_000 // (cols + 1)) // batch * batch))
+    X, y = synth(sample_rows, cols, 42)
     nb = int(np.floor(np.float32(sample_rows) / np.float32(batch)))
     line = {"impl": "reference", "metric": "samples_per_sec_per_sgd_epoch", "unit": "samples/s",
-            "n_gpus": args.gpus, "steps": K, "warmup": W, "higher_is_better": True, "scaling": "weak",
+            "n_gpus": args.gpus, "steps": K, "warmup": W, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: sample of {sample_rows} x {cols} fp32 rows, batch {batch}, "
-                                   f"lr {lr} (same C and B as the workload; the reference's per-step cost "
-                                   "does not depend on R)", "l2": "not flushed: reference run as shipped"}}
+            "config": {"workload": f"{name}: bounded sample of {sample_rows} x {cols} fp32 rows, batch {batch}, lr {lr} "
+                                   f"(same C and B as the workload, {nb} steps per epoch; the reference indexes elements "
+                                   "with 32-bit int, sgd_thrust.cuh:128-133, keeps a 2x shuffled copy, main.cu:413, and "
+                                   "reads its data from a CSV, so the 142 GB workload is out of its reach)",
+                       "l2": "not flushed: reference run as shipped"}}
     ok = False
     if os.path.exists(ref) and torch.cuda.is_available():
+        import cuda_sgd_sese_project_b200 as pkg
         with tempfile.TemporaryDirectory() as tmp:
             csv = os.path.join(tmp, "bench_sample.csv")
-            with open(csv, "w") as f:
-                for row, lab in zip(X, y):
-                    f.write(",".join("%.9g" % v for v in row) + ",%.9g\n" % lab)
+            pkg.write_csv(csv, X, y)   # sgd_write_csv: host-side utility of the library, not on the timed path
 
-            def run(epochs, cuda_run="0"):
+            def run(epochs, cuda_run):
                 r = subprocess.run([ref, repr(lr), str(epochs), csv, str(sample_rows), str(cols), str(batch), cuda_run],
                                    capture_output=True, text=True, cwd=tmp, timeout=1500)
                 if r.returncode != 0:
                     raise RuntimeError(r.stderr[-500:])
                 return float(re.search(r"GPU time = (\S+) ms", r.stdout).group(1))
-            def timed_ms(cuda_run):
-                """gpu_time of the K timed epochs: gpu_time(W + K epochs) - gpu_time(W epochs) of two runs.
-                Every run pays CUDA / cuBLAS start-up inside its gpu_time with a jitter of hundreds of ms, so
-                for a small K the difference can come out near zero or negative; then the average epoch of
-                the long run (start-up included: an upper bound of the epoch time) stands in."""
-                run(1, cuda_run)  # discarded: the first start of the binary on a fresh box pays one-time library loads
-                t_w = run(W, cuda_run) if W > 0 else 0.0
-                t_all = run(W + K, cuda_run)
-                avg = t_all * K / (W + K)
-                diff = t_all - t_w
-                ok_diff = 0.25 * avg <= diff <= t_all
-                return (diff if ok_diff else avg), {"gpu_time_ms_all": t_all, "gpu_time_ms_warmup": t_w,
-                                                    "method": "difference of two runs" if ok_diff else
-                                                              "average epoch of the long run (difference implausible)"}
+
+            def timed(cuda_run):
+                """median over three runs of gpu_time(W + K epochs) / (W + K) * K: the reference's own timer
+                (main.cu:444-514) spans the whole epoch loop of a process, so its warm-up epochs cannot be
+                cut out; they are run and averaged in (an upper bound of the steady-state epoch)."""
+                run(1, cuda_run)   # discarded: the first start of the binary on a fresh box pays one-time library loads
+                reps = sorted(run(W + K, cuda_run) for _ in range(3))
+                ms = reps[1] * K / (W + K)
+                return ms, {"gpu_time_ms_of_W_plus_K_epochs": reps, "method": "median of 3 runs, scaled to K epochs"}
             try:
-                ms, how = timed_ms("0")
-                value = K * nb * batch / (ms * 1e-3)
-                line["reference_timing"] = how
-                # for the record: the reference's other code path (cudaRun = 1, plain CUDA kernel +
-                # Thrust), which on a B200 is the faster of the two (no cublasCreate per step)
-                try:
-                    ms1, how1 = timed_ms("1")
-                    line["reference_plain_cuda_path"] = {"value": K * nb * batch / (ms1 * 1e-3), "unit": "samples/s",
-                                                         "ms_per_step": ms1 / K, "timing": how1}
-                except Exception as ex:
-                    line["reference_plain_cuda_path"] = {"error": str(ex)[:120]}
-                line.update({"value": value, "ms_per_step": ms / K,
-                             "cpu_baseline": {"value": value, "unit": "samples/s", "cores": 1, "kind": "reference",
-                                              "sample": f"unmodified reference binary (cuBLAS code path, cudaRun=0) on the "
-                                                        f"B200 -- the reference has no CPU path; {sample_rows} rows, "
-                                                        f"gpu_time({W + K} epochs) - gpu_time({W} epochs)"}})
-                ok = True
+                paths = {}
+                for cuda_run, label in (("0", "cublas"), ("1", "plain_cuda")):
+                    try:
+                        ms, how = timed(cuda_run)
+                        paths[label] = {"value": K * nb * batch / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms / K,
+                                        "timing": how}
+                    except Exception as ex:
+                        paths[label] = {"error": str(ex)[:160]}
+                good = {k: v for k, v in paths.items() if "value" in v}
+                if good:
+                    best = max(good, key=lambda k: good[k]["value"])
+                    line["reference_paths"] = paths
+                    line.update({"value": good[best]["value"], "ms_per_step": good[best]["ms_per_step"],
+                                 "cpu_baseline": {"value": good[best]["value"], "unit": "samples/s", "cores": 1, "kind": "reference",
+                                                  "sample": f"unmodified reference binary on the B200 (it has no CPU path), the faster of "
+                                                            f"its two code paths here: {best} (cudaRun={'0' if best == 'cublas' else '1'}); "
+                                                            f"{sample_rows} rows, median of 3 runs of {W + K} epochs"}})
+                    ok = True
+                else:
+                    line["reference_binary_error"] = json.dumps(paths)[:300]
             except Exception as ex:  # fall through to the port
                 line["reference_binary_error"] = str(ex)[:200]
     if not ok:
@@ -224,6 +255,74 @@ def reference_arm(args, cols, batch, lr):
     return line
 
 
+# ------------------------------------------------------------------------------- sweep (N = 1)
+def sweep_entry(pkg, peak, label, R, C, B, lr, epochs=2, warm=1):
+    """CUDA-event time of the step loop of one shape on one GPU (one launch per epoch)."""
+    try:
+        with pkg.SGDEngine(R, C, B, lr) as eng:
+            eng.load_synthetic(seed=42)
+            eng.shuffle()
+            for e in range(warm):
+                eng.epoch(1 + e)
+            best = None
+            for e in range(epochs):
+                t = eng.epoch(1 + warm + e)
+                if best is None or t["steploop_ms"] < best["steploop_ms"]:
+                    best = t
+            gbs = best["bytes"] / (best["steploop_ms"] * 1e-3) * 1e-9
+            return {"config": label, "rows": R, "cols": C, "batch": B, "steps_per_epoch": best["steps"],
+                    "us_per_sgd_step": round(best["steploop_ms"] * 1e3 / max(1, best["steps"]), 3),
+                    "hbm_gbs": round(gbs, 1), "frac_of_peak": round(gbs / peak, 4),
+                    "msamples_per_s": round(best["samples"] / (best["steploop_ms"] * 1e-3) * 1e-6, 1),
+                    "kernel": eng.kernel_name, "grid": eng.grid,
+                    "weights_finite": bool(np.all(np.isfinite(eng.weights)))}
+    except Exception as ex:
+        return {"config": label, "rows": R, "cols": C, "batch": B, "error": str(ex)[:160]}
+
+
+def run_sweep(pkg, peak, clocks_index):
+    sampler = ClockSampler(clocks_index)
+    sampler.start()
+    out = [sweep_entry(pkg, peak, "c2 (configs[1])", 4_000_000, 100, 1000, 0.1)]
+    for B in (10, 100, 4096, 10_000, 100_000):
+        out.append(sweep_entry(pkg, peak, "c3 (configs[2])", 4_000_000, 100, B, 0.001,
+                               epochs=2 if B >= 100 else 1, warm=1 if B >= 100 else 0))
+    out.append(sweep_entry(pkg, peak, "c4 (configs[3]) B=4096", 16_777_216, 2048, 4096, 0.1))
+    out.append(sweep_entry(pkg, peak, "c4 (configs[3]) B=65536", 16_777_216, 2048, 65536, 0.1))
+    return {"note": "one GPU, step loop only (CUDA events around the epoch kernel), best of 2 epochs after 1 warm-up; "
+                    "inputs larger than L2", "clocks": sampler.stop(), "entries": out}
+
+
+# ------------------------------------------------------------------------------- multi-GPU parity (N > 1)
+def multi_gpu_parity(pkg, connect_peers, dist, torch, rank, N, local_rank):
+    """Small sharded problems against the CPU oracle inside the same job (checker only)."""
+    from oracle import loader as orc
+    res = []
+    for (R, C, B, lr, epochs) in ((40_000, 100, 1000, 0.05, 2), (50_000, 512, 4096, 0.05, 2)):
+        X, y = synth(R, C, 11)
+        eng = pkg.SGDEngine(R, C, B, lr, device=local_rank, rank=rank, nranks=N)
+        b, e = pkg.shard_range(R, rank, N)
+        eng.load_rows(b, X[b:e], y[b:e])
+        connect_peers(eng)
+        eng.run(1, epochs)
+        w = eng.weights
+        perm = eng.permutation()
+        s = torch.tensor([eng.abs_error_sum()], dtype=torch.float64, device="cuda")
+        dist.all_reduce(s)
+        kernel = eng.kernel_name
+        eng.close()
+        ws = [None] * N
+        dist.all_gather_object(ws, w.tobytes())
+        if rank == 0:
+            mae_o, w_o, ind_o = orc.run(X, y, B, lr, epochs)
+            rel = float(np.linalg.norm(w.astype(np.float64) - w_o) / np.linalg.norm(w_o))
+            res.append({"shape": f"{R}x{C}, B={B}, {epochs} epochs", "kernel": kernel,
+                        "multi_gpu_rel_l2_vs_oracle": rel, "replicas_bit_identical": all(b2 == ws[0] for b2 in ws),
+                        "permutation_bit_exact_vs_oracle": bool(np.array_equal(perm, ind_o)),
+                        "mae": float(s[0]) / R, "mae_oracle": mae_o})
+    return res
+
+
 # ------------------------------------------------------------------------------- our arm
 def main() -> int:
     ap = argparse.ArgumentParser()
@@ -231,31 +330,33 @@ def main() -> int:
     ap.add_argument("--steps", type=int, default=10, help="timed epochs")
     ap.add_argument("--warmup", type=int, default=3, help="untimed warm-up epochs (>= 3)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--rows", type=int, default=0, help="override rows per GPU")
+    ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
+    ap.add_argument("--rows", type=int, default=0, help="override the rows of the whole job")
     ap.add_argument("--cols", type=int, default=0)
-    ap.add_argument("--batch", type=int, default=0, help="override batch per GPU")
+    ap.add_argument("--batch", type=int, default=0, help="override the (global) batch")
     ap.add_argument("--engine", default="persistent", choices=["persistent", "graph"])
     ap.add_argument("--grid", type=int, default=0)
-    ap.add_argument("--reduce", default="auto", choices=["auto", "allgather", "scatter", "dataflow", "dataflow1"])
-    ap.add_argument("--ref-rows", type=int, default=100_000)
+    ap.add_argument("--reduce", default="auto", choices=["auto", "allgather", "scatter", "dataflow", "dataflow1", "cluster"])
+    ap.add_argument("--ref-rows", type=int, default=0)
+    ap.add_argument("--e2e-rows", type=int, default=0, help="rows of the bounded host-buffer slice (default: <= 8 GiB)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--cpu-epochs", type=int, default=100, help="epochs of the bounded cpu_baseline sample")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU seconds of the bounded cpu_baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the configs[1..3] sweep (N = 1)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    rows_pg, cols, batch_pg, lr = WORKLOADS[args.workload]
-    rows_pg = args.rows or rows_pg
+    R, cols, B, lr, cfg_name = WORKLOADS[args.workload]
+    R = args.rows or R
     cols = args.cols or cols
-    batch_pg = args.batch or batch_pg
+    B = args.batch or B
 
     if args.impl == "reference":
         if rank != 0:
             return 0
-        print(json.dumps(reference_arm(args, cols, batch_pg, lr)), flush=True)
+        print(json.dumps(reference_arm(args, args.workload, cols, B, lr)), flush=True)
         return 0
 
     import torch
@@ -263,6 +364,7 @@ def main() -> int:
 
     import cuda_sgd_sese_project_b200 as pkg
     from cuda_sgd_sese_project_b200 import _lib
+    from cuda_sgd_sese_project_b200.dist import connect_peers
 
     if not torch.cuda.is_available() or pkg.device_count() < 1:
         raise SystemExit("bench.py needs a B200: the engine has no CPU fallback")
@@ -273,24 +375,42 @@ def main() -> int:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     assert N == args.gpus or world == 1, "launch with torchrun --nproc-per-node N for --gpus N"
 
-    R, B = rows_pg * N, batch_pg * N
     K, W = args.steps, max(args.warmup, 3)
-    eng = pkg.SGDEngine(R, cols, B, lr, device=local_rank, rank=rank, nranks=N,
-                        engine=_lib.SGD_ENGINE_GRAPH if args.engine == "graph" else _lib.SGD_ENGINE_PERSISTENT,
-                        reduce={"auto": 0, "allgather": 1, "scatter": 2, "dataflow": 3, "dataflow1": 4}[args.reduce], grid=args.grid)
+    kw = dict(device=local_rank, rank=rank, nranks=N,
+              engine=_lib.SGD_ENGINE_GRAPH if args.engine == "graph" else _lib.SGD_ENGINE_PERSISTENT,
+              reduce={"auto": 0, "allgather": 1, "scatter": 2, "dataflow": 3, "dataflow1": 4, "cluster": 5}[args.reduce], grid=args.grid)
+    eng = pkg.SGDEngine(R, cols, B, lr, **kw)
     eng.load_synthetic(seed=42)
-    from cuda_sgd_sese_project_b200.dist import connect_peers
     if N > 1:
         connect_peers(eng)
+    rows_pg = eng.local_rows
 
     def barrier():
         if N > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- value: K epochs, data resident, permutation pipeline included
-    eng.run(1, W)
+    # ---- warm-up: W epochs; the permutations of epochs 1 and 2 are checked against the golden vectors
+    # produced by the real glibc rand() + libstdc++ random_shuffle (tests/golden/thirdparty_kat.json)
+    perm_check = []
+    done = 0
+    for e in (1, 2):
+        gold = golden_perm(R, e)
+        if gold is None or W < e:
+            break
+        eng.run(done + 1, e - done)
+        done = e
+        if rank == 0:
+            p = eng.permutation()
+            cs = perm_checksum(p)
+            perm_check.append({"epoch": e, "rows": R, "checksum": cs, "golden": gold["checksum"],
+                               "match": bool(cs == gold["checksum"] and p[:4].tolist() == gold["head"] and int(p[-1]) == gold["last"])})
+            del p
+    if W > done:
+        eng.run(done + 1, W - done)
     barrier()
+
+    # ---- value: K epochs, data resident, permutation pipeline included
     sampler = ClockSampler(local_rank)
     sampler.start()
     t0 = time.perf_counter()
@@ -310,30 +430,43 @@ def main() -> int:
     mae = float(mae_sum[0]) / R
     w_final = eng.weights
     w_err = float(np.linalg.norm(w_final - eng.true_weights()) / np.linalg.norm(eng.true_weights()))
+    replicas_identical = None
+    if N > 1:
+        ws = [None] * N
+        dist.all_gather_object(ws, w_final.tobytes())
+        replicas_identical = all(b2 == ws[0] for b2 in ws)
+    kernel_name, grid, reduce_mode = eng.kernel_name, eng.grid, eng.reduce
+    ring_rows, smem_bytes, cluster_size = eng.nslots, eng.smem_bytes, eng.cluster_size
 
-    # ---- e2e: through the C-ABI from pinned HOST buffers, at N GPUs: every rank holds its row
-    # shard in pinned host memory; the timed region has sgd_create, the H2D of the shard, K epochs
-    # (permutation state upload inside), the weights and MAE read-back
+    # ---- bounded host slice for e2e / cpu_baseline: the first rows of every rank's shard
     e2e = None
     cpu = None
-    if not args.no_e2e and rows_pg * (cols + 1) * 4 <= (24 << 30):
-        rb, nloc = eng.local_row_begin, eng.local_rows
+    e2e_rows = args.e2e_rows or min(R, max(B, ((8 << 30) // (4 * (cols + 1))) // B * B))
+    e2e_rows = min(e2e_rows, R)
+    need_host = (not args.no_e2e) or (N == 1 and not args.no_cpu)
+    if need_host:
+        rb_e, re_e = pkg.shard_range(e2e_rows, rank, N)          # this rank's shard of the e2e problem
+        nloc = re_e - rb_e
         Xh = torch.empty((nloc, cols), dtype=torch.float32, pin_memory=True)
         yh = torch.empty((nloc,), dtype=torch.float32, pin_memory=True)
-        Xn, yn = eng.get_rows(rb, nloc)
-        Xh.numpy()[:] = Xn
-        yh.numpy()[:] = yn
-        del Xn, yn
-        eng.close()
-        kw = dict(device=local_rank, rank=rank, nranks=N,
-                  engine=_lib.SGD_ENGINE_GRAPH if args.engine == "graph" else _lib.SGD_ENGINE_PERSISTENT,
-                  reduce={"auto": 0, "allgather": 1, "scatter": 2, "dataflow": 3, "dataflow1": 4}[args.reduce], grid=args.grid)
+        step_rows = max(1, (256 << 20) // (4 * (cols + 1)))
+        for r0 in range(0, nloc, step_rows):                     # rows of this rank's OWN shard of the big problem
+            n = min(step_rows, nloc - r0)
+            Xn, yn = eng.get_rows(eng.local_row_begin + r0, n)
+            Xh.numpy()[r0:r0 + n] = Xn
+            yh.numpy()[r0:r0 + n] = yn
+            del Xn, yn
+    eng.close()
+
+    if not args.no_e2e:
+        # through the C-ABI from pinned HOST buffers at N GPUs: the timed region has sgd_create, the H2D
+        # of the shard, K epochs (permutation state upload inside), the weights and MAE read-back
         passes = []
         for it in range(4):  # first pass warms allocator / page tables; three timed passes, the median is reported
             barrier()
             t0 = time.perf_counter()
-            e2 = pkg.SGDEngine(R, cols, B, lr, **kw)
-            e2.load_rows_ptr(rb, nloc, Xh.data_ptr(), yh.data_ptr())   # H2D from pinned memory
+            e2 = pkg.SGDEngine(e2e_rows, cols, B, lr, **kw)
+            e2.load_rows_ptr(rb_e, nloc, Xh.data_ptr(), yh.data_ptr())   # H2D from pinned memory
             if N > 1:
                 connect_peers(e2)
             te = e2.run(1, K)
@@ -351,55 +484,82 @@ def main() -> int:
         passes = sorted(float(v) for v in dts)
         dt = passes[len(passes) // 2]
         e2e = {"value": te["samples"] / dt, "unit": "samples/s",
-               "h2d_bytes_per_step": int((4 * R * (cols + 1) + K * 31 * 4 * 8192) / K),
+               "h2d_bytes_per_step": int((4 * e2e_rows * (cols + 1) + K * 31 * 4 * 8192) / K),
                "d2h_bytes_per_step": int(N * (4 * cols + 8 * 148 * 8) / K),
-               "seconds": dt, "seconds_all_passes": passes, "note": "median of three passes of: sgd_create + upload of every rank's row shard from pinned host memory + "
-                                      f"{K} epochs + weights and MAE read-back, amortised over the {K} epochs; max over ranks",
-               "mae": float(s_e2e[0]) / R}
-        # ---- cpu_baseline (rank 0, N = 1): OpenMP port on the host cores, bounded sample
-        if N == 1 and not args.no_cpu:
-            sample = min(R, 4_000_000)
-            cpu_epochs = args.cpu_epochs
-            v, threads, dtc = cpu_port_baseline(Xh.numpy()[:sample], yh.numpy()[:sample], B, lr, cpu_epochs)
-            cpu = {"value": v, "unit": "samples/s", "cores": threads, "kind": "port",
-                   "sample": f"first {sample} rows of the workload (same C = {cols}, B = {B}), {cpu_epochs} epochs incl. the "
-                             f"exact shuffle, OpenMP port of the reference's plain-CUDA path, {dtc:.1f} s of CPU work"}
-    else:
-        eng.close()
+               "rows": e2e_rows, "seconds": dt, "seconds_all_passes": passes,
+               "note": f"bounded slice of the workload: {e2e_rows} x {cols} rows from pinned host memory (same C and B; the host "
+                       f"cannot hold the 142 GB data set).  Median of three passes of: sgd_create + upload of every rank's "
+                       f"row shard + {K} epochs + weights and MAE read-back, amortised over the {K} epochs; max over ranks",
+               "mae": float(s_e2e[0]) / e2e_rows}
+
+    # ---- cpu_baseline (rank 0, N = 1): OpenMP port on the host cores, bounded sample
+    if N == 1 and not args.no_cpu:
+        sample = min(e2e_rows, max(B, (1 << 20) // B * B))
+        Xs, ys = Xh.numpy()[:sample], yh.numpy()[:sample]
+        v1, threads, dt1 = cpu_port_baseline(Xs, ys, B, lr, 1)          # calibrate: one epoch
+        cpu_epochs = int(max(1, min(200, args.cpu_seconds / max(dt1, 1e-3))))
+        v, threads, dtc = cpu_port_baseline(Xs, ys, B, lr, cpu_epochs)
+        cpu = {"value": v, "unit": "samples/s", "cores": threads, "kind": "port",
+               "sample": f"first {sample} rows of the workload (same C = {cols}, B = {B}), {cpu_epochs} epochs incl. the "
+                         f"exact shuffle, OpenMP port of the reference's plain-CUDA path, {dtc:.1f} s of CPU work"}
+    if need_host:
+        del Xh, yh
+
+    parity = None
+    if N > 1:
+        parity = multi_gpu_parity(pkg, connect_peers, dist, torch, rank, N, local_rank)
+
+    sweep = None
+    if N == 1 and not args.no_sweep and rank == 0:
+        sweep = run_sweep(pkg, measured_peaks()[0], local_rank)
 
     if rank == 0:
         peak, peak_src = measured_peaks()
         achieved = bytes_rank / loop_s * 1e-9                      # GB/s per GPU, step loop
         steps_epoch = t["steps"] // K
+        rows_step_gpu = B / N
+        traffic_key = f"{args.workload}_n{N}"
         line = {
             "metric": "samples_per_sec_per_sgd_epoch", "value": samples / wall, "unit": "samples/s",
             "n_gpus": N, "steps": K, "warmup": W, "ms_per_step": wall * 1e3 / K,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {R} x {cols} fp32 rows ({4 * R * (cols + 1) / 1e9:.2f} GB, "
-                                   f"{rows_pg} rows per GPU), batch {B}, lr {lr}, {steps_epoch} steps per epoch; "
-                                   "one bench step = one SGD epoch incl. its bit-exact permutation",
+            "config": {"workload": f"{args.workload} (BASELINE {cfg_name}): {R} x {cols} fp32 rows ({4 * R * (cols + 1) / 1e9:.1f} GB, "
+                                   f"{rows_pg} rows on every GPU), batch {B} ({rows_step_gpu:.0f} rows per GPU and step), lr {lr}, "
+                                   f"{steps_epoch} steps per epoch; one bench step = one SGD epoch incl. its bit-exact permutation; "
+                                   "the same total problem at every N",
                        "l2": "inputs larger than L2 (per-GPU data %.1f GB vs 126 MB)" % (4 * rows_pg * (cols + 1) / 1e9),
-                       "engine": args.engine, "grid": eng.grid,
-                       "reduce": ("cluster all-gather in shared memory" + (" + L2 hop between clusters" if eng.grid > eng.cluster_size else "")) if eng.cluster_size else
-                                 {1: "allgather", 2: "scatter", 3: "dataflow-2hop", 4: "dataflow-1hop"}[eng.reduce],
-                       "kernel": eng.kernel_name,
-                       "ring_slots": eng.nslots, "smem_bytes": eng.smem_bytes,
-                       "parallelism": f"dp{N} row-sharded, fused NVLink gradient exchange" if N > 1 else "single GPU"},
+                       "engine": args.engine, "grid": grid,
+                       "reduce": ("cluster all-gather in shared memory" + (" + L2 hop between clusters" if grid > cluster_size else "")) if cluster_size else
+                                 REDUCE_NAMES.get(reduce_mode, str(reduce_mode)),
+                       "kernel": kernel_name,
+                       "ring_rows": ring_rows, "smem_bytes": smem_bytes,
+                       "parallelism": f"dp{N} row-sharded, fused NVLink gradient exchange inside the step kernel" if N > 1 else "single GPU"},
             "steploop": {"samples_per_s": samples / loop_s, "ms_per_epoch": loop_s * 1e3 / K,
-                         "us_per_sgd_step": loop_s * 1e6 / t["steps"], "hbm_gbs_per_gpu": achieved},
+                         "us_per_sgd_step": loop_s * 1e6 / t["steps"], "hbm_gbs_per_gpu": achieved,
+                         "rows_per_gpu_and_step": rows_step_gpu},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": profile_traffic(args.workload),
-                         "peak_source": peak_src, "kernel": eng.kernel_name.split("<")[0].split(" (")[0] + " (1 launch per epoch)",
-                         "algorithmic_bytes_per_launch": bytes_rank // K},
+                         "frac": achieved / peak, "traffic": profile_traffic(traffic_key),
+                         "peak_source": peak_src, "kernel": kernel_name.split("<")[0].split(" (")[0] + " (1 launch per epoch)",
+                         "algorithmic_bytes_per_launch": bytes_rank // K,
+                         "step": f"{rows_step_gpu:.0f} rows x {cols} features per GPU"},
             "clocks": clocks,
             "gpu_launches": t["launches"],
-            "quality": {"mae": mae, "weights_rel_err_vs_generating_weights": w_err},
+            "quality": {"mae": mae, "weights_rel_err_vs_generating_weights": w_err,
+                        "permutation_golden_check": perm_check},
         }
+        if replicas_identical is not None:
+            line["quality"]["replicas_bit_identical"] = replicas_identical
+        if parity is not None:
+            line["quality"]["multi_gpu_parity_vs_oracle"] = parity
+            if parity:
+                line["quality"]["multi_gpu_rel_l2_vs_oracle"] = max(p["multi_gpu_rel_l2_vs_oracle"] for p in parity)
         if e2e is not None:
             line["e2e"] = e2e
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if sweep is not None:
+            line["sweep"] = sweep
         print(json.dumps(line), flush=True)
     if N > 1:
         dist.barrier()

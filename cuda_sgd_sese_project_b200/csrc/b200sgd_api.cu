@@ -185,6 +185,17 @@ struct sgd_ctx {
   int32_t *d_cnt = nullptr, *d_start = nullptr, *d_hits = nullptr, *d_first = nullptr, *d_tilesum = nullptr;
   int32_t scan_tiles = 0;
   bool host_ind_stale = false;  // h_ind lags behind the device permutation
+  // several ranks: the permutation work is shared (shuffle_kernels.cuh): rank (k-1) % nranks computes
+  // the position map of shuffle k ahead of time, everybody applies it with one gather pass
+  bool shared_shuffle = false;     // buffers exist (device shuffle, nranks > 1); used once the peers are connected
+  int64_t shuf_no = 0;             // shuffles performed so far (the same number on every rank)
+  int64_t own_next = 0;            // next shuffle this rank computes the map of
+  int64_t shared_first = 0;        // number of the first shuffle done the shared way (earlier ones: every rank on its own)
+  b200sgd::GlibcRand rng_own;      // stands at the start of shuffle own_next's stream
+  size_t flag_off = 0, src_off[2] = {0, 0};  // byte offsets of the flags / the two map buffers in the exchange block
+  cudaStream_t own_stream = nullptr;
+  cudaEvent_t ev_own_up[2] = {nullptr, nullptr};  // upload out of h_states_own[i] finished
+  uint32_t* h_states_own[2] = {nullptr, nullptr};
 
   // host permutation state
   std::vector<int32_t> h_ind;                // the reference's ind_vector (main.cu:421-424)
@@ -268,8 +279,14 @@ void free_all(sgd_ctx* c) {
   cudaFree(c->d_ll_part); cudaFree(c->d_ll_w); cudaFree(c->d_dbg); cudaFree(c->d_loss);
   cudaFree(c->d_tgt); cudaFree(c->d_cnt); cudaFree(c->d_start); cudaFree(c->d_hits); cudaFree(c->d_first);
   cudaFree(c->d_tilesum); cudaFree(c->d_states);
+  if (c->own_stream) cudaStreamSynchronize(c->own_stream);
   if (c->h_states[0]) cudaFreeHost(c->h_states[0]);
   if (c->h_states[1]) cudaFreeHost(c->h_states[1]);
+  for (int i = 0; i < 2; ++i) {
+    if (c->h_states_own[i]) cudaFreeHost(c->h_states_own[i]);
+    if (c->ev_own_up[i]) cudaEventDestroy(c->ev_own_up[i]);
+  }
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
   cudaFree(c->d_mae); cudaFree(c->d_xchg_block); cudaFree(c->d_cl_inbox); cudaFree(c->d_clt_inbox);
   if (c->h_stage[0]) cudaFreeHost(c->h_stage[0]);
   if (c->h_stage[1]) cudaFreeHost(c->h_stage[1]);
@@ -397,7 +414,10 @@ int configure_launch(sgd_ctx* c) {
     if (const char* e = std::getenv("B200SGD_CLT")) cs = std::atoi(e);  // 0 = off; 2, 4, 8, 16 = CTAs per cluster
     const bool cs_ok = cs == 2 || cs == 4 || cs == 8 || cs == 16;
     const bool grid_ok = c->cfg.grid <= 0 ? grid >= 2 * cs : (c->cfg.grid % cs == 0);
-    if (cs_ok && grid_ok && c->C4 <= 2048) {
+    // (narrow rows on one GPU keep the LEAN 8-lanes-per-row kernel: B = 100000 at C = 100 runs 12.3 us per
+    // step there against 13.1 with the cluster tail, whose instantiation keeps its run-time switches)
+    const bool narrow_single = c->C4 <= 32 && c->cfg.nranks == 1 && c->cfg.reduce != SGD_REDUCE_CLUSTER && !std::getenv("B200SGD_CLT");
+    if (cs_ok && grid_ok && c->C4 <= 2048 && !narrow_single) {
       const int slice = (c->C4 + cs - 1) / cs;
       int g = c->cfg.grid > 0 ? c->cfg.grid : std::max(cs, grid / cs * cs);
       for (int pass = 0; pass < 3; ++pass) {
@@ -828,6 +848,95 @@ int enqueue_device_shuffle(sgd_ctx* c, int stage_buf, int src, int dst, int* lau
   return SGD_OK;
 }
 
+// ---- shared permutation work (nranks > 1, peers connected): see shuffle_kernels.cuh -----------------
+constexpr int kFlagReady = 0;   // [owner rank][buffer]: number of the shuffle whose map stands in the owner's buffer
+constexpr int kFlagDone = 16;   // [buffer][consumer rank] (in the OWNER's block): last shuffle the consumer applied from it
+
+bool use_shared_shuffle(const sgd_ctx* c) { return c->shared_shuffle && c->peers_ready; }
+
+unsigned long long watchdog_ns(const sgd_ctx* c) {
+  unsigned long long ns = c->cfg.nranks > 1 ? 30000000000ull : 4000000000ull;
+  if (const char* e = std::getenv("B200SGD_WATCHDOG_MS")) ns = 1000000ull * (unsigned long long)std::max(1ll, std::atoll(e));
+  return ns;
+}
+
+// Rank (k-1) % N: the position map of shuffle k -> own buffer ((k-1) / N) & 1, on own_stream.
+int enqueue_own_map(sgd_ctx* c, int64_t k, int* launches) {
+  const int N = c->cfg.nranks, me = c->cfg.rank;
+  const int b = (int)(((k - 1) / N) & 1);
+  const int64_t n = c->R;
+  // the host's part: chunk start states of shuffle k's stream (rng_own stands at its start)
+  CUDA_TRY(cudaEventSynchronize(c->ev_own_up[b]));  // staging buffer free again
+  c->rng_own.chunk_states(c->jump_chunk, c->nchunks, c->h_states_own[b]);
+  if (n > 1) c->rng_own.skip((uint64_t)N * (uint64_t)(n - 1));  // to my next shuffle
+  cudaStream_t st = c->own_stream;
+  CUDA_TRY(cudaStreamWaitEvent(st, c->ev_done[2], 0));  // a shuffle of the unshared kind may still use the scratch arrays
+  uint32_t* flags = (uint32_t*)((char*)c->d_xchg_block + c->flag_off);
+  if (k - 2 * (int64_t)N >= c->shared_first) {  // every rank has applied the map that stood in this buffer before (shuffle k - 2N)
+    b200sgd::shuf_wait_flags_kernel<<<1, 32, 0, st>>>(flags, kFlagDone + b * 8, N, 1, (uint32_t)(k - 2 * N), c->d_bar + 1,
+                                                    watchdog_ns(c));
+    *launches += 1;
+  }
+  CUDA_TRY(cudaMemcpyAsync(c->d_states, c->h_states_own[b], sizeof(uint32_t) * 31 * (size_t)c->nchunks, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaEventRecord(c->ev_own_up[b], st));
+  const int blocks = (int)std::min<int64_t>((n + 255) / 256, (int64_t)c->num_sms * 16);
+  int32_t* map = (int32_t*)((char*)c->d_xchg_block + c->src_off[b]);
+  CUDA_TRY(cudaMemsetAsync(c->d_cnt, 0, sizeof(int32_t) * ((size_t)n + 1), st));
+  b200sgd::shuf_targets_stream_kernel<<<(int)((c->nchunks + 127) / 128), 128, 0, st>>>(c->d_states, c->chunk_len, c->nchunks, n,
+                                                                                   c->d_tgt, c->d_cnt);
+  b200sgd::scan_tile_sums_kernel<<<c->scan_tiles, b200sgd::kScanBlock, 0, st>>>(c->d_cnt, n, c->d_tilesum);
+  b200sgd::scan_tile_offsets_kernel<<<1, b200sgd::kScanBlock, 0, st>>>(c->d_tilesum, c->scan_tiles, c->d_tilesum + c->scan_tiles);
+  b200sgd::scan_apply_kernel<<<c->scan_tiles, b200sgd::kScanBlock, 0, st>>>(c->d_cnt, n, c->d_tilesum, c->d_tilesum + c->scan_tiles,
+                                                                        c->d_start);
+  CUDA_TRY(cudaMemsetAsync(c->d_cnt, 0, sizeof(int32_t) * ((size_t)n + 1), st));
+  b200sgd::shuf_fill_kernel<<<blocks, 256, 0, st>>>(c->d_tgt, n, c->d_start, c->d_cnt, c->d_hits);
+  b200sgd::shuf_order_kernel<<<blocks, 256, 0, st>>>(n, c->d_start, c->d_hits, c->d_first);
+  b200sgd::shuf_resolve_kernel<<<blocks, 256, 0, st>>>(c->d_tgt, n, c->d_start, c->d_hits, c->d_first, nullptr, map);
+  b200sgd::PeerFlagPtrs t{};
+  for (int r = 0; r < N; ++r) t.p[r] = (uint32_t*)((char*)c->peer_block[r] + c->flag_off);
+  b200sgd::shuf_set_flags_kernel<<<1, 32, 0, st>>>(t, N, kFlagReady + me * 2 + b, (uint32_t)k);
+  CUDA_TRY(cudaGetLastError());
+  *launches += 8;
+  return SGD_OK;
+}
+
+// Every rank: shuffle number k = shuf_no + 1 turns d_perm[src] into d_perm[dst] on the shuffle stream.
+int enqueue_shared_shuffle(sgd_ctx* c, int src, int dst, int* launches) {
+  const int N = c->cfg.nranks, me = c->cfg.rank;
+  const int64_t k = c->shuf_no + 1;
+  if (c->shared_first == 0) {  // first shared shuffle: skip the maps of shuffles that were done the unshared way
+    c->shared_first = k;
+    while (c->own_next < k) {
+      c->own_next += N;
+      if (c->R > 1) c->rng_own.skip((uint64_t)N * (uint64_t)(c->R - 1));
+    }
+  }
+  // my maps are computed N - 1 shuffles ahead of their use (each takes about N epochs' worth of time)
+  while (c->own_next <= k + N - 1) {
+    SGD_TRY(enqueue_own_map(c, c->own_next, launches));
+    c->own_next += N;
+  }
+  if (c->R > 1) c->rng.skip((uint64_t)(c->R - 1));  // the context's own generator stays in step (host-side fallbacks)
+  const int owner = (int)((k - 1) % N), b = (int)(((k - 1) / N) & 1);
+  cudaStream_t st = c->shuf_stream;
+  CUDA_TRY(cudaStreamWaitEvent(st, c->ev_done[dst], 0));  // last epoch that read d_perm[dst]
+  CUDA_TRY(cudaStreamWaitEvent(st, c->ev_perm[src], 0));  // d_perm[src] uploaded (sgd_set_permutation)
+  uint32_t* flags = (uint32_t*)((char*)c->d_xchg_block + c->flag_off);
+  b200sgd::shuf_wait_flags_kernel<<<1, 32, 0, st>>>(flags, kFlagReady + owner * 2 + b, 1, 1, (uint32_t)k, c->d_bar + 1, watchdog_ns(c));
+  const int64_t n = c->R;
+  const int blocks = (int)std::min<int64_t>((n + 1023) / 1024, (int64_t)c->num_sms * 8);
+  const int32_t* map = (const int32_t*)((const char*)c->peer_block[owner] + c->src_off[b]);
+  b200sgd::shuf_apply_kernel<<<blocks, 256, 0, st>>>(map, c->d_perm[src], c->d_perm[dst], n);
+  b200sgd::PeerFlagPtrs t{};
+  t.p[0] = (uint32_t*)((char*)c->peer_block[owner] + c->flag_off);
+  b200sgd::shuf_set_flags_kernel<<<1, 32, 0, st>>>(t, 1, kFlagDone + b * 8 + me, (uint32_t)k);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaEventRecord(c->ev_shuf[dst], st));
+  c->shuf_no = k;
+  *launches += 3;
+  return SGD_OK;
+}
+
 // Pinned staging of host-side permutations: only the host shuffle and sgd_set_permutation need it, and
 // page-locking 8 bytes per row costs milliseconds, so it is allocated on first use.
 int ensure_host_stage(sgd_ctx* c) {
@@ -874,7 +983,8 @@ int check_watchdog(sgd_ctx* c) {
   if (err != 0) {
     cudaMemset(c->d_bar + 1, 0, sizeof(unsigned int));
     return fail(c->cfg.nranks > 1 ? SGD_ERR_COMM : SGD_ERR_CUDA,
-                err == 3   ? "dataflow reduction timed out (a CTA or a peer rank did not publish)"
+                err == 5   ? "shared shuffle timed out (a peer rank did not deliver / apply its permutation map)"
+                : err == 3 ? "dataflow reduction timed out (a CTA or a peer rank did not publish)"
                 : err == 4 ? "cluster exchange timed out (rows or partial sums did not arrive)"
                            : "grid barrier timed out (CTAs not co-resident?)");
   }
@@ -1170,8 +1280,24 @@ int sgd_create(const sgd_config* cfg, const float* X, const float* y, sgd_ctx** 
       if (c->direct) c->xchg_bytes = c->xpart_off + sizeof(uint4) * 2 * 2 * (size_t)c->C4 * c->cfg.nranks * c->grid;
       // cluster tail: tagged slice sums of every cluster of every rank, [2][nranks * clusters][C4p] float4
       if (c->clt) c->xchg_bytes = sizeof(uint4) * 2 * 2 * (size_t)c->cfg.nranks * c->clt_ng * (((size_t)c->C4 + 3) & ~(size_t)3);
+      if (c->device_shuffle && !std::getenv("B200SGD_NO_SHARED_SHUFFLE")) {
+        // shared permutation work: sequence-number flags + two position-map buffers every peer can read
+        c->shared_shuffle = true;
+        c->flag_off = (c->xchg_bytes + 4095) / 4096 * 4096;
+        c->src_off[0] = c->flag_off + 4096;
+        c->src_off[1] = c->src_off[0] + (sizeof(int32_t) * (size_t)c->R + 4095) / 4096 * 4096;
+        c->xchg_bytes = c->src_off[1] + sizeof(int32_t) * (size_t)c->R;
+        CUDA_TRY(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+          CUDA_TRY(cudaEventCreateWithFlags(&c->ev_own_up[i], cudaEventDisableTiming));
+          CUDA_TRY(cudaMallocHost(&c->h_states_own[i], sizeof(uint32_t) * 31 * (size_t)c->nchunks));
+        }
+        c->own_next = c->cfg.rank + 1;
+        c->rng_own = c->rng;
+        if (c->cfg.rank > 0 && c->R > 1) c->rng_own.skip((uint64_t)c->cfg.rank * (uint64_t)(c->R - 1));
+      }
       CUDA_TRY(cudaMalloc(&c->d_xchg_block, c->xchg_bytes));
-      CUDA_TRY(cudaMemset(c->d_xchg_block, 0, c->xchg_bytes));
+      CUDA_TRY(cudaMemset(c->d_xchg_block, 0, std::min<size_t>(c->xchg_bytes, c->shared_shuffle ? c->src_off[0] : c->xchg_bytes)));
       c->peer_block[c->cfg.rank] = c->d_xchg_block;
     }
     if (c->clt && c->cfg.nranks == 1 && c->clt_ng > 1) {
@@ -1356,10 +1482,16 @@ int sgd_shuffle(sgd_ctx* c) {
   if (c->device_shuffle) {
     const int buf = c->cur ^ 1;
     int launches = 0;
-    CUDA_TRY(cudaEventSynchronize(c->ev_perm[buf]));
-    prepare_stream_states(c, buf);
-    SGD_TRY(enqueue_device_shuffle(c, buf, c->cur, buf, &launches));
+    if (use_shared_shuffle(c)) {
+      SGD_TRY(enqueue_shared_shuffle(c, c->cur, buf, &launches));
+    } else {
+      CUDA_TRY(cudaEventSynchronize(c->ev_perm[buf]));
+      prepare_stream_states(c, buf);
+      SGD_TRY(enqueue_device_shuffle(c, buf, c->cur, buf, &launches));
+      c->shuf_no += 1;
+    }
     CUDA_TRY(cudaStreamSynchronize(c->shuf_stream));
+    SGD_TRY(check_watchdog(c));
     c->cur = buf;
     c->perm_valid = true;
     c->host_ind_stale = true;
@@ -1484,9 +1616,14 @@ int sgd_run(sgd_ctx* c, int32_t first_epoch, int32_t num_epochs, sgd_timings* to
   auto stage_next = [&]() -> int {  // host part of the shuffle runs while the GPU runs the previous epoch
     if (c->device_shuffle) {
       const int buf = c->cur ^ 1;
-      CUDA_TRY(cudaEventSynchronize(c->ev_perm[buf]));  // staging buffer free again
-      prepare_stream_states(c, buf);
-      SGD_TRY(enqueue_device_shuffle(c, buf, c->cur, buf, &launches));
+      if (use_shared_shuffle(c)) {
+        SGD_TRY(enqueue_shared_shuffle(c, c->cur, buf, &launches));
+      } else {
+        CUDA_TRY(cudaEventSynchronize(c->ev_perm[buf]));  // staging buffer free again
+        prepare_stream_states(c, buf);
+        SGD_TRY(enqueue_device_shuffle(c, buf, c->cur, buf, &launches));
+        c->shuf_no += 1;
+      }
       c->cur = buf;
       c->perm_valid = true;
       c->host_ind_stale = true;

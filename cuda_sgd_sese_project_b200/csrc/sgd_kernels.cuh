@@ -1404,13 +1404,15 @@ __global__ void __launch_bounds__(32 * (NW + NPMAX), 1)
         const int Qe = TG > 1 ? min(Qn, TG) : 1;  // of which poll sources
         float4 w_old = make_float4(0.f, 0.f, 0.f, 0.f);
         if (active) w_old = w_s[f];               // before anybody can send the new one
-        if (active && q == 0) {  // (2) the cluster's sum of column f, sources in CTA order
+        if (active && q < (TG > 1 ? o_nranks : 1)) {  // (2) the cluster's sum of column f, sources in CTA order
           const float4* src = rsbuf + (size_t)parc * cs * SL + col;
           float4 tot = src[0];
           for (int k = 1; k < cs; ++k) tot = f4_add(tot, src[(size_t)k * SL]);
-          if (TG > 1) {  // to slot [parity][me] of every rank's inbox: L2 on this GPU, NVLink to the peers
+          if (TG > 1) {
+            // to slot [parity][me] of every rank's inbox (L2 on this GPU, NVLink to the peers): thread q
+            // of the column serves ranks q, q + Qn, ... so that the stores to the peers leave side by side
             const int64_t at = (((int64_t)parc * TG + me) * C4p + f) * 2;
-            for (int r = 0; r < o_nranks; ++r) ll_store_f4(p.cl_inbox_peer[r] + at, tot, tag);
+            for (int r = q; r < o_nranks; r += Qn) ll_store_f4(p.cl_inbox_peer[r] + at, tot, tag);
           } else {
             xpart[cl] = tot;
           }

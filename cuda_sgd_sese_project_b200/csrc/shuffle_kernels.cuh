@@ -211,7 +211,65 @@ __global__ void __launch_bounds__(256) shuf_resolve_kernel(const uint32_t* __res
       int32_t nx;
       while ((nx = first[pos]) >= 0) pos = nx;
     }
-    out[pos] = in[i];
+    out[pos] = in ? in[i] : (int32_t)i;  // in == nullptr: the position map itself (out[final] = i)
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Several GPUs (one process each): the ranks SHARE the permutation work instead of every rank
+// recomputing it.  The loop above moves values around without looking at them, so epoch k's shuffle is
+// a position map  src_k[p] = "the slot whose value ends up at p"  that depends on the rand() stream of
+// epoch k only:  perm_k[p] = perm_{k-1}[src_k[p]].  Rank (k-1) mod N computes src_k with the five
+// kernels above (in = nullptr) -- N epochs ahead, on its own stream -- into a buffer every rank has
+// mapped (the exchange block, NVLink); every rank then applies it with one gather pass, reading the
+// owner's buffer directly over NVLink.  Hand-shake: 32-bit sequence numbers written with system-scope
+// release stores into the consumers' / the owner's exchange block and polled by one tiny wait kernel
+// (a spinning kernel of one warp cannot keep the cooperative step kernel off the SMs).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) shuf_wait_flags_kernel(const uint32_t* flags, int first, int count, int stride,
+                                                             uint32_t want, unsigned int* err, unsigned long long timeout_ns) {
+  const int i = threadIdx.x;
+  if (i >= count) return;
+  const uint32_t* f = flags + first + i * stride;
+  unsigned long long t0 = 0;
+  unsigned int spins = 0;
+  for (;;) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+    if ((int32_t)(v - want) >= 0) return;
+    if ((++spins & 255u) == 0) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > timeout_ns) { atomicCAS(err, 0u, 5u); return; }
+    }
+    __nanosleep(200);
+  }
+}
+
+struct PeerFlagPtrs { uint32_t* p[8]; };
+
+// thread r stores `value` into flag `idx` of target r (everything this stream did before is visible first)
+__global__ void __launch_bounds__(32) shuf_set_flags_kernel(PeerFlagPtrs t, int ntargets, int idx, uint32_t value) {
+  const int r = threadIdx.x;
+  if (r >= ntargets || t.p[r] == nullptr) return;
+  __threadfence_system();
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(t.p[r] + idx), "r"(value) : "memory");
+}
+
+// out[p] = in[src[p]]: src is read once, in order (possibly from a peer GPU), `in` at random
+__global__ void __launch_bounds__(256) shuf_apply_kernel(const int32_t* __restrict__ src, const int32_t* __restrict__ in,
+                                                         int32_t* __restrict__ out, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += 4 * stride) {
+    int32_t s[4], v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) s[u] = (i + u * stride < n) ? __ldcs(src + i + u * stride) : 0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = __ldg(in + s[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (i + u * stride < n) out[i + u * stride] = v[u];
   }
 }
 

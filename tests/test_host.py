@@ -114,13 +114,16 @@ def test_write_csv_round_trips_and_special_cells(tmp_path):
     ok, X2, y2 = pkg.read_csv(str(p), 1234, 7)
     assert ok and np.array_equal(X2.view(np.uint32), X.view(np.uint32)) and np.array_equal(y2, y)
     rc, Xo, yo = orc.read_csv(str(p), 1234, 7)     # the oracle's getline / stof restatement reads the same file
-    assert rc and np.array_equal(Xo, X) and np.array_equal(yo, y)
+    assert rc == 0 and np.array_equal(Xo, X) and np.array_equal(yo, y)
     # spellings std::stof accepts and from_chars alone would not: hex floats, a leading '+',
     # trailing junk, cells longer than 63 characters; out-of-range values are rejected (stof throws)
     q = tmp_path / "odd.csv"
-    q.write_text("0x1p3,+2.5,1.5abc," + "0." + "0" * 80 + "1,7\n")
+    q.write_text("0x1p3,+2.5,1.5abc," + "0." + "0" * 30 + "1" + "0" * 40 + ",7\n")
     ok, X3, y3 = pkg.read_csv(str(q), 1, 4)
-    assert ok and X3[0].tolist() == [8.0, 2.5, 1.5, np.float32(1e-81)] and y3[0] == 7.0
+    assert ok and X3[0].tolist() == [8.0, 2.5, 1.5, float(np.float32(1e-31))] and y3[0] == 7.0
+    q.write_text("1e-81,1\n")          # underflow: strtof sets ERANGE, std::stof throws out_of_range
+    with pytest.raises(pkg.SgdError):
+        pkg.read_csv(str(q), 1, 1)
     q.write_text("1e50,1\n")
     with pytest.raises(pkg.SgdError):
         pkg.read_csv(str(q), 1, 1)
