@@ -26,7 +26,7 @@ EXPORTS = [
     "sgd_abi_version", "sgd_last_error", "sgd_device_count", "sgd_read_csv", "sgd_write_csv",
     "sgd_get_filename_from_path", "sgd_write_experiment_output", "sgd_init_weights",
     "sgd_batch_geometry", "sgd_host_shuffle", "sgd_shard_range", "sgd_host_bucket", "sgd_get_local_schedule", "sgd_get_loss_curve",
-    "sgd_create", "sgd_destroy", "sgd_load_rows",
+    "sgd_create", "sgd_destroy", "sgd_load_rows", "sgd_load_csv",
     "sgd_load_synthetic", "sgd_get_rows", "sgd_get_true_weights", "sgd_get_weights",
     "sgd_set_weights", "sgd_get_config", "sgd_local_rows", "sgd_local_row_begin", "sgd_shuffle",
     "sgd_set_permutation", "sgd_get_permutation", "sgd_epoch", "sgd_iteration", "sgd_run",
@@ -54,6 +54,19 @@ class SgdTimings(C.Structure):
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class SgdLoadStats(C.Structure):
+    _fields_ = [
+        ("rows", C.c_int64), ("bytes_uploaded", C.c_int64), ("parse_seconds", C.c_double),
+        ("total_seconds", C.c_double), ("from_cache", C.c_int32), ("cache_written", C.c_int32),
+    ]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+SGD_CSV_CACHE = 0x1
 
 
 class SgdError(RuntimeError):
@@ -94,6 +107,7 @@ def load() -> C.CDLL:
         "sgd_create": ([C.POINTER(SgdConfig), vp, vp, C.POINTER(vp)], C.c_int),
         "sgd_destroy": ([vp], None),
         "sgd_load_rows": ([vp, i64, i64, vp, vp], C.c_int),
+        "sgd_load_csv": ([vp, C.c_char_p, i32, C.POINTER(SgdLoadStats)], C.c_int),
         "sgd_load_synthetic": ([vp, C.c_uint64, i32], C.c_int),
         "sgd_get_rows": ([vp, i64, i64, vp, vp], C.c_int),
         "sgd_get_true_weights": ([vp, vp], C.c_int),

@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstddef>
@@ -21,6 +22,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "host_io.hpp"
@@ -911,8 +913,13 @@ int enqueue_shared_shuffle(sgd_ctx* c, int src, int dst, int* launches) {
       if (c->R > 1) c->rng_own.skip((uint64_t)N * (uint64_t)(c->R - 1));
     }
   }
-  // my maps are computed N - 1 shuffles ahead of their use (each takes about N epochs' worth of time)
-  while (c->own_next <= k + N - 1) {
+  // Shuffles come in blocks of N (one map per rank).  My map of the NEXT block is started when the
+  // current block begins -- on every rank at the same shuffle: computing a map slows the step loop of
+  // the GPU it runs on by ~40 % (random 32-byte accesses against the row stream), and a step is as slow
+  // as the slowest rank, so the ranks had better be slow together for one map's time and undisturbed
+  // for the rest of the block than take turns at being the slow one all the time.
+  static const bool stagger = std::getenv("B200SGD_MAP_STAGGER") != nullptr;  // A/B: every rank N - 1 shuffles ahead of its own use
+  while (stagger ? c->own_next <= k + N - 1 : (c->own_next - 1) / N <= (k - 1) / N + 1) {
     SGD_TRY(enqueue_own_map(c, c->own_next, launches));
     c->own_next += N;
   }
@@ -1373,6 +1380,198 @@ int sgd_load_rows(sgd_ctx* c, int64_t row_begin, int64_t nrows, const float* X, 
     if (e != cudaSuccess) return fail(SGD_ERR_CUDA, std::string("upload failed: ") + cudaGetErrorString(e));
   }
   c->data_loaded = true;
+  return SGD_OK;
+}
+
+// ---- CSV -> HBM with the parse and the upload overlapped, optional raw cache -----------------------
+namespace {
+struct RawCacheHeader {  // <csv>.f32: header, then rows * (cols + 1) floats (`x..., label` per row)
+  char magic[8];
+  uint32_t version, cols;
+  int64_t rows, csv_size, csv_mtime_ns;
+  char pad[24];
+};
+static_assert(sizeof(RawCacheHeader) == 64, "raw cache header layout");
+const char kRawMagic[8] = {'B', '2', 'S', 'G', 'D', 'F', '3', '2'};
+}  // namespace
+
+int sgd_load_csv(sgd_ctx* c, const char* path, int32_t flags, sgd_load_stats* stats) {
+  SGD_TRY(check_ctx(c));
+  if (!path) return fail(SGD_ERR_ARG, "sgd_load_csv: null path");
+  SGD_TRY(bind(c));
+  const auto t_all = clk::now();
+  const int64_t R = c->R, W = (int64_t)c->C + 1;
+  sgd_load_stats st{};
+  // pieces of ~4 MB of text; a pipeline stage is as many pieces as fit the staging buffer (~96 MB of
+  // floats), parsed by all host threads (each takes the next unparsed piece)
+  b200sgd::CsvFile csv;
+  std::string err;
+  if (csv.open(path, (size_t)4 << 20, &err) != 0) return fail(SGD_ERR_IO, err);
+  const std::string cache_path = std::string(path) + ".f32";
+  bool from_cache = false;
+  FILE* fc = nullptr;
+  if (flags & SGD_CSV_CACHE) {
+    fc = std::fopen(cache_path.c_str(), "rb");
+    RawCacheHeader h{};
+    if (fc && std::fread(&h, sizeof(h), 1, fc) == 1 && std::memcmp(h.magic, kRawMagic, 8) == 0 && h.version == 1 &&
+        h.cols == (uint32_t)c->C && h.rows == R && h.csv_size == csv.size() && h.csv_mtime_ns == csv.mtime_ns()) {
+      from_cache = true;
+    } else if (fc) {
+      std::fclose(fc);
+      fc = nullptr;
+    }
+  }
+  // staging: two pinned buffers of `stage_rows` records each
+  const int64_t stage_rows = std::max<int64_t>(1, std::min<int64_t>(R, ((int64_t)96 << 20) / (4 * W)));
+  float* h_stage[2] = {nullptr, nullptr};
+  float* d_stage[2] = {nullptr, nullptr};
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  int rc = SGD_OK;
+  auto cleanup = [&] {
+    cudaStreamSynchronize(c->stream);
+    for (int i = 0; i < 2; ++i) {
+      if (h_stage[i]) cudaFreeHost(h_stage[i]);
+      if (d_stage[i]) cudaFree(d_stage[i]);
+      if (ev[i]) cudaEventDestroy(ev[i]);
+    }
+    if (fc) std::fclose(fc);
+  };
+  for (int i = 0; i < 2 && rc == SGD_OK; ++i) {
+    if (cudaMallocHost(&h_stage[i], sizeof(float) * (size_t)(stage_rows * W)) != cudaSuccess ||
+        cudaMalloc(&d_stage[i], sizeof(float) * (size_t)(stage_rows * W)) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) != cudaSuccess) {
+      cudaGetLastError();
+      rc = fail(SGD_ERR_NOMEM, "sgd_load_csv: staging allocation failed");
+    }
+  }
+  if (rc != SGD_OK) { cleanup(); return rc; }
+  // upload of stage buffer b holding file rows [r0, r0 + n): the part inside this rank's shard
+  auto upload = [&](int b, int64_t r0, int64_t n) -> int {
+    const int64_t lo = std::max(r0, c->row_begin), hi = std::min(r0 + n, c->row_end);
+    if (hi > lo) {
+      const float* hs = h_stage[b] + (lo - r0) * W;
+      CUDA_TRY(cudaMemcpyAsync(d_stage[b], hs, sizeof(float) * (size_t)((hi - lo) * W), cudaMemcpyHostToDevice, c->stream));
+      const int blocks = (int)std::min<int64_t>(((hi - lo) * c->ld + 255) / 256, (int64_t)c->num_sms * 16);
+      b200sgd::sgd_pack_rec_kernel<<<blocks, 256, 0, c->stream>>>(d_stage[b], hi - lo, c->C, c->ld,
+                                                                 c->d_rec + (lo - c->row_begin) * c->ld);
+      CUDA_TRY(cudaGetLastError());
+      st.bytes_uploaded += (hi - lo) * W * 4;
+    }
+    CUDA_TRY(cudaEventRecord(ev[b], c->stream));
+    return SGD_OK;
+  };
+  FILE* fw = nullptr;  // cache being written (only when the whole file passes through this rank)
+  std::string tmp_path;
+  if ((flags & SGD_CSV_CACHE) && !from_cache) {
+    tmp_path = cache_path + ".tmp";
+    fw = std::fopen(tmp_path.c_str(), "wb");
+    if (fw) {
+      RawCacheHeader h{};
+      std::memcpy(h.magic, kRawMagic, 8);
+      h.version = 1;
+      h.cols = (uint32_t)c->C;
+      h.rows = R;
+      h.csv_size = csv.size();
+      h.csv_mtime_ns = csv.mtime_ns();
+      if (std::fwrite(&h, sizeof(h), 1, fw) != 1) { std::fclose(fw); fw = nullptr; }
+    }
+  }
+  int64_t rows_seen = 0;
+  int stage = 0;
+  if (from_cache) {
+    st.from_cache = 1;
+    for (int64_t r0 = 0; r0 < R && rc == SGD_OK; r0 += stage_rows, stage ^= 1) {
+      const int64_t n = std::min(stage_rows, R - r0);
+      if (cudaEventSynchronize(ev[stage]) != cudaSuccess) { rc = fail(SGD_ERR_CUDA, "sgd_load_csv: upload failed"); break; }
+      const bool mine = r0 < c->row_end && r0 + n > c->row_begin;
+      if (mine) {
+        if (std::fread(h_stage[stage], sizeof(float) * (size_t)W, (size_t)n, fc) != (size_t)n) {
+          rc = fail(SGD_ERR_IO, "raw cache " + cache_path + " is truncated");
+          break;
+        }
+        rc = upload(stage, r0, n);
+      } else if (std::fseek(fc, (long)(sizeof(float) * (size_t)(W * n)), SEEK_CUR) != 0) {
+        rc = fail(SGD_ERR_IO, "raw cache seek failed");
+      }
+    }
+    rows_seen = R;
+  } else {
+    // a stage = consecutive pieces holding at most stage_rows rows, parsed by one thread per piece
+    const auto& pcs = csv.pieces();
+    size_t k = 0;
+    while (k < pcs.size() && rc == SGD_OK) {
+      size_t k1 = k;
+      int64_t n = 0;
+      while (k1 < pcs.size() && (k1 == k || n + pcs[k1].rows <= stage_rows)) n += pcs[k1++].rows;
+      const int64_t r0 = pcs[k].row0;
+      if (n > stage_rows) {  // cannot happen for well-formed input (>= 2 bytes of text per value); a file of empty lines could
+        rc = fail(SGD_ERR_PARSE, "a 4 MB piece of the CSV holds more rows than the staging buffer");
+        break;
+      }
+      if (cudaEventSynchronize(ev[stage]) != cudaSuccess) { rc = fail(SGD_ERR_CUDA, "sgd_load_csv: upload failed"); break; }
+      const bool mine = (r0 < c->row_end && r0 + n > c->row_begin) || fw != nullptr;
+      if (mine) {
+        const auto tp = clk::now();
+        const int64_t nz = std::min<int64_t>(n, std::max<int64_t>(0, R - r0));
+        std::memset(h_stage[stage], 0, sizeof(float) * (size_t)(nz * W));  // thrust::host_vector zero-fills
+        std::atomic<int> prc{0};
+        std::atomic<size_t> next{k};
+        const unsigned hw = std::thread::hardware_concurrency();
+        const size_t T = std::min<size_t>(k1 - k, hw ? hw : 4);
+        std::vector<std::thread> th;
+        for (size_t t = 0; t < T; ++t)
+          th.emplace_back([&] {
+            for (size_t q = next.fetch_add(1); q < k1; q = next.fetch_add(1)) {
+              const int r = csv.parse_piece(q, R, c->C, h_stage[stage], r0);
+              if (r != 0) prc.store(r);
+            }
+          });
+        for (auto& t : th) t.join();
+        st.parse_seconds += ms_since(tp) * 1e-3;
+        if (prc.load() != 0) {
+          rc = fail(SGD_ERR_PARSE, std::string("CSV has more rows/columns than announced or an unparsable cell: ") + path);
+          break;
+        }
+        if (fw && nz > 0 && std::fwrite(h_stage[stage], sizeof(float) * (size_t)W, (size_t)nz, fw) != (size_t)nz) {
+          std::fclose(fw);
+          fw = nullptr;
+          std::remove(tmp_path.c_str());
+        }
+        if (nz > 0) rc = upload(stage, r0, nz);
+      }
+      rows_seen = std::max(rows_seen, std::min(R, r0 + n));
+      stage ^= 1;
+      k = k1;
+    }
+  }
+  if (rc == SGD_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail(SGD_ERR_CUDA, "sgd_load_csv: upload failed");
+  if (rc == SGD_OK && rows_seen < R) {
+    // fewer lines than announced: the remaining rows are zeros (the reference's zero-filled host vectors)
+    const int64_t lo = std::max(rows_seen, c->row_begin), hi = c->row_end;
+    if (hi > lo) {
+      if (cudaMemsetAsync(c->d_rec + (lo - c->row_begin) * c->ld, 0, sizeof(float) * (size_t)((hi - lo) * c->ld), c->stream) != cudaSuccess ||
+          cudaStreamSynchronize(c->stream) != cudaSuccess)
+        rc = fail(SGD_ERR_CUDA, "sgd_load_csv: zero fill failed");
+    }
+    if (fw) {  // the cache holds exactly `rows` records
+      std::vector<float> z((size_t)W, 0.f);
+      for (int64_t r = rows_seen; r < R && fw; ++r)
+        if (std::fwrite(z.data(), sizeof(float) * (size_t)W, 1, fw) != 1) { std::fclose(fw); fw = nullptr; std::remove(tmp_path.c_str()); }
+    }
+  }
+  if (fw) {
+    const bool ok = std::fclose(fw) == 0 && rc == SGD_OK;
+    fw = nullptr;
+    if (ok) std::rename(tmp_path.c_str(), cache_path.c_str());
+    else std::remove(tmp_path.c_str());
+    st.cache_written = ok ? 1 : 0;
+  }
+  cleanup();
+  if (rc != SGD_OK) return rc;
+  c->data_loaded = true;
+  st.rows = R;
+  st.total_seconds = ms_since(t_all) * 1e-3;
+  if (stats) *stats = st;
   return SGD_OK;
 }
 

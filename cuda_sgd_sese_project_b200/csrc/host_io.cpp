@@ -61,7 +61,9 @@ inline bool parse_cell(const char* b, const char* e, float* out) {
 }
 
 // Parses the lines in [b, e) (whole lines) starting at row `row`.  Returns 0 or a negative code.
-int parse_lines(const char* b, const char* e, int64_t row, int64_t R, int32_t C, float* X, float* y) {
+// Row r goes to X[r * px .. + C) and y[r * py] (px = C, py = 1: the reference's two arrays; px = py = C + 1
+// with y = X + C: records `x..., label`, the layout of the raw cache and of the upload staging).
+int parse_lines(const char* b, const char* e, int64_t row, int64_t R, int32_t C, float* X, float* y, int64_t px, int64_t py) {
   while (b < e) {
     const char* eol = (const char*)std::memchr(b, '\n', (size_t)(e - b));
     if (!eol) eol = e;
@@ -77,7 +79,7 @@ int parse_lines(const char* b, const char* e, int64_t row, int64_t R, int32_t C,
         float v;
         if (!parse_cell(p, ce, &v)) return -3;
         if (col > C) return -3;  // the reference would write into the next row here
-        if (col != C) X[row * (int64_t)C + col] = v; else y[row] = v;
+        if (col != C) X[row * px + col] = v; else y[row * py] = v;
         ++col;
         if (!q) break;
         p = q + 1;
@@ -147,7 +149,7 @@ int read_csv(const char* path, int64_t R, int32_t C, float* X, float* y, std::st
     std::vector<std::thread> th;
     for (size_t k = 0; k < nchunks; ++k)
       th.emplace_back([&, k] {
-        int r = parse_lines(base + cut[k], base + cut[k + 1], row0[k], R, C, X, y);
+        int r = parse_lines(base + cut[k], base + cut[k + 1], row0[k], R, C, X, y, C, 1);
         if (r != 0) rc.store(r);
       });
     for (auto& t : th) t.join();
@@ -156,6 +158,73 @@ int read_csv(const char* path, int64_t R, int32_t C, float* X, float* y, std::st
   if (rc.load() != 0 && err)
     *err = std::string("CSV has more rows/columns than announced or an unparsable cell: ") + path;
   return rc.load();
+}
+
+// ---- chunked access for the overlapped load (sgd_load_csv): the file is mapped once and cut into
+// pieces of whole lines whose first row is known, so that any piece can be parsed on its own ----
+CsvFile::~CsvFile() {
+  if (base_) munmap((void*)base_, len_);
+}
+
+int CsvFile::open(const char* path, size_t piece_bytes, std::string* err) {
+  int fd = ::open(path, O_RDONLY);
+  if (fd < 0) {
+    if (err) *err = std::string("Could not open file: ") + path;
+    return -2;
+  }
+  struct stat st;
+  if (fstat(fd, &st) != 0) { ::close(fd); if (err) *err = "fstat failed"; return -2; }
+  len_ = (size_t)st.st_size;
+  size_ = (int64_t)st.st_size;
+  mtime_ns_ = (int64_t)st.st_mtim.tv_sec * 1000000000ll + (int64_t)st.st_mtim.tv_nsec;
+  if (len_ == 0) { ::close(fd); return 0; }
+  base_ = (const char*)mmap(nullptr, len_, PROT_READ, MAP_PRIVATE, fd, 0);
+  ::close(fd);
+  if (base_ == MAP_FAILED) { base_ = nullptr; if (err) *err = "mmap failed"; return -2; }
+  madvise((void*)base_, len_, MADV_SEQUENTIAL);
+  const size_t np = std::max<size_t>(1, (len_ + piece_bytes - 1) / piece_bytes);
+  std::vector<size_t> cut(np + 1, len_);
+  cut[0] = 0;
+  for (size_t k = 1; k < np; ++k) {
+    size_t pos = std::max(cut[k - 1], len_ / np * k);
+    const char* nl = (const char*)std::memchr(base_ + pos, '\n', len_ - pos);
+    cut[k] = nl ? (size_t)(nl - base_) + 1 : len_;
+  }
+  pieces_.assign(np, Piece{});
+  unsigned hw = std::thread::hardware_concurrency();
+  const size_t T = std::min<size_t>(np, hw ? hw : 4);
+  std::atomic<size_t> next{0};
+  std::vector<std::thread> th;
+  for (size_t t = 0; t < T; ++t)
+    th.emplace_back([&] {
+      for (size_t k = next.fetch_add(1); k < np; k = next.fetch_add(1)) {
+        int64_t n = 0;
+        const char* p = base_ + cut[k];
+        const char* e = base_ + cut[k + 1];
+        while (p < e) {
+          const char* nl = (const char*)std::memchr(p, '\n', (size_t)(e - p));
+          ++n;
+          if (!nl) break;  // last line without EOL
+          p = nl + 1;
+        }
+        pieces_[k].begin = cut[k];
+        pieces_[k].end = cut[k + 1];
+        pieces_[k].rows = n;
+      }
+    });
+  for (auto& t : th) t.join();
+  int64_t r = 0;
+  for (auto& pc : pieces_) {
+    pc.row0 = r;
+    r += pc.rows;
+  }
+  return 0;
+}
+
+int CsvFile::parse_piece(size_t k, int64_t R, int32_t C, float* rec, int64_t rec_row0) const {
+  const Piece& pc = pieces_[k];
+  float* X = rec - rec_row0 * ((int64_t)C + 1);  // so that row r lands at rec + (r - rec_row0) * (C + 1)
+  return parse_lines(base_ + pc.begin, base_ + pc.end, pc.row0, R, C, X, X + C, (int64_t)C + 1, (int64_t)C + 1);
 }
 
 // The reference's data_set_creation scripts write `f1,...,fC,label` lines with csv.writer; this is the

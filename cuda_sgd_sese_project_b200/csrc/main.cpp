@@ -52,7 +52,7 @@ int main(int argc, char** argv) {
   const int batch_arg = atoi(pos[5]);
   const bool cudaRun = atoi(pos[6]) == 1;  // main.cu:345
 
-  bool synthetic = false, fp16 = false, per_epoch = false;
+  bool synthetic = false, fp16 = false, per_epoch = false, use_cache = false;
   unsigned long long seed = 42;
   std::string dump_weights;
   sgd_config cfg;
@@ -67,6 +67,7 @@ int main(int argc, char** argv) {
     if (starts_with(o, "--synthetic=")) { synthetic = true; seed = strtoull(o + 12, nullptr, 10); }
     else if (!std::strcmp(o, "--fp16")) fp16 = true;
     else if (!std::strcmp(o, "--per-epoch")) per_epoch = true;
+    else if (!std::strcmp(o, "--cache")) use_cache = true;
     else if (!std::strcmp(o, "--engine=graph")) cfg.engine = SGD_ENGINE_GRAPH;
     else if (!std::strcmp(o, "--engine=persistent")) cfg.engine = SGD_ENGINE_PERSISTENT;
     else if (starts_with(o, "--grid=")) cfg.grid = atoi(o + 7);
@@ -80,28 +81,44 @@ int main(int argc, char** argv) {
   const double t_mem0 = now_ms();
   std::cout << "Data size: ~" << float(R) * C * sizeof(float) / (1024 * 1024) << "MB" << std::endl;  // main.cu:356
 
-  std::vector<float> data_h, labels_h;
-  double csv_time = 0.0;
-  if (!synthetic) {
-    data_h.resize((size_t)R * C);
-    labels_h.resize((size_t)R);
-    const double t0 = now_ms();
-    const int rc = sgd_read_csv(filepath.c_str(), R, C, data_h.data(), labels_h.data());
-    if (rc != SGD_OK) {
-      std::cout << "Warning: " << sgd_last_error() << std::endl;
+  // main.cu:365 (read_csv) + :381-384 (device vectors): one overlapped pass here -- all host cores parse
+  // the next piece of the file into pinned memory while the previous one is copied and packed on the
+  // device (sgd_load_csv); `--cache` keeps the parsed rows in <csv>.f32 for the next run
+  if (!synthetic) {  // main.cu:366-370: an unreadable file ends the run before anything is allocated
+    FILE* f = std::fopen(filepath.c_str(), "rb");
+    if (!f) {
+      std::cout << "Warning: Could not open file: " << filepath << std::endl;
       std::cout << "Could not read file, exiting..." << std::endl;  // main.cu:368
       return 2;
     }
-    csv_time = now_ms() - t0;
+    std::fclose(f);
   }
-  printf("%s time = %f ms\n", "csv read", csv_time);  // main.cu:373
-
   const double t_copy0 = now_ms();
   sgd_ctx* ctx = nullptr;
-  int rc = sgd_create(&cfg, synthetic ? nullptr : data_h.data(), synthetic ? nullptr : labels_h.data(), &ctx);
-  if (rc == SGD_OK && synthetic) rc = sgd_load_synthetic(ctx, seed, fp16 ? 1 : 0);
+  int rc = sgd_create(&cfg, nullptr, nullptr, &ctx);
   if (rc != SGD_OK) {
     std::cerr << "b200sgd: " << sgd_last_error() << std::endl;
+    return 3;
+  }
+  double csv_time = 0.0;
+  if (!synthetic) {
+    sgd_load_stats st;
+    std::memset(&st, 0, sizeof(st));
+    rc = sgd_load_csv(ctx, filepath.c_str(), use_cache ? SGD_CSV_CACHE : 0, &st);
+    if (rc == SGD_ERR_IO || rc == SGD_ERR_PARSE) {
+      std::cout << "Warning: " << sgd_last_error() << std::endl;
+      std::cout << "Could not read file, exiting..." << std::endl;  // main.cu:368
+      sgd_destroy(ctx);
+      return 2;
+    }
+    csv_time = st.parse_seconds * 1e3;
+  } else {
+    rc = sgd_load_synthetic(ctx, seed, fp16 ? 1 : 0);
+  }
+  printf("%s time = %f ms\n", "csv read", csv_time);  // main.cu:373 (the parser's share of the overlapped load)
+  if (rc != SGD_OK) {
+    std::cerr << "b200sgd: " << sgd_last_error() << std::endl;
+    sgd_destroy(ctx);
     return 3;
   }
   printf("%s time = %f ms\n", "GPU copy", now_ms() - t_copy0);  // main.cu:386

@@ -900,6 +900,13 @@ __global__ void __launch_bounds__(32 * (NW + NPMAX), 1)
   };
   if (prof) t_prev = clock64();
 
+  // bucketed row lists (several GPUs): the offsets of step s+1 are loaded while step s runs, so that no
+  // L2 round trip stands between the new weights and the first row of the next step
+  int64_t so_cur = 0, so_next = 0;
+  if (o_step_off != nullptr && p.nb > 0) {
+    so_cur = o_step_off[first_step];
+    so_next = o_step_off[first_step + 1];
+  }
   for (int s = 0; s < p.nb; ++s) {
     cur_step = s;
     if (ctid == 0) steps_done = s;  // all consumers have finished step s-1 (they passed its last barrier)
@@ -909,10 +916,12 @@ __global__ void __launch_bounds__(32 * (NW + NPMAX), 1)
       lo = lo_uni;
       n = n_uni;
     } else {
-      const int64_t rows = step_rows(s);
-      off = step_begin(s);
+      const int64_t rows = so_next - so_cur;
+      off = so_cur;
       lo = slice_lo(rows, cta, G);
       n = slice_lo(rows, cta + 1, G) - lo;
+      so_cur = so_next;
+      if (s + 1 < p.nb) so_next = o_step_off[(int64_t)first_step + s + 2];  // not needed before the next iteration
     }
 #pragma unroll
     for (int k = 0; k < KC; ++k) g[k] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1719,6 +1728,18 @@ __global__ void sgd_pack_kernel(const float* __restrict__ X, const float* __rest
     if (c < C) v = X[row * C + c];
     else if (c == C) v = y[row];
     rec[i] = v;
+  }
+}
+
+// records `x_0..x_{C-1}, label` (C + 1 floats, the staging / raw-cache layout) -> padded records
+__global__ void sgd_pack_rec_kernel(const float* __restrict__ src, int64_t nrows, int32_t C, int64_t ld,
+                                    float* __restrict__ rec) {
+  const int64_t total = nrows * ld;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / ld;
+    const int32_t c = (int32_t)(i - row * ld);
+    rec[i] = (c <= C) ? src[row * ((int64_t)C + 1) + c] : 0.f;
   }
 }
 

@@ -177,6 +177,12 @@ class SGDEngine:
         """Raw host pointers (e.g. pinned torch tensors' data_ptr())."""
         L.check(L.load().sgd_load_rows(self._h, row_begin, nrows, C.c_void_p(data_ptr), C.c_void_p(labels_ptr)))
 
+    def load_csv(self, filename: str, cache: bool = False) -> dict:
+        """read_csv + upload in one overlapped pass (main.cu:365 + :381-384); optional raw cache `<csv>.f32`."""
+        st = L.SgdLoadStats()
+        L.check(L.load().sgd_load_csv(self._h, os.fsencode(filename), L.SGD_CSV_CACHE if cache else 0, C.byref(st)))
+        return st.as_dict()
+
     def load_synthetic(self, seed: int = 42, round_fp16: bool = False) -> None:
         L.check(L.load().sgd_load_synthetic(self._h, seed, int(round_fp16)))
 

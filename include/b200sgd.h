@@ -148,6 +148,24 @@ int sgd_create(const sgd_config* cfg, const float* X, const float* y, sgd_ctx** 
 void sgd_destroy(sgd_ctx* ctx);
 /* upload rows [row_begin, row_begin+nrows) of the whole data set (host, row-major, C per row) */
 int sgd_load_rows(sgd_ctx* ctx, int64_t row_begin, int64_t nrows, const float* X, const float* y);
+/* read_csv + upload in one call (main.cu:365 + :381-384), the way the reference's dominant wall time
+ * ("the most time consuming part", report/sese_report_tvas.tex:737-740) is best spent: the file is
+ * mapped and cut into pieces of whole lines, all host cores parse piece k+1 into pinned memory while
+ * piece k is copied to the device and packed into records, and no full host copy of the data ever
+ * exists.  Same cell semantics and errors as sgd_read_csv.  With SGD_CSV_CACHE the parsed rows are
+ * also written to `<path>.f32` (64-byte header: magic, rows, cols, size and mtime of the CSV; then
+ * rows * (cols + 1) floats); a later call finds the cache, checks the header against the CSV and
+ * streams the floats instead of parsing text.  stats may be NULL. */
+#define SGD_CSV_CACHE 0x1
+typedef struct sgd_load_stats {
+  int64_t rows;           /* rows of the data set                                   */
+  int64_t bytes_uploaded; /* host -> device bytes of this rank                      */
+  double parse_seconds;   /* wall time inside the text parser (0 from the cache)    */
+  double total_seconds;   /* whole call                                             */
+  int32_t from_cache;     /* 1: the raw cache was used                              */
+  int32_t cache_written;  /* 1: this call wrote the raw cache                       */
+} sgd_load_stats;
+int sgd_load_csv(sgd_ctx* ctx, const char* path, int32_t flags, sgd_load_stats* stats);
 /* fill this rank's shard on the device with the data_set_creation/generate_data.py distribution
  * (X~N(0,1), w_true~100*U(0,1), y = X w_true), counter-based so the values do not depend on the
  * number of ranks.  round_fp16 != 0 rounds through float16 as generate_data.py:37 does. */

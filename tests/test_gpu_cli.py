@@ -67,6 +67,60 @@ def test_cli_full_batch_docstring_example(tmp_path, fixtures):
     assert mae == pytest.approx(198.1447, rel=1e-4)
 
 
+def test_load_csv_overlapped_and_raw_cache(tmp_path):
+    """sgd_load_csv (parse of piece k+1 overlapped with the upload of piece k) gives the rows sgd_read_csv
+    gives; the raw cache <csv>.f32 is written once, used while the CSV is unchanged, rebuilt afterwards."""
+    import cuda_sgd_sese_project_b200 as pkg
+    R, C = 300_000, 100       # ~330 MB of text: several 32 MB pieces, two pipeline stages
+    rng = np.random.default_rng(9)
+    X = rng.standard_normal((R, C)).astype(np.float32)
+    y = rng.standard_normal(R).astype(np.float32)
+    csv = tmp_path / "big.csv"
+    pkg.write_csv(str(csv), X, y)
+    ok, Xr, yr = pkg.read_csv(str(csv), R, C)
+    assert ok and np.array_equal(Xr, X) and np.array_equal(yr, y)
+    with pkg.SGDEngine(R, C, 1000, 0.1) as eng:
+        st = eng.load_csv(str(csv))
+        assert st["rows"] == R and st["from_cache"] == 0 and st["cache_written"] == 0 and st["parse_seconds"] > 0
+        Xd, yd = eng.get_rows(0, R)
+        assert np.array_equal(Xd, X) and np.array_equal(yd, y)
+    with pkg.SGDEngine(R, C, 1000, 0.1) as eng:
+        st1 = eng.load_csv(str(csv), cache=True)
+        assert st1["from_cache"] == 0 and st1["cache_written"] == 1 and os.path.exists(str(csv) + ".f32")
+        st2 = eng.load_csv(str(csv), cache=True)
+        assert st2["from_cache"] == 1 and st2["parse_seconds"] == 0
+        Xd, yd = eng.get_rows(0, R)
+        assert np.array_equal(Xd, X) and np.array_equal(yd, y)
+    # a shard of a two-rank layout loads its rows only
+    with pkg.SGDEngine(R, C, 1000, 0.1, rank=1, nranks=2) as sh:
+        st3 = sh.load_csv(str(csv), cache=True)
+        assert st3["from_cache"] == 1 and st3["bytes_uploaded"] == (R // 2) * (C + 1) * 4
+        Xs, ys = sh.get_rows(R // 2, R // 2)
+        assert np.array_equal(Xs, X[R // 2:]) and np.array_equal(ys, y[R // 2:])
+    # the CSV changes -> the cache is stale and is rebuilt
+    X[0, 0] = 42.0
+    pkg.write_csv(str(csv), X, y)
+    with pkg.SGDEngine(R, C, 1000, 0.1) as eng:
+        st4 = eng.load_csv(str(csv), cache=True)
+        assert st4["from_cache"] == 0 and st4["cache_written"] == 1
+        assert eng.get_rows(0, 1)[0][0, 0] == 42.0
+    # errors: as sgd_read_csv
+    with pkg.SGDEngine(10, 3, 5, 0.1) as eng:
+        with pytest.raises(pkg.SgdError) as ei:
+            eng.load_csv(str(tmp_path / "missing.csv"))
+        assert ei.value.code == pkg._lib.SGD_ERR_IO
+        bad = tmp_path / "bad.csv"
+        bad.write_text("1,2,3,4,5\n")
+        with pytest.raises(pkg.SgdError) as ei:
+            eng.load_csv(str(bad))
+        assert ei.value.code == pkg._lib.SGD_ERR_PARSE
+        short = tmp_path / "short.csv"
+        short.write_text("1,2,3,4\n5,6,7,8\n")            # fewer lines than announced: the rest is zero
+        eng.load_csv(str(short))
+        Xs, ys = eng.get_rows(0, 10)
+        assert Xs[1].tolist() == [5.0, 6.0, 7.0] and ys[1] == 8.0 and not Xs[2:].any() and not ys[2:].any()
+
+
 def test_experiment_runner_feature_sweep(tmp_path):
     data = str(tmp_path / "data") + "/"
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "run_experiment.py"), "--generate", "-i", data,
