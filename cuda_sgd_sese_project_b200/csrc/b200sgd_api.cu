@@ -155,9 +155,12 @@ struct sgd_ctx {
   float* d_w = nullptr;
   float* d_wtrue = nullptr;
   int32_t* d_perm[2] = {nullptr, nullptr};  // global permutation, double-buffered across epochs
-  int32_t* d_perm_local = nullptr;          // nranks > 1: bucketed local rows
-  int64_t* d_step_off = nullptr;            // nranks > 1: nb+1 offsets
+  // nranks > 1: bucketed local rows and nb+1 step offsets, one set per permutation buffer (the
+  // schedule of epoch e+1 is built on the shuffle stream while epoch e still reads the other set)
+  int32_t* d_perm_local[2] = {nullptr, nullptr};
+  int64_t* d_step_off[2] = {nullptr, nullptr};
   int64_t* d_counts = nullptr;
+  bool bucketed[2] = {false, false};        // the set belongs to the permutation in d_perm[i]
   float4* d_partials = nullptr;
   float4* d_wstage = nullptr;
   uint4* d_ll_part = nullptr;  // DATAFLOW reduction: tagged partials [grid][C4][2]
@@ -275,8 +278,8 @@ void free_all(sgd_ctx* c) {
     if (c->peer_open[i] && c->peer_block[i]) cudaIpcCloseMemHandle(c->peer_block[i]);
   if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
   cudaFree(c->d_rec); cudaFree(c->d_w); cudaFree(c->d_wtrue);
-  cudaFree(c->d_perm[0]); cudaFree(c->d_perm[1]); cudaFree(c->d_perm_local);
-  cudaFree(c->d_step_off); cudaFree(c->d_counts); cudaFree(c->d_partials); cudaFree(c->d_wstage);
+  cudaFree(c->d_perm[0]); cudaFree(c->d_perm[1]); cudaFree(c->d_perm_local[0]); cudaFree(c->d_perm_local[1]);
+  cudaFree(c->d_step_off[0]); cudaFree(c->d_step_off[1]); cudaFree(c->d_counts); cudaFree(c->d_partials); cudaFree(c->d_wstage);
   cudaFree(c->d_glast); cudaFree(c->d_rout); cudaFree(c->d_bar); cudaFree(c->d_ctl);
   cudaFree(c->d_ll_part); cudaFree(c->d_ll_w); cudaFree(c->d_dbg); cudaFree(c->d_loss);
   cudaFree(c->d_tgt); cudaFree(c->d_cnt); cudaFree(c->d_start); cudaFree(c->d_hits); cudaFree(c->d_first);
@@ -601,8 +604,8 @@ void fill_params(sgd_ctx* c, b200sgd::EpochParams* p, int32_t epoch, int buf) {
   p->ld = c->ld;
   p->C = c->C;
   p->C4 = c->C4;
-  p->perm = c->cfg.nranks > 1 ? c->d_perm_local : c->d_perm[buf];
-  p->step_off = c->cfg.nranks > 1 ? c->d_step_off : nullptr;
+  p->perm = c->cfg.nranks > 1 ? c->d_perm_local[buf] : c->d_perm[buf];
+  p->step_off = c->cfg.nranks > 1 ? c->d_step_off[buf] : nullptr;
   p->B = c->B;
   p->nb = c->nb;
   p->first_step = 0;
@@ -653,6 +656,7 @@ void fill_params(sgd_ctx* c, b200sgd::EpochParams* p, int32_t epoch, int buf) {
 int upload_perm(sgd_ctx* c, int buf) {
   // h_stage[buf] -> d_perm[buf] on the copy stream, once the last reader of d_perm[buf] is done;
   // the compute stream waits on ev_perm[buf] before it uses the buffer
+  c->bucketed[buf] = false;
   CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->ev_done[buf], 0));
   CUDA_TRY(cudaMemcpyAsync(c->d_perm[buf], c->h_stage[buf], sizeof(int32_t) * (size_t)c->R,
                            cudaMemcpyHostToDevice, c->copy_stream));
@@ -660,17 +664,20 @@ int upload_perm(sgd_ctx* c, int buf) {
   return SGD_OK;
 }
 
-// nranks > 1: keep, per step, the rows this rank owns.  Runs on the compute stream.
-int bucket_perm(sgd_ctx* c, int buf, int* launches) {
-  if (c->cfg.nranks == 1 || c->nb == 0) return SGD_OK;
+// nranks > 1: keep, per step, the rows this rank owns.  Runs on `st`: the compute stream, or
+// the shuffle stream right behind the shared shuffle (then it is off the critical path between epochs).
+int bucket_perm(sgd_ctx* c, int buf, int* launches, cudaStream_t st = nullptr) {
+  if (c->cfg.nranks == 1 || c->nb == 0 || c->bucketed[buf]) return SGD_OK;
+  if (!st) st = c->stream;
   const int blocks = std::min(c->nb, 4 * c->num_sms);
-  b200sgd::sgd_bucket_count_kernel<<<blocks, 256, 0, c->stream>>>(
+  b200sgd::sgd_bucket_count_kernel<<<blocks, 256, 0, st>>>(
       c->d_perm[buf], c->B, c->nb, c->row_begin, c->row_end, c->d_counts);
-  b200sgd::sgd_scan_kernel<<<1, 1024, 0, c->stream>>>(c->d_counts, c->nb, c->d_step_off);
-  b200sgd::sgd_bucket_write_kernel<<<blocks, 256, 0, c->stream>>>(
-      c->d_perm[buf], c->B, c->nb, c->row_begin, c->row_end, c->d_step_off, c->d_perm_local);
+  b200sgd::sgd_scan_kernel<<<1, 1024, 0, st>>>(c->d_counts, c->nb, c->d_step_off[buf]);
+  b200sgd::sgd_bucket_write_kernel<<<blocks, 256, 0, st>>>(
+      c->d_perm[buf], c->B, c->nb, c->row_begin, c->row_end, c->d_step_off[buf], c->d_perm_local[buf]);
   *launches += 3;
   CUDA_TRY(cudaGetLastError());
+  c->bucketed[buf] = true;
   return SGD_OK;
 }
 
@@ -822,6 +829,7 @@ void prepare_stream_states(sgd_ctx* c, int buf) {
 // d_perm[src] on the compute stream.  No host sync.
 int enqueue_device_shuffle(sgd_ctx* c, int stage_buf, int src, int dst, int* launches) {
   const int64_t n = c->R;
+  c->bucketed[dst] = false;
   CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->ev_done[2], 0));  // previous shuffle done with d_states
   CUDA_TRY(cudaMemcpyAsync(c->d_states, c->h_states[stage_buf], sizeof(uint32_t) * 31 * (size_t)c->nchunks,
                            cudaMemcpyHostToDevice, c->copy_stream));
@@ -838,11 +846,12 @@ int enqueue_device_shuffle(sgd_ctx* c, int stage_buf, int src, int dst, int* lau
                                                                              c->d_tilesum + c->scan_tiles);
   b200sgd::scan_apply_kernel<<<c->scan_tiles, b200sgd::kScanBlock, 0, c->shuf_stream>>>(
       c->d_cnt, n, c->d_tilesum, c->d_tilesum + c->scan_tiles, c->d_start);
-  CUDA_TRY(cudaMemsetAsync(c->d_cnt, 0, sizeof(int32_t) * ((size_t)n + 1), c->shuf_stream));
-  b200sgd::shuf_fill_kernel<<<blocks, 256, 0, c->shuf_stream>>>(c->d_tgt, n, c->d_start, c->d_cnt, c->d_hits);
-  b200sgd::shuf_order_kernel<<<blocks, 256, 0, c->shuf_stream>>>(n, c->d_start, c->d_hits, c->d_first);
-  b200sgd::shuf_resolve_kernel<<<blocks, 256, 0, c->shuf_stream>>>(c->d_tgt, n, c->d_start, c->d_hits, c->d_first,
-                                                            c->d_perm[src], c->d_perm[dst]);
+  // the fill cursors start at the lists' offsets; afterwards the array is free and takes the successors
+  CUDA_TRY(cudaMemcpyAsync(c->d_cnt, c->d_start, sizeof(int32_t) * ((size_t)n + 1), cudaMemcpyDeviceToDevice, c->shuf_stream));
+  b200sgd::shuf_fill_kernel<<<blocks, 256, 0, c->shuf_stream>>>(c->d_tgt, n, c->d_cnt, c->d_hits);
+  b200sgd::shuf_order_kernel<<<blocks, 256, 0, c->shuf_stream>>>(n, c->d_start, c->d_hits, c->d_first, c->d_cnt);
+  b200sgd::shuf_resolve_kernel<<<blocks, 256, 0, c->shuf_stream>>>(c->d_tgt, n, c->d_cnt, c->d_first, c->d_perm[src],
+                                                            c->d_perm[dst]);
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaEventRecord(c->ev_done[2], c->shuf_stream));
   CUDA_TRY(cudaEventRecord(c->ev_shuf[dst], c->shuf_stream));
@@ -881,7 +890,12 @@ int enqueue_own_map(sgd_ctx* c, int64_t k, int* launches) {
   }
   CUDA_TRY(cudaMemcpyAsync(c->d_states, c->h_states_own[b], sizeof(uint32_t) * 31 * (size_t)c->nchunks, cudaMemcpyHostToDevice, st));
   CUDA_TRY(cudaEventRecord(c->ev_own_up[b], st));
-  const int blocks = (int)std::min<int64_t>((n + 255) / 256, (int64_t)c->num_sms * 16);
+  // At most 8 / N blocks per SM: a map is needed every N-th epoch only, and a GPU filled with long-running
+  // map blocks keeps the next epoch's cooperative step kernel from starting until they drain (one
+  // 256-thread block fits an SM beside a step CTA; more do not) -- measured at N = 8 as ~2.8 ms per epoch
+  int bps = std::max(1, 8 / N);
+  if (const char* e = std::getenv("B200SGD_MAP_BLOCKS_PER_SM")) bps = std::max(1, std::atoi(e));
+  const int blocks = (int)std::min<int64_t>((n + 255) / 256, (int64_t)c->num_sms * bps);
   int32_t* map = (int32_t*)((char*)c->d_xchg_block + c->src_off[b]);
   CUDA_TRY(cudaMemsetAsync(c->d_cnt, 0, sizeof(int32_t) * ((size_t)n + 1), st));
   b200sgd::shuf_targets_stream_kernel<<<(int)((c->nchunks + 127) / 128), 128, 0, st>>>(c->d_states, c->chunk_len, c->nchunks, n,
@@ -890,10 +904,10 @@ int enqueue_own_map(sgd_ctx* c, int64_t k, int* launches) {
   b200sgd::scan_tile_offsets_kernel<<<1, b200sgd::kScanBlock, 0, st>>>(c->d_tilesum, c->scan_tiles, c->d_tilesum + c->scan_tiles);
   b200sgd::scan_apply_kernel<<<c->scan_tiles, b200sgd::kScanBlock, 0, st>>>(c->d_cnt, n, c->d_tilesum, c->d_tilesum + c->scan_tiles,
                                                                         c->d_start);
-  CUDA_TRY(cudaMemsetAsync(c->d_cnt, 0, sizeof(int32_t) * ((size_t)n + 1), st));
-  b200sgd::shuf_fill_kernel<<<blocks, 256, 0, st>>>(c->d_tgt, n, c->d_start, c->d_cnt, c->d_hits);
-  b200sgd::shuf_order_kernel<<<blocks, 256, 0, st>>>(n, c->d_start, c->d_hits, c->d_first);
-  b200sgd::shuf_resolve_kernel<<<blocks, 256, 0, st>>>(c->d_tgt, n, c->d_start, c->d_hits, c->d_first, nullptr, map);
+  CUDA_TRY(cudaMemcpyAsync(c->d_cnt, c->d_start, sizeof(int32_t) * ((size_t)n + 1), cudaMemcpyDeviceToDevice, st));
+  b200sgd::shuf_fill_kernel<<<blocks, 256, 0, st>>>(c->d_tgt, n, c->d_cnt, c->d_hits);
+  b200sgd::shuf_order_kernel<<<blocks, 256, 0, st>>>(n, c->d_start, c->d_hits, c->d_first, c->d_cnt);
+  b200sgd::shuf_resolve_kernel<<<blocks, 256, 0, st>>>(c->d_tgt, n, c->d_cnt, c->d_first, nullptr, map);
   b200sgd::PeerFlagPtrs t{};
   for (int r = 0; r < N; ++r) t.p[r] = (uint32_t*)((char*)c->peer_block[r] + c->flag_off);
   b200sgd::shuf_set_flags_kernel<<<1, 32, 0, st>>>(t, N, kFlagReady + me * 2 + b, (uint32_t)k);
@@ -938,6 +952,9 @@ int enqueue_shared_shuffle(sgd_ctx* c, int src, int dst, int* launches) {
   t.p[0] = (uint32_t*)((char*)c->peer_block[owner] + c->flag_off);
   b200sgd::shuf_set_flags_kernel<<<1, 32, 0, st>>>(t, 1, kFlagDone + b * 8 + me, (uint32_t)k);
   CUDA_TRY(cudaGetLastError());
+  // the schedule of the new permutation right behind it (d_counts: only this stream uses it in this mode)
+  c->bucketed[dst] = false;
+  SGD_TRY(bucket_perm(c, dst, launches, st));
   CUDA_TRY(cudaEventRecord(c->ev_shuf[dst], st));
   c->shuf_no = k;
   *launches += 3;
@@ -1218,8 +1235,10 @@ int sgd_create(const sgd_config* cfg, const float* X, const float* y, sgd_ctx** 
       CUDA_TRY(cudaMalloc(&c->d_perm[i], sizeof(int32_t) * (size_t)c->R));
     }
     if (c->cfg.nranks > 1) {
-      CUDA_TRY(cudaMalloc(&c->d_perm_local, sizeof(int32_t) * (size_t)std::max<int64_t>(1, c->local_rows)));
-      CUDA_TRY(cudaMalloc(&c->d_step_off, sizeof(int64_t) * ((size_t)c->nb + 1)));
+      for (int i = 0; i < 2; ++i) {
+        CUDA_TRY(cudaMalloc(&c->d_perm_local[i], sizeof(int32_t) * (size_t)std::max<int64_t>(1, c->local_rows)));
+        CUDA_TRY(cudaMalloc(&c->d_step_off[i], sizeof(int64_t) * ((size_t)c->nb + 1)));
+      }
       CUDA_TRY(cudaMalloc(&c->d_counts, sizeof(int64_t) * ((size_t)c->nb + 1)));
     }
     CUDA_TRY(cudaMalloc(&c->d_partials, sizeof(float4) * 2 * (size_t)c->grid * c->C4));
@@ -1943,10 +1962,10 @@ int sgd_get_local_schedule(sgd_ctx* c, int32_t* local_perm, int64_t local_cap, i
   if (c->cfg.nranks < 2) return fail(SGD_ERR_STATE, "single-rank contexts have no bucketed schedule");
   SGD_TRY(bind(c));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
-  CUDA_TRY(cudaMemcpy(step_off, c->d_step_off, sizeof(int64_t) * ((size_t)c->nb + 1), cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(step_off, c->d_step_off[c->cur], sizeof(int64_t) * ((size_t)c->nb + 1), cudaMemcpyDeviceToHost));
   const int64_t n = step_off[c->nb];
   if (n > local_cap) return fail(SGD_ERR_ARG, "local_perm too small");
-  CUDA_TRY(cudaMemcpy(local_perm, c->d_perm_local, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(local_perm, c->d_perm_local[c->cur], sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost));
   return SGD_OK;
 }
 

@@ -20,9 +20,10 @@
 //
 //   K1 targets : regenerate the stream chunk by chunk, j_i = rand() % (i+1), count hits per position
 //   K2 scan    : exclusive prefix sum of the counts  -> CSR offsets
-//   K3 fill    : scatter i into its target's list (atomic cursor, arbitrary order)
-//   K4 order   : sort every (tiny) list ascending, record first(hits(p))
-//   K5 resolve : one thread per value follows its trajectory and writes out[final] = in[i]
+//   K3 fill    : scatter i into its target's list (atomic cursor that starts at the list's offset)
+//   K4 order   : sort every (tiny) list ascending, record first(hits(p)) and every hit's successor nxt[i]
+//   K5 resolve : one thread per value follows its trajectory (nxt[i], then first[..]) and writes out[final] = in[i]
+// (~6.5 random 32-byte accesses per element in total: they, not the arithmetic, are the cost)
 //
 // tests/test_gpu_shuffle.py checks it against the host loop and the golden vectors of
 // tests/golden/thirdparty_kat.json (real glibc + libstdc++ outputs).
@@ -157,19 +158,38 @@ __global__ void __launch_bounds__(kScanBlock) scan_apply_kernel(const int32_t* _
   if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = *grand_total;
 }
 
-// cursor must be zero on entry
+// cursor must hold a copy of the CSR offsets (`start`) on entry: one random access (the atomic) finds the
+// slot, instead of a read of start[j] plus an atomic on a zeroed counter.  Four elements per thread in
+// flight: the kernel mostly runs beside the persistent step kernel, one block per SM.
 __global__ void __launch_bounds__(256) shuf_fill_kernel(const uint32_t* __restrict__ tgt, int64_t n,
-                                                        const int32_t* __restrict__ start,
                                                         int32_t* __restrict__ cursor, int32_t* __restrict__ hits) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x + 1; i < n;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const uint32_t j = tgt[i];
-    if ((int64_t)j != i) hits[start[j] + atomicAdd(cursor + j, 1)] = (int32_t)i;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x + 1; i0 < n; i0 += 4 * stride) {
+    uint32_t j[4];
+    int32_t slot[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t i = i0 + u * stride;
+      j[u] = i < n ? tgt[i] : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t i = i0 + u * stride;
+      slot[u] = (i < n && (int64_t)j[u] != i) ? atomicAdd(cursor + j[u], 1) : -1;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (slot[u] >= 0) hits[slot[u]] = (int32_t)(i0 + u * stride);
   }
 }
 
+// Sorts every (tiny) list, records first(hits(p)) and, for every hit i of p, its SUCCESSOR in the list:
+// nxt[i] = the next later step that targets the same position, or -1 (i is the last one: the value that
+// moved to p at time i stays there).  The resolve pass then reads nxt[i] in order instead of looking the
+// list of its target up (start[j], hits[..]: two random reads per value less).
 __global__ void __launch_bounds__(256) shuf_order_kernel(int64_t n, const int32_t* __restrict__ start,
-                                                         int32_t* __restrict__ hits, int32_t* __restrict__ first) {
+                                                         int32_t* __restrict__ hits, int32_t* __restrict__ first,
+                                                         int32_t* __restrict__ nxt) {
   for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n;
        p += (int64_t)gridDim.x * blockDim.x) {
     const int32_t lo = start[p], hi = start[p + 1];
@@ -183,35 +203,51 @@ __global__ void __launch_bounds__(256) shuf_order_kernel(int64_t n, const int32_
       hits[b + 1] = key;
     }
     first[p] = hi > lo ? hits[lo] : -1;
+    for (int32_t a = lo; a < hi; ++a) nxt[hits[a]] = (a + 1 < hi) ? hits[a + 1] : -1;
   }
 }
 
 __global__ void __launch_bounds__(256) shuf_resolve_kernel(const uint32_t* __restrict__ tgt, int64_t n,
-                                                           const int32_t* __restrict__ start,
-                                                           const int32_t* __restrict__ hits,
+                                                           const int32_t* __restrict__ nxt,
                                                            const int32_t* __restrict__ first,
                                                            const int32_t* __restrict__ in, int32_t* __restrict__ out) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    int32_t pos = (int32_t)i;
-    bool settled = false;
-    const uint32_t j = tgt[i];
-    if (i >= 1 && (int64_t)j != i) {
-      // moved to j at time i; thrown out again by the next hit of j after time i, if any
-      const int32_t lo = start[j], hi = start[j + 1];
-      int32_t nxt = -1;
-      for (int32_t a = lo; a < hi; ++a) {
-        const int32_t h = hits[a];
-        if (h > (int32_t)i) { nxt = h; break; }
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += 4 * stride) {
+    int32_t pos[4], val[4];
+    bool live[4];  // still travelling
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t i = i0 + u * stride;
+      pos[u] = (int32_t)i;
+      live[u] = i < n;
+      val[u] = 0;
+      if (i < n) {
+        val[u] = in ? in[i] : (int32_t)i;  // in == nullptr: the position map itself (out[final] = i)
+        const uint32_t j = tgt[i];
+        if (i >= 1 && (int64_t)j != i) {
+          // moved to j at time i; thrown out again by the next hit of j after time i, if any
+          const int32_t nx = nxt[i];
+          if (nx < 0) { pos[u] = (int32_t)j; live[u] = false; }
+          else pos[u] = nx;
+        }
       }
-      if (nxt < 0) { pos = (int32_t)j; settled = true; }
-      else pos = nxt;
     }
-    if (!settled) {
-      int32_t nx;
-      while ((nx = first[pos]) >= 0) pos = nx;
+    // from then on: the first hit of every position it lands on (all four chains advance together)
+    bool any = true;
+    while (any) {
+      int32_t nx[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) nx[u] = live[u] ? first[pos[u]] : -1;
+      any = false;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (nx[u] >= 0) { pos[u] = nx[u]; any = true; }
+        else live[u] = false;
+      }
     }
-    out[pos] = in ? in[i] : (int32_t)i;  // in == nullptr: the position map itself (out[final] = i)
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (i0 + u * stride < n) out[pos[u]] = val[u];
   }
 }
 
