@@ -126,14 +126,19 @@ class ClockSampler:
                 "samples": len(self.samples)}
 
 
-def profile_traffic(key: str):
-    """dram bytes per launch of the epoch kernel from the committed ncu --set full capture of THIS
-    shape (profiles/roofline_traffic.json), or None when the shape has no capture."""
+def profile_traffic(key: str, alg_bytes: int):
+    """DRAM bytes per launch of the epoch kernel: the traffic / algorithmic ratio of the committed
+    `ncu --set full` capture of THIS step shape (profiles/roofline_traffic.json) times the algorithmic
+    bytes of this launch; (None, None) when the shape has no capture."""
     try:
         with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
-            return json.load(f).get(key)
+            e = json.load(f).get(key)
+        if not e:
+            return None, None
+        return int(e["ratio"] * alg_bytes), (f"ncu dram__bytes_read+write / algorithmic = {e['ratio']:.4f} measured on the same kernel "
+                                             f"and step shape ({e['captured_step']}; {e['capture']}), times the algorithmic bytes of this launch")
     except Exception:
-        return None
+        return None, None
 
 
 def perm_checksum(perm: np.ndarray) -> int:
@@ -518,7 +523,7 @@ def main() -> int:
         achieved = bytes_rank / loop_s * 1e-9                      # GB/s per GPU, step loop
         steps_epoch = t["steps"] // K
         rows_step_gpu = B / N
-        traffic_key = f"{args.workload}_n{N}"
+        traffic, traffic_note = profile_traffic(f"{args.workload}_n{N}", bytes_rank // K)
         line = {
             "metric": "samples_per_sec_per_sgd_epoch", "value": samples / wall, "unit": "samples/s",
             "n_gpus": N, "steps": K, "warmup": W, "ms_per_step": wall * 1e3 / K,
@@ -539,7 +544,7 @@ def main() -> int:
                          "us_per_sgd_step": loop_s * 1e6 / t["steps"], "hbm_gbs_per_gpu": achieved,
                          "rows_per_gpu_and_step": rows_step_gpu},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": profile_traffic(traffic_key),
+                         "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note,
                          "peak_source": peak_src, "kernel": kernel_name.split("<")[0].split(" (")[0] + " (1 launch per epoch)",
                          "algorithmic_bytes_per_launch": bytes_rank // K,
                          "step": f"{rows_step_gpu:.0f} rows x {cols} features per GPU"},

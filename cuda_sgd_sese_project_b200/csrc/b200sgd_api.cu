@@ -794,7 +794,9 @@ int launch_epoch(sgd_ctx* c, int32_t epoch, int buf, int* launches) {
     at[1].id = cudaLaunchAttributeCooperative;
     at[1].val.cooperative = 1;
     lc.attrs = at;
-    lc.numAttrs = (c->clt_ng > 1 && c->cluster_coop) ? 2 : 1;
+    // (B200SGD_NO_COOP=1: ncu cannot replay a launch that is both cooperative and clustered; without the
+    // attribute co-residency rests on the occupancy check of configure_launch, which holds on an idle GPU)
+    lc.numAttrs = (c->clt_ng > 1 && c->cluster_coop && !std::getenv("B200SGD_NO_COOP")) ? 2 : 1;
     cudaError_t e = cudaLaunchKernelExC(&lc, c->kc.fn_clt, args);
     if (e != cudaSuccess && lc.numAttrs == 2) {  // cooperative + cluster refused: the occupancy check stands in
       cudaGetLastError();
