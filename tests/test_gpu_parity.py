@@ -428,3 +428,45 @@ def test_config_c2_full_size_properties(kat):
     assert rel_l2(w, w_o) <= W_TOL
     # the fit has converged to fp32 resolution of the labels (|y| ~ 450): the MAE is rounding noise
     assert abs(mae - mae_o) <= MAE_TOL * mae_o + 1e-6 * float(np.mean(np.abs(y)))
+
+
+# ------------------------------------------------------------------ BASELINE configs 4 and 5 at full size
+@pytest.mark.slow
+@pytest.mark.parametrize("R,C,B,lr,tol", [
+    (16777216, 2048, 4096, 0.1, 2e-3),      # config 4: 138.5 GB of records on one GPU, 4096 steps
+    (16777216, 2048, 65536, 0.1, 0.9),      # config 4 at the streaming batch size: 256 steps (far from converged)
+    (8388608, 512, 8192, 0.1, 2e-3),        # config 5's per-GPU shape at 8 GPUs (1024 steps of 8192 rows)
+    (67108864, 512, 65536, 0.1, 0.6),       # config 5 on one GPU: 141.7 GB, 1024 steps of 65536 rows
+])
+def test_configs_4_and_5_full_size_properties(kat, R, C, B, lr, tol):
+    """One epoch at full size: the golden permutation checksum (real glibc + libstdc++), the step count,
+    finite weights that moved towards the generating ones, a mean absolute error consistent with them
+    (an independent pass over the data), and the running loss of the epoch (summed inside the step
+    kernel) equal to what the residual statistics imply."""
+    with pkg.SGDEngine(R, C, B, lr) as eng:
+        eng.load_synthetic(seed=42)
+        w0 = eng.weights
+        wt = eng.true_weights()
+        mae0 = eng.calculate_mean_abs_error()
+        t = eng.run(1, 1)
+        assert t["steps"] == R // B and t["samples"] == (R // B) * B
+        rec = [r for r in kat["shuffle_kat"] if r["R"] == R and r["epoch"] == 1]
+        if rec:
+            perm = eng.permutation()
+            i = np.arange(1, R + 1, dtype=np.uint64)
+            assert perm[:4].tolist() == rec[0]["head"] and int(perm[-1]) == rec[0]["last"]
+            assert int((i * perm.astype(np.uint64)).sum(dtype=np.uint64)) == rec[0]["checksum"]
+            del perm, i
+        w = eng.weights
+        assert np.all(np.isfinite(w))
+        e0, e1 = rel_l2(w0, wt), rel_l2(w, wt)
+        assert e1 < tol and e1 < 0.9 * e0, (e0, e1)
+        mae = eng.calculate_mean_abs_error()
+        assert mae < mae0 and np.isfinite(mae)
+        # |X (w - w*)| for X ~ N(0, 1): the residual is N(0, |w - w*|^2), so its mean absolute value is
+        # sqrt(2 / pi) |w - w*| (labels are y = X w* up to fp32 rounding of a C-term sum)
+        want = np.sqrt(2 / np.pi) * float(np.linalg.norm(w.astype(np.float64) - wt))
+        noise = 4e-7 * float(np.linalg.norm(wt)) * np.sqrt(C)
+        assert abs(mae - want) <= 0.02 * want + noise, (mae, want)
+        la, lq = eng.loss_curve()
+        assert la.shape == (1,) and 0 < la[0] / t["samples"] < mae0 * 1.01      # running mean |r| of the epoch

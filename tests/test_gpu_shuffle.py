@@ -45,7 +45,7 @@ def test_device_and_host_paths_agree_and_interleave():
         assert np.array_equal(dev.permutation(), ref)
 
 
-@pytest.mark.parametrize("R", [4000000, 16777216])
+@pytest.mark.parametrize("R", [4000000, 16777216, 67108864])   # configs 2/3, 4 and 5
 def test_device_shuffle_golden_kat(kat, R):
     # golden values from the REAL glibc / libstdc++ (tests/golden/thirdparty_kat.json)
     recs = [r for r in kat["shuffle_kat"] if r["R"] == R]
