@@ -440,6 +440,20 @@ def main() -> int:
         ws = [None] * N
         dist.all_gather_object(ws, w_final.tobytes())
         replicas_identical = all(b2 == ws[0] for b2 in ws)
+    # ---- the same kernel WITHOUT the concurrent permutation work: shuffle first, then one epoch on its own
+    # (twice, the faster one).  In the timed region above the next epoch's permutation (random 32-byte
+    # DRAM accesses) runs beside the step kernel and slows its row stream; this line says what the kernel
+    # itself reaches on the same data.
+    alone_s = None
+    for it in range(2):
+        eng.shuffle()
+        barrier()
+        ti = eng.epoch(W + K + 1 + it)
+        tt = torch.tensor([ti["steploop_ms"] * 1e-3], dtype=torch.float64, device="cuda")
+        if N > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        alone_s = float(tt[0]) if alone_s is None else min(alone_s, float(tt[0]))
+    alone_bytes, alone_steps = ti["bytes"], ti["steps"]
     kernel_name, grid, reduce_mode = eng.kernel_name, eng.grid, eng.reduce
     ring_rows, smem_bytes, cluster_size = eng.nslots, eng.smem_bytes, eng.cluster_size
 
@@ -547,7 +561,12 @@ def main() -> int:
                          "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note,
                          "peak_source": peak_src, "kernel": kernel_name.split("<")[0].split(" (")[0] + " (1 launch per epoch)",
                          "algorithmic_bytes_per_launch": bytes_rank // K,
-                         "step": f"{rows_step_gpu:.0f} rows x {cols} features per GPU"},
+                         "step": f"{rows_step_gpu:.0f} rows x {cols} features per GPU",
+                         "timed_region": "K epochs of sgd_run: the next epoch's permutation kernels run beside the step kernel",
+                         "kernel_alone": {"achieved": alone_bytes / alone_s * 1e-9, "frac": alone_bytes / alone_s * 1e-9 / peak,
+                                          "us_per_sgd_step": alone_s * 1e6 / alone_steps,
+                                          "how": "same kernel, same data, one epoch launched after its permutation was complete "
+                                                 "(no concurrent kernels), CUDA events, best of 2, max over ranks"}},
             "clocks": clocks,
             "gpu_launches": t["launches"],
             "quality": {"mae": mae, "weights_rel_err_vs_generating_weights": w_err,

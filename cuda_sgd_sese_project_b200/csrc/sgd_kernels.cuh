@@ -517,10 +517,9 @@ __device__ __forceinline__ float4 tree_sum_sources(const float4* src, int64_t st
 //          (KC float4 of gradient per thread).  No cross-warp gradient scratch, so the ring is
 //          deeper; the staged row is read from shared memory twice instead of once.
 constexpr int kIdxStages = 4;  // rounds of permutation indices in flight per producer warp
-// Software pipeline of the consumers over the tiles of a step (rows of tile t+1 fetched into a second
-// register set before tile t is computed).  Measured in round 2: 2x SLOWER than the plain loop on every
-// shape (C = 512: 1475 vs 807 cycles per 16-row tile; spills and a 6000-instruction kernel), so off.
-constexpr bool kPipelineTiles = false;
+// (A software pipeline of the consumers over the tiles of a step -- rows of tile t+1 fetched into a second
+// register set before tile t is computed -- was measured in round 2: 2x SLOWER than the plain loops below on
+// every shape, C = 512: 1475 vs 807 cycles per 16-row tile, spills and a 6000-instruction kernel.  Removed.)
 template <int KC, int NW, bool WIDE, int U = 1, int CW = 0>
 struct EpochSmem {
   static constexpr int kRW = CW > 0 ? NW / CW : 1;                  // COLSPLIT: warps along the rows
@@ -1000,20 +999,15 @@ __global__ void __launch_bounds__(32 * (NW + NPMAX), 1)
       const int ridx = lane >> LG;     // the one whose dot product ends up in this lane
       const int n32 = (int)n;
       const int nt = (n32 + TR - 1) / TR;
-      // Software pipeline over the tiles (see the row mapping): my part of tile t+1 is fetched into
-      // a second register set -- if the tile has landed -- before tile t is reduced, exchanged
-      // (CTA barrier) and accumulated.
-      constexpr bool kPipe = kPipelineTiles && (RPW * KC <= 8);
-      float4 xa[RPW][KC], xb[kPipe ? RPW : 1][kPipe ? KC : 1];
-      float ya = 0.f, yb = 0.f;
-      auto take_tile = [&](uint32_t* tile, uint32_t* use) {
-        *tile = ctile;
-        *use = cuse;
+      for (int ti = 0; ti < nt; ++ti) {
+        const uint32_t tq = tqbase + (uint32_t)ti;
+        const uint32_t tile = ctile, use = cuse;
         if (++ctile == (uint32_t)ntiles) { ctile = 0; ++cuse; }
-      };
-      auto tile_cnt = [&](int ti) -> int { return (n32 - ti * TR) < TR ? (n32 - ti * TR) : TR; };
-      auto load_part = [&](auto& x, float& yv, uint32_t tile, int cnt) {
+        const int cnt = (n32 - ti * TR) < TR ? (n32 - ti * TR) : TR;
         const unsigned char* tbase = ring + (size_t)tile * tile_bytes + (size_t)row0 * p.slot_bytes;
+        mbar_wait(full0 + 8u * tile, use & 1u);
+        mark(7);  // (profile) time spent waiting for the rows to land
+        float4 x[RPW][KC];
 #pragma unroll
         for (int i = 0; i < RPW; ++i) {
           const float4* row = reinterpret_cast<const float4*>(tbase + (size_t)i * p.slot_bytes);
@@ -1024,12 +1018,10 @@ __global__ void __launch_bounds__(32 * (NW + NPMAX), 1)
             x[i][k] = (live && f < C4) ? row[f] : make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
-        yv = (row0 + ridx < cnt) ? reinterpret_cast<const float*>(tbase + (size_t)ridx * p.slot_bytes)[p.C] : 0.f;
+        const bool my_live = row0 + ridx < cnt;
+        const float yv = my_live ? reinterpret_cast<const float*>(tbase + (size_t)ridx * p.slot_bytes)[p.C] : 0.f;
         __syncwarp();
         if (lane == 0) mbar_arrive(empty0 + 8u * tile);  // my part of the tile is in registers
-      };
-      auto compute_part = [&](auto& x, float yv, int cnt, int ti) {
-        const bool my_live = row0 + ridx < cnt;
         float v[RPW];
 #pragma unroll
         for (int i = 0; i < RPW; ++i) {
@@ -1057,7 +1049,7 @@ __global__ void __launch_bounds__(32 * (NW + NPMAX), 1)
         }
 #pragma unroll
         for (int m = 16 >> LB; m >= 1; m >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], m);
-        float* pd = pd_s + ((tqbase + (uint32_t)ti) & 1u) * (CW * TRc);
+        float* pd = pd_s + (tq & 1u) * (CW * TRc);
         if ((lane & ((1 << LG) - 1)) == 0) pd[cg * TRc + row0 + ridx] = v[0];
         consumer_bar<kCT>();
         float dsum = pd[row0 + ridx];
@@ -1080,49 +1072,7 @@ __global__ void __launch_bounds__(32 * (NW + NPMAX), 1)
             g[k].w = fmaf(ri, x[i][k].w, g[k].w);
           }
         }
-      };
-      if constexpr (kPipe) {
-        uint32_t tile, use;
-        if (nt > 0) {
-          take_tile(&tile, &use);
-          mbar_wait(full0 + 8u * tile, use & 1u);
-          mark(7);  // (profile) time spent waiting for the rows to land
-          load_part(xa, ya, tile, tile_cnt(0));
-        }
-        for (int ti = 0; ti < nt; ++ti) {
-          const bool more = ti + 1 < nt;
-          bool early = false;
-          if (more) {
-            take_tile(&tile, &use);
-            early = __all_sync(0xffffffffu, mbar_try_wait(full0 + 8u * tile, use & 1u));
-            if (early) load_part(xb, yb, tile, tile_cnt(ti + 1));
-          }
-          compute_part(xa, ya, tile_cnt(ti), ti);
-          mark(0);  // (profile) rows of the tile processed
-          if (more) {
-            if (!early) {
-              mbar_wait(full0 + 8u * tile, use & 1u);
-              mark(7);
-              load_part(xb, yb, tile, tile_cnt(ti + 1));
-            }
-            ya = yb;
-#pragma unroll
-            for (int i = 0; i < RPW; ++i) {
-#pragma unroll
-              for (int k = 0; k < KC; ++k) xa[i][k] = xb[i][k];
-            }
-          }
-        }
-      } else {
-        for (int ti = 0; ti < nt; ++ti) {
-          uint32_t tile, use;
-          take_tile(&tile, &use);
-          mbar_wait(full0 + 8u * tile, use & 1u);
-          mark(7);
-          load_part(xa, ya, tile, tile_cnt(ti));
-          compute_part(xa, ya, tile_cnt(ti), ti);
-          mark(0);
-        }
+        mark(0);  // (profile) rows of the tile processed
       }
       tqbase += (uint32_t)nt;
     } else if constexpr (NARROW8) {
@@ -1202,23 +1152,20 @@ __global__ void __launch_bounds__(32 * (NW + NPMAX), 1)
       float4 wv[KC];
 #pragma unroll
       for (int k = 0; k < KC; ++k) wv[k] = w_s[k * 32 + lane];
-      // Software pipeline over the tiles of the step (kPipe: where two tiles' rows fit the registers):
-      // all warps wait for the same tile, so without it they load together (the shared-memory pipe is
-      // the only busy unit, ~530 cycles for a 67 KB tile) and then compute together (the pipe idles).
-      // With it the rows of tile t+1 are fetched -- if they have landed -- before tile t is computed.
-      constexpr bool kPipe = kPipelineTiles && (U * KC <= 8);
-      float4 xa[U][KC], xb[kPipe ? U : 1][kPipe ? KC : 1];
-      float ya[U], yb[kPipe ? U : 1];
-      auto take_tile = [&](uint32_t* tile, uint32_t* use) {  // the next ring tile of my sequence
-        *tile = ctile;
-        *use = cuse;
+      for (int ti = 0; ti < nt; ++ti) {
+        const uint32_t tile = ctile, use = cuse;
         if (++ctile == (uint32_t)ntiles) { ctile = 0; ++cuse; }
-      };
-      auto load_rows = [&](auto& x, auto& y, uint32_t tile, int cnt) {
+        const int cnt = (n32 - ti * TR) < TR ? (n32 - ti * TR) : TR;
         const unsigned char* tbase = ring + (size_t)tile * tile_bytes;
+        float4 x[U][KC];
+        float dot[U], dot2[U], y[U];
+        mbar_wait(full0 + 8u * tile, use & 1u);  // all rows of the tile have landed
+        mark(7);  // (profile) time spent waiting for the rows to land
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const int r = cw + u * NW;
+          dot[u] = 0.f;
+          dot2[u] = 0.f;
           y[u] = 0.f;
           if (r < cnt) {  // warp-uniform
             const float4* row = reinterpret_cast<const float4*>(tbase + (size_t)r * p.slot_bytes);
@@ -1235,11 +1182,6 @@ __global__ void __launch_bounds__(32 * (NW + NPMAX), 1)
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(empty0 + 8u * tile);  // my rows are in registers
-      };
-      auto compute_rows = [&](auto& x, auto& y, int cnt, int ti) {
-        float dot[U], dot2[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) dot[u] = dot2[u] = 0.f;
 #pragma unroll
         for (int k = 0; k < KC; ++k) {
 #pragma unroll
@@ -1281,50 +1223,7 @@ __global__ void __launch_bounds__(32 * (NW + NPMAX), 1)
             if (rr < cnt) o_r_out[off + lo + (int64_t)ti * TR + rr] = r;
           }
         }
-      };
-      auto tile_cnt = [&](int ti) -> int { return (n32 - ti * TR) < TR ? (n32 - ti * TR) : TR; };
-      if constexpr (kPipe) {
-        uint32_t tile, use;
-        if (nt > 0) {
-          take_tile(&tile, &use);
-          mbar_wait(full0 + 8u * tile, use & 1u);  // all rows of the tile have landed
-          mark(7);  // (profile) time spent waiting for the rows to land
-          load_rows(xa, ya, tile, tile_cnt(0));
-        }
-        for (int ti = 0; ti < nt; ++ti) {
-          const bool more = ti + 1 < nt;
-          bool early = false;
-          if (more) {
-            take_tile(&tile, &use);
-            early = __all_sync(0xffffffffu, mbar_try_wait(full0 + 8u * tile, use & 1u));
-            if (early) load_rows(xb, yb, tile, tile_cnt(ti + 1));
-          }
-          compute_rows(xa, ya, tile_cnt(ti), ti);
-          mark(0);  // (profile) rows of the tile processed
-          if (more) {
-            if (!early) {
-              mbar_wait(full0 + 8u * tile, use & 1u);
-              mark(7);
-              load_rows(xb, yb, tile, tile_cnt(ti + 1));
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-              ya[u] = yb[u];
-#pragma unroll
-              for (int k = 0; k < KC; ++k) xa[u][k] = xb[u][k];
-            }
-          }
-        }
-      } else {
-        for (int ti = 0; ti < nt; ++ti) {
-          uint32_t tile, use;
-          take_tile(&tile, &use);
-          mbar_wait(full0 + 8u * tile, use & 1u);
-          mark(7);
-          load_rows(xa, ya, tile, tile_cnt(ti));
-          compute_rows(xa, ya, tile_cnt(ti), ti);
-          mark(0);
-        }
+        mark(0);  // (profile) rows of the tile processed
       }
       tqbase += (uint32_t)nt;
     }
