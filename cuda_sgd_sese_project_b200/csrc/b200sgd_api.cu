@@ -105,7 +105,8 @@ bool choose_kernel(int C4, int64_t rows_per_cta, KernelChoice* out) {
   if (C4 <= 32) {
     if (rows_per_cta <= 8) *out = make_choice<1, 1, 8>();
     else if (rows_per_cta <= 16) *out = make_choice<1, 2, 8>();
-    else *out = make_choice<1, 4, 8, false, true, true>();  // 8 lanes per row, 4 rows per warp
+    else if (rows_per_cta >= 128 && v == 4) *out = make_choice<1, 8, 8, false, true, true>();  // A/B: 2 x 4 rows per warp, tiles of 64 (no gain: 13.1 vs 12.8 us at B = 100000)
+    else *out = make_choice<1, 4, 8, false, true, true>();  // 8 lanes per row, 4 rows per warp, tiles of 32
   } else if (C4 <= 64) {
     if (v == 8) *out = make_choice<1, 8, 8, false, false, false, 2>();   // COLSPLIT 2 x 4 warps (A/B)
     else *out = make_choice<2, 4, 8>();                                  // rows: 4 per warp in flight, tiles of 32
@@ -587,9 +588,15 @@ int make_record_tensor_map(sgd_ctx* c) {
   const cuuint64_t gstride[1] = {(cuuint64_t)c->ld * 4};
   const cuuint32_t box[2] = {(cuuint32_t)c->ld, 1};
   const cuuint32_t estr[2] = {1, 1};
+  CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_NONE;
+  if (const char* e = std::getenv("B200SGD_L2_PROMO")) {  // experiment: 1 = 64 B, 2 = 128 B, 3 = 256 B
+    const int v = std::atoi(e);
+    promo = v == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : v == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+          : v == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_NONE;
+  }
   const CUresult r = ((encode_fn)fn)(&c->rec_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, c->d_rec, gdim, gstride, box, estr,
-                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                     CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo,
+                                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   c->have_rec_map = (r == CUDA_SUCCESS);
   // the generic kernel issues gather4 when its ring tile is a whole number of four-row groups
   c->use_gather4 = c->have_rec_map && c->kc.tile_rows() % 4 == 0 && !c->kc.wide;
@@ -818,6 +825,8 @@ int launch_epoch(sgd_ctx* c, int32_t epoch, int buf, int* launches) {
   return SGD_OK;
 }
 
+size_t shuf_smem_bytes();
+
 // Host part of one device shuffle: the start state of every chunk of the n-1 values of the rand()
 // stream this epoch consumes (main.cu:90 / :207 consume exactly n-1 per std::random_shuffle), by
 // jump-ahead; then the host generator is moved past the epoch.  ~1 us per chunk.
@@ -841,7 +850,7 @@ int enqueue_device_shuffle(sgd_ctx* c, int stage_buf, int src, int dst, int* lau
   CUDA_TRY(cudaStreamWaitEvent(c->shuf_stream, c->ev_perm[src], 0));  // d_perm[src] uploaded (sgd_set_permutation)
   const int blocks = (int)std::min<int64_t>((n + 255) / 256, (int64_t)c->num_sms * 16);
   CUDA_TRY(cudaMemsetAsync(c->d_cnt, 0, sizeof(int32_t) * ((size_t)n + 1), c->shuf_stream));
-  b200sgd::shuf_targets_stream_kernel<<<(int)((c->nchunks + 127) / 128), 128, 0, c->shuf_stream>>>(
+  b200sgd::shuf_targets_stream_kernel<<<(int)((c->nchunks + 127) / 128), 128, shuf_smem_bytes(), c->shuf_stream>>>(
       c->d_states, c->chunk_len, c->nchunks, n, c->d_tgt, c->d_cnt);
   b200sgd::scan_tile_sums_kernel<<<c->scan_tiles, b200sgd::kScanBlock, 0, c->shuf_stream>>>(c->d_cnt, n, c->d_tilesum);
   b200sgd::scan_tile_offsets_kernel<<<1, b200sgd::kScanBlock, 0, c->shuf_stream>>>(c->d_tilesum, c->scan_tiles,
@@ -850,9 +859,9 @@ int enqueue_device_shuffle(sgd_ctx* c, int stage_buf, int src, int dst, int* lau
       c->d_cnt, n, c->d_tilesum, c->d_tilesum + c->scan_tiles, c->d_start);
   // the fill cursors start at the lists' offsets; afterwards the array is free and takes the successors
   CUDA_TRY(cudaMemcpyAsync(c->d_cnt, c->d_start, sizeof(int32_t) * ((size_t)n + 1), cudaMemcpyDeviceToDevice, c->shuf_stream));
-  b200sgd::shuf_fill_kernel<<<blocks, 256, 0, c->shuf_stream>>>(c->d_tgt, n, c->d_cnt, c->d_hits);
-  b200sgd::shuf_order_kernel<<<blocks, 256, 0, c->shuf_stream>>>(n, c->d_start, c->d_hits, c->d_first, c->d_cnt);
-  b200sgd::shuf_resolve_kernel<<<blocks, 256, 0, c->shuf_stream>>>(c->d_tgt, n, c->d_cnt, c->d_first, c->d_perm[src],
+  b200sgd::shuf_fill_kernel<<<blocks, 256, shuf_smem_bytes(), c->shuf_stream>>>(c->d_tgt, n, c->d_cnt, c->d_hits);
+  b200sgd::shuf_order_kernel<<<blocks, 256, shuf_smem_bytes(), c->shuf_stream>>>(n, c->d_start, c->d_hits, c->d_first, c->d_cnt);
+  b200sgd::shuf_resolve_kernel<<<blocks, 256, shuf_smem_bytes(), c->shuf_stream>>>(c->d_tgt, n, c->d_cnt, c->d_first, c->d_perm[src],
                                                             c->d_perm[dst]);
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaEventRecord(c->ev_done[2], c->shuf_stream));
@@ -866,6 +875,17 @@ constexpr int kFlagReady = 0;   // [owner rank][buffer]: number of the shuffle w
 constexpr int kFlagDone = 16;   // [buffer][consumer rank] (in the OWNER's block): last shuffle the consumer applied from it
 
 bool use_shared_shuffle(const sgd_ctx* c) { return c->shared_shuffle && c->peers_ready; }
+
+// Dynamic shared memory the permutation kernels ASK for without using it (B200SGD_SHUF_SMEM_KB): a block
+// that wants 40 KB does not fit on an SM beside a step CTA (199-227 KB), so the block scheduler keeps the
+// permutation work on the SMs the step kernel leaves idle (28 of 148 with 15 clusters of 8, 36 with 7 of 16).
+size_t shuf_smem_bytes() {
+  static const size_t v = [] {
+    const char* e = std::getenv("B200SGD_SHUF_SMEM_KB");
+    return e ? (size_t)std::min(48, std::max(0, std::atoi(e))) * 1024 : (size_t)0;
+  }();
+  return v;
+}
 
 unsigned long long watchdog_ns(const sgd_ctx* c) {
   unsigned long long ns = c->cfg.nranks > 1 ? 30000000000ull : 4000000000ull;
@@ -897,19 +917,32 @@ int enqueue_own_map(sgd_ctx* c, int64_t k, int* launches) {
   // 256-thread block fits an SM beside a step CTA; more do not) -- measured at N = 8 as ~2.8 ms per epoch
   int bps = std::max(1, 8 / N);
   if (const char* e = std::getenv("B200SGD_MAP_BLOCKS_PER_SM")) bps = std::max(1, std::atoi(e));
-  const int blocks = (int)std::min<int64_t>((n + 255) / 256, (int64_t)c->num_sms * bps);
+  int blocks = (int)std::min<int64_t>((n + 255) / 256, (int64_t)c->num_sms * bps);
+  // A/B switch B200SGD_MAP_CONFINE=1: keep the map off the step kernel's SMs altogether -- its kernels ASK
+  // for 40 KB of dynamic shared memory they do not use, so their blocks do not fit beside a step CTA
+  // (199-227 KB) and run on the SMs the step grid leaves idle (36 of 148 with 7 clusters of 16), five per
+  // SM.  Measured: the step loop is disturbed less (one GPU, 64M x 512: 34.9 -> 29.4 us per step), but a
+  // map on 28-36 SMs takes ~2x as long and the epoch then waits for it or for its blocks to drain:
+  // N = 2: 28.3 ms per epoch against 23.9, N = 8: 11.6 against 10.2, N = 4: 16.3 against 16.7.  Off.
+  size_t map_smem = shuf_smem_bytes();
+  const int idle_sms = c->num_sms - c->grid;
+  const char* force = std::getenv("B200SGD_MAP_CONFINE");
+  if (idle_sms >= 16 && force && force[0] == '1') {
+    map_smem = (size_t)40 << 10;
+    blocks = (int)std::min<int64_t>((n + 255) / 256, (int64_t)idle_sms * 5);
+  }
   int32_t* map = (int32_t*)((char*)c->d_xchg_block + c->src_off[b]);
   CUDA_TRY(cudaMemsetAsync(c->d_cnt, 0, sizeof(int32_t) * ((size_t)n + 1), st));
-  b200sgd::shuf_targets_stream_kernel<<<(int)((c->nchunks + 127) / 128), 128, 0, st>>>(c->d_states, c->chunk_len, c->nchunks, n,
+  b200sgd::shuf_targets_stream_kernel<<<(int)((c->nchunks + 127) / 128), 128, map_smem, st>>>(c->d_states, c->chunk_len, c->nchunks, n,
                                                                                    c->d_tgt, c->d_cnt);
   b200sgd::scan_tile_sums_kernel<<<c->scan_tiles, b200sgd::kScanBlock, 0, st>>>(c->d_cnt, n, c->d_tilesum);
   b200sgd::scan_tile_offsets_kernel<<<1, b200sgd::kScanBlock, 0, st>>>(c->d_tilesum, c->scan_tiles, c->d_tilesum + c->scan_tiles);
   b200sgd::scan_apply_kernel<<<c->scan_tiles, b200sgd::kScanBlock, 0, st>>>(c->d_cnt, n, c->d_tilesum, c->d_tilesum + c->scan_tiles,
                                                                         c->d_start);
   CUDA_TRY(cudaMemcpyAsync(c->d_cnt, c->d_start, sizeof(int32_t) * ((size_t)n + 1), cudaMemcpyDeviceToDevice, st));
-  b200sgd::shuf_fill_kernel<<<blocks, 256, 0, st>>>(c->d_tgt, n, c->d_cnt, c->d_hits);
-  b200sgd::shuf_order_kernel<<<blocks, 256, 0, st>>>(n, c->d_start, c->d_hits, c->d_first, c->d_cnt);
-  b200sgd::shuf_resolve_kernel<<<blocks, 256, 0, st>>>(c->d_tgt, n, c->d_cnt, c->d_first, nullptr, map);
+  b200sgd::shuf_fill_kernel<<<blocks, 256, map_smem, st>>>(c->d_tgt, n, c->d_cnt, c->d_hits);
+  b200sgd::shuf_order_kernel<<<blocks, 256, map_smem, st>>>(n, c->d_start, c->d_hits, c->d_first, c->d_cnt);
+  b200sgd::shuf_resolve_kernel<<<blocks, 256, map_smem, st>>>(c->d_tgt, n, c->d_cnt, c->d_first, nullptr, map);
   b200sgd::PeerFlagPtrs t{};
   for (int r = 0; r < N; ++r) t.p[r] = (uint32_t*)((char*)c->peer_block[r] + c->flag_off);
   b200sgd::shuf_set_flags_kernel<<<1, 32, 0, st>>>(t, N, kFlagReady + me * 2 + b, (uint32_t)k);
@@ -1181,6 +1214,10 @@ int sgd_create(const sgd_config* cfg, const float* X, const float* y, sgd_ctx** 
   c->C = cfg->cols;
   batch_geometry(c->R, cfg->batch, &c->B, &c->nb);
   c->ld = ((int64_t)c->C + 1 + 15) / 16 * 16;  // 64-byte records: whole HBM bursts, see DESIGN.md
+  if (const char* e = std::getenv("B200SGD_LD_ALIGN")) {  // experiment: record pitch in floats (a multiple of 16)
+    const int64_t al = std::max<int64_t>(16, std::atoll(e) / 16 * 16);
+    c->ld = ((int64_t)c->C + 1 + al - 1) / al * al;
+  }
   c->C4 = (c->C + 3) / 4;
   c->rows_per_rank = (c->R + cfg->nranks - 1) / cfg->nranks;
   c->row_begin = std::min<int64_t>(c->R, c->rows_per_rank * cfg->rank);
@@ -1204,7 +1241,9 @@ int sgd_create(const sgd_config* cfg, const float* X, const float* y, sgd_ctx** 
   };
   auto setup = [&]() -> int {
     SGD_TRY(bind(c));
-    CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    int prio_lo = 0, prio_hi = 0;  // the step kernel's CTAs go first when an SM frees up
+    CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    CUDA_TRY(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi));
     CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&c->shuf_stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreateWithFlags(&c->ev_shuf[0], cudaEventDisableTiming));
@@ -1315,7 +1354,9 @@ int sgd_create(const sgd_config* cfg, const float* X, const float* y, sgd_ctx** 
         c->src_off[0] = c->flag_off + 4096;
         c->src_off[1] = c->src_off[0] + (sizeof(int32_t) * (size_t)c->R + 4095) / 4096 * 4096;
         c->xchg_bytes = c->src_off[1] + sizeof(int32_t) * (size_t)c->R;
-        CUDA_TRY(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+        int plo = 0, phi = 0;
+        CUDA_TRY(cudaDeviceGetStreamPriorityRange(&plo, &phi));
+        CUDA_TRY(cudaStreamCreateWithPriority(&c->own_stream, cudaStreamNonBlocking, plo));
         for (int i = 0; i < 2; ++i) {
           CUDA_TRY(cudaEventCreateWithFlags(&c->ev_own_up[i], cudaEventDisableTiming));
           CUDA_TRY(cudaMallocHost(&c->h_states_own[i], sizeof(uint32_t) * 31 * (size_t)c->nchunks));

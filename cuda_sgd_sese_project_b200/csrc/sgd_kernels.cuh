@@ -574,7 +574,7 @@ __global__ void __launch_bounds__(32 * (NW + NPMAX), 1)
   static_assert(!(CLT && LEAN), "the cluster tail keeps its run-time switches");
   static_assert(CW == 0 || (!WIDE && !NARROW8 && NW % CW == 0 && (U == 1 || U == 2 || U == 4 || U == 8)), "COLSPLIT geometry");
   using Smem = EpochSmem<KC, NW, WIDE, U, CW>;
-  static_assert(!NARROW8 || (KC == 1 && U == 4 && !WIDE), "NARROW8 is the <1,4,NW> row mapping");
+  static_assert(!NARROW8 || (KC == 1 && (U == 4 || U == 8) && NW == 8 && !WIDE), "NARROW8 is the <1,4|8,8> row mapping");
   // run-time switches, constant-folded in the LEAN instantiations
   StepCtl* const o_ctl = LEAN ? nullptr : p.ctl;
   const int64_t* const o_step_off = LEAN ? nullptr : p.step_off;
@@ -1087,47 +1087,66 @@ __global__ void __launch_bounds__(32 * (NW + NPMAX), 1)
       }
       const int n32 = (int)n;
       const int nt = (n32 + TR - 1) / TR;
+      // H = U / 4 rows per lane group and tile pass (tiles of 32 * H rows).  H = 2 was tried against the
+      // latency chain of a pass (wait, loads, 16 FMAs, 3 shuffles, 16 FMAs: ~36 bytes per clock and SM at
+      // 4M x 100, B = 100000) and changed nothing (13.1 vs 12.8 us per step); H = 1 is what runs.
+      constexpr int H = U / 4;
       for (int ti = 0; ti < nt; ++ti) {
         const uint32_t tile = ctile, use = cuse;
         if (++ctile == (uint32_t)ntiles) { ctile = 0; ++cuse; }
         const int cnt = (n32 - ti * TR) < TR ? (n32 - ti * TR) : TR;
-        const int r = cw * 4 + rg;  // my row of the tile
-        const bool live = r < cnt;
-        const float4* row = reinterpret_cast<const float4*>(ring + (size_t)tile * tile_bytes + (size_t)r * p.slot_bytes);
+        const unsigned char* tbase = ring + (size_t)tile * tile_bytes;
         mbar_wait(full0 + 8u * tile, use & 1u);
         mark(7);  // (profile) time spent waiting for the rows to land
-        float4 x[4];
+        float4 x[H][4];
+        float y[H], dot[H];
+        bool live[H];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int f = sl + 8 * k;
-          x[k] = (live && f < C4) ? row[f] : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int h = 0; h < H; ++h) {
+          const int r = h * 32 + cw * 4 + rg;  // my rows of the tile
+          live[h] = r < cnt;
+          const float4* row = reinterpret_cast<const float4*>(tbase + (size_t)r * p.slot_bytes);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int f = sl + 8 * k;
+            x[h][k] = (live[h] && f < C4) ? row[f] : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          y[h] = live[h] ? reinterpret_cast<const float*>(row)[p.C] : 0.f;
         }
-        const float y = live ? reinterpret_cast<const float*>(row)[p.C] : 0.f;
         __syncwarp();
         if (lane == 0) mbar_arrive(empty0 + 8u * tile);
-        float dot = 0.f;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          dot = fmaf(x[k].x, wv[k].x, dot);
-          dot = fmaf(x[k].y, wv[k].y, dot);
-          dot = fmaf(x[k].z, wv[k].z, dot);
-          dot = fmaf(x[k].w, wv[k].w, dot);
-        }
-        dot += __shfl_xor_sync(0xffffffffu, dot, 1);
-        dot += __shfl_xor_sync(0xffffffffu, dot, 2);
-        dot += __shfl_xor_sync(0xffffffffu, dot, 4);
-        const float res = dot - y;  // sgd_thrust.cu:43-48; dead rows: 0
+        for (int h = 0; h < H; ++h) {
+          float d0 = 0.f, d1 = 0.f;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          g8[k].x = fmaf(res, x[k].x, g8[k].x);
-          g8[k].y = fmaf(res, x[k].y, g8[k].y);
-          g8[k].z = fmaf(res, x[k].z, g8[k].z);
-          g8[k].w = fmaf(res, x[k].w, g8[k].w);
+          for (int k = 0; k < 4; ++k) {
+            d0 = fmaf(x[h][k].x, wv[k].x, d0);
+            d1 = fmaf(x[h][k].y, wv[k].y, d1);
+            d0 = fmaf(x[h][k].z, wv[k].z, d0);
+            d1 = fmaf(x[h][k].w, wv[k].w, d1);
+          }
+          dot[h] = d0 + d1;
         }
-        if (sl == 0) {  // one lane per row keeps the running loss and the residual
-          loss_abs += (double)fabsf(res);
-          loss_sq += (double)res * (double)res;
-          if (o_r_out != nullptr && live) o_r_out[off + lo + (int64_t)ti * TR + r] = res;
+#pragma unroll
+        for (int m = 1; m <= 4; m <<= 1) {
+#pragma unroll
+          for (int h = 0; h < H; ++h) dot[h] += __shfl_xor_sync(0xffffffffu, dot[h], m);
+        }
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+          const float res = dot[h] - y[h];  // sgd_thrust.cu:43-48; dead rows: 0
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            g8[k].x = fmaf(res, x[h][k].x, g8[k].x);
+            g8[k].y = fmaf(res, x[h][k].y, g8[k].y);
+            g8[k].z = fmaf(res, x[h][k].z, g8[k].z);
+            g8[k].w = fmaf(res, x[h][k].w, g8[k].w);
+          }
+          if (sl == 0) {  // one lane per row keeps the running loss and the residual
+            loss_abs += (double)fabsf(res);
+            loss_sq += (double)res * (double)res;
+            if (o_r_out != nullptr && live[h]) o_r_out[off + lo + (int64_t)ti * TR + h * 32 + cw * 4 + rg] = res;
+          }
         }
         mark(0);
       }

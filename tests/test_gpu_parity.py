@@ -259,6 +259,17 @@ def test_cluster_kernel_agrees_with_the_generic_kernel(monkeypatch):
     assert rel_l2(w_c, w_g) < 1e-5 and abs(mae_c - mae_g) <= 1e-5 * abs(mae_g) + 1e-6 * float(np.mean(np.abs(y)))
 
 
+@pytest.mark.parametrize("R,C,B", [(60000, 100, 30000), (40000, 31, 20000), (70000, 127, 33333), (50000, 1, 25000)])
+@pytest.mark.parametrize("variant,u", [("0", -4), ("4", -8)])
+def test_narrow_rows_streaming_steps(R, C, B, variant, u, monkeypatch):
+    # steps beyond the cluster kernel's reach: 8 lanes per row; one (default) or two rows per lane group
+    monkeypatch.setenv("B200SGD_VARIANT", variant)
+    X, y, _ = make_regression(R, C, seed=R + C)
+    with pkg.SGDEngine(R, C, B, 0.02) as probe:
+        assert probe.kernel_shape[0] == 1 and probe.kernel_shape[1] == u, probe.kernel_shape
+    check_run(X, y, B, 0.02, 3)
+
+
 def test_cluster_kernel_is_not_used_where_it_does_not_apply():
     for kw in (dict(C=128, B=1000), dict(C=100, B=24), dict(C=100, B=16384)):
         with pkg.SGDEngine(20000, kw["C"], kw["B"], 0.1) as eng:

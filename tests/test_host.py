@@ -162,3 +162,24 @@ def test_experiment_json_is_byte_compatible_with_jsoncpp(tmp_path):
     pkg.write_experiment_output(str(p), 0.0, 8.0, float("nan"), float("inf"), -1.5)
     assert p.read_text() == ('{\n   "error" : -1.5,\n   "gpu_time" : null,\n   "shuffle_time" : 0,\n'
                              '   "total_gradient_time" : 8,\n   "transfer_time" : 1e+9999\n}\n')
+
+
+def test_shuffle_is_a_position_map_independent_of_the_values():
+    """What the ranks' shared permutation work rests on (csrc/shuffle_kernels.cuh): std::random_shuffle moves
+    values without looking at them, so epoch k's pass is a position map src_k that depends on epoch k's
+    rand() stream only, and perm_k[p] = perm_{k-1}[src_k[p]].  Checked on the host: the map of every epoch
+    comes from shuffling the IDENTITY with that epoch's part of the stream (skip_epochs = k - 1)."""
+    R, E = 20011, 5
+    perm = np.arange(R, dtype=np.int32)
+    want = np.arange(R, dtype=np.int32)
+    for k in range(1, E + 1):
+        src = np.arange(R, dtype=np.int32)
+        pkg.host_shuffle(src, skip_epochs=k - 1, epochs=1)       # the map of shuffle k alone
+        perm = perm[src]                                         # applied by a gather
+        pkg.host_shuffle(want, skip_epochs=k - 1, epochs=1)      # the reference's cumulative loop
+        assert np.array_equal(perm, want), k
+    g = orc.Rand()
+    ind = np.arange(R, dtype=np.int32)
+    for _ in range(E):
+        g.shuffle(ind)
+    assert np.array_equal(ind, want)
