@@ -28,7 +28,7 @@ ENV_KEYS = {"CLT": "B200SGD_CLT", "INFLIGHT_KB": "B200SGD_INFLIGHT_KB", "CLUSTER
             "PRODUCER_WARPS": "B200SGD_PRODUCER_WARPS", "VARIANT": "B200SGD_VARIANT", "DBGSKIP": "B200SGD_DBGSKIP"}
 
 
-def run(R, C, B, lr=0.01, epochs=2, warm=1, reduce=0, grid=0, **env):
+def run(R, C, B, lr=0.01, epochs=2, warm=1, reduce=0, grid=0, seq=0, **env):
     saved = {}
     for k, v in env.items():
         name = ENV_KEYS[k]
@@ -37,7 +37,10 @@ def run(R, C, B, lr=0.01, epochs=2, warm=1, reduce=0, grid=0, **env):
     try:
         with pkg.SGDEngine(R, C, B, lr, reduce=reduce, grid=grid) as eng:
             eng.load_synthetic(seed=42)
-            eng.shuffle()
+            if seq:   # rows in storage order: what the random gather itself costs
+                eng.set_permutation(np.arange(R, dtype=np.int32))
+            else:
+                eng.shuffle()
             for e in range(warm):
                 eng.epoch(1 + e)
             best = None
@@ -58,6 +61,8 @@ def run(R, C, B, lr=0.01, epochs=2, warm=1, reduce=0, grid=0, **env):
                 out["marks_mean"] = [round(float(d[:, i].mean())) for i in range(8)]
                 out["marks_max"] = [round(float(d[:, i].max())) for i in range(8)]
             out.update(env)
+            if seq:
+                out["rows_in_storage_order"] = True
             print(json.dumps(out), flush=True)
             return out
     except Exception as ex:  # keep the sweep going
@@ -104,7 +109,7 @@ def main():
     elif what == "one":
         a = [int(v) for v in sys.argv[2:5]]
         kv = dict(x.split("=") for x in sys.argv[5:])
-        kw = {k: int(v) for k, v in kv.items() if k in ("reduce", "grid", "epochs", "warm")}
+        kw = {k: int(v) for k, v in kv.items() if k in ("reduce", "grid", "epochs", "warm", "seq")}
         env = {k: v for k, v in kv.items() if k in ENV_KEYS}
         run(a[0], a[1], a[2], **kw, **env)
 
