@@ -30,6 +30,7 @@
 #include "sgd_kernels.cuh"
 #include "sgd_cluster_kernel.cuh"
 #include "shuffle_kernels.cuh"
+#include "shuffle2_kernels.cuh"
 
 namespace {
 
@@ -190,6 +191,15 @@ struct sgd_ctx {
   b200sgd::GlibcRand::Poly jump_chunk{};
   int32_t *d_cnt = nullptr, *d_start = nullptr, *d_hits = nullptr, *d_first = nullptr, *d_tilesum = nullptr;
   int32_t scan_tiles = 0;
+  // backward formulation (shuffle2_kernels.cuh), B200SGD_SHUFFLE=2|3: 2 = scatter by granule, R in place;
+  // 3 (default) = two-level scatters (coarse buckets + refine, coarse ranges + place); 1 = the forward kernels
+  int shuf_ver = 3;
+  static constexpr int kSubChunks = 8;  // device-derived sub-chunk states per host chunk state
+  int cshift = 13;                      // log2 positions per coarse bucket (<= 8192 buckets)
+  int64_t ngran = 0, ncoarse = 0, nranges = 0;
+  uint2 *d_pairs1 = nullptr, *d_pairs2 = nullptr;  // coarse-bucketed pairs (later: the entries of R by range) / pairs by granule
+  int32_t *d_last = nullptr, *d_R = nullptr, *d_gstart = nullptr, *d_ccnt = nullptr, *d_cstart = nullptr, *d_rcur = nullptr;
+  uint32_t *d_states_x = nullptr, *d_subjump = nullptr;
   bool host_ind_stale = false;  // h_ind lags behind the device permutation
   // several ranks: the permutation work is shared (shuffle_kernels.cuh): rank (k-1) % nranks computes
   // the position map of shuffle k ahead of time, everybody applies it with one gather pass
@@ -285,6 +295,8 @@ void free_all(sgd_ctx* c) {
   cudaFree(c->d_ll_part); cudaFree(c->d_ll_w); cudaFree(c->d_dbg); cudaFree(c->d_loss);
   cudaFree(c->d_tgt); cudaFree(c->d_cnt); cudaFree(c->d_start); cudaFree(c->d_hits); cudaFree(c->d_first);
   cudaFree(c->d_tilesum); cudaFree(c->d_states);
+  cudaFree(c->d_pairs1); cudaFree(c->d_pairs2); cudaFree(c->d_last); cudaFree(c->d_R); cudaFree(c->d_gstart);
+  cudaFree(c->d_ccnt); cudaFree(c->d_cstart); cudaFree(c->d_rcur); cudaFree(c->d_states_x); cudaFree(c->d_subjump);
   if (c->own_stream) cudaStreamSynchronize(c->own_stream);
   if (c->h_states[0]) cudaFreeHost(c->h_states[0]);
   if (c->h_states[1]) cudaFreeHost(c->h_states[1]);
@@ -835,6 +847,69 @@ void prepare_stream_states(sgd_ctx* c, int buf) {
   c->rng.skip((uint64_t)(c->R - 1));
 }
 
+// The kernels of one device shuffle on stream `st`: d_states (uploaded) -> out[p] = in[src(p)], or the
+// position map src itself (in == nullptr).  `blocks`: grid of the grid-stride kernels.
+int enqueue_perm_kernels(sgd_ctx* c, cudaStream_t st, int blocks, size_t smem, const int32_t* in, int32_t* out, int* launches) {
+  const int64_t n = c->R;
+  if (c->shuf_ver == 1) {  // forward formulation (shuffle_kernels.cuh)
+    CUDA_TRY(cudaMemsetAsync(c->d_cnt, 0, sizeof(int32_t) * ((size_t)n + 1), st));
+    b200sgd::shuf_targets_stream_kernel<<<(int)((c->nchunks + 127) / 128), 128, smem, st>>>(c->d_states, c->chunk_len, c->nchunks, n,
+                                                                                     c->d_tgt, c->d_cnt);
+    b200sgd::scan_tile_sums_kernel<<<c->scan_tiles, b200sgd::kScanBlock, 0, st>>>(c->d_cnt, n, c->d_tilesum);
+    b200sgd::scan_tile_offsets_kernel<<<1, b200sgd::kScanBlock, 0, st>>>(c->d_tilesum, c->scan_tiles, c->d_tilesum + c->scan_tiles);
+    b200sgd::scan_apply_kernel<<<c->scan_tiles, b200sgd::kScanBlock, 0, st>>>(c->d_cnt, n, c->d_tilesum, c->d_tilesum + c->scan_tiles,
+                                                                          c->d_start);
+    // the fill cursors start at the lists' offsets; afterwards the array is free and takes the successors
+    CUDA_TRY(cudaMemcpyAsync(c->d_cnt, c->d_start, sizeof(int32_t) * ((size_t)n + 1), cudaMemcpyDeviceToDevice, st));
+    b200sgd::shuf_fill_kernel<<<blocks, 256, smem, st>>>(c->d_tgt, n, c->d_cnt, c->d_hits);
+    b200sgd::shuf_order_kernel<<<blocks, 256, smem, st>>>(n, c->d_start, c->d_hits, c->d_first, c->d_cnt);
+    b200sgd::shuf_resolve_kernel<<<blocks, 256, smem, st>>>(c->d_tgt, n, c->d_cnt, c->d_first, in, out);
+    CUDA_TRY(cudaGetLastError());
+    *launches += 7;
+    return SGD_OK;
+  }
+  // backward formulation (shuffle2_kernels.cuh)
+  constexpr int S = sgd_ctx::kSubChunks;
+  const int64_t Lx = c->chunk_len / S, nx = (n - 1 + Lx - 1) / Lx;  // sub-chunks in use (<= nchunks * S)
+  const int sgrid = (int)std::max<int64_t>(1, (nx + 127) / 128);
+  unsigned int* err = c->d_bar + 1;
+  b200sgd::shuf2_expand_states_kernel<<<(int)((c->nchunks * S + 127) / 128), 128, 0, st>>>(c->d_states, c->nchunks, c->d_subjump, S,
+                                                                                     c->d_states_x);
+  const bool two_level = c->shuf_ver == 3;
+  const int64_t nbins = two_level ? c->ncoarse : c->ngran;  // K1a counts per coarse bucket / per granule
+  const int shift = two_level ? c->cshift : b200sgd::kGranLog;
+  int32_t* starts = two_level ? c->d_cstart : c->d_gstart;
+  const int tiles = (int)((nbins + b200sgd::kScanTile - 1) / b200sgd::kScanTile);
+  CUDA_TRY(cudaMemsetAsync(c->d_ccnt, 0, sizeof(int32_t) * ((size_t)nbins + 1), st));
+  b200sgd::shuf2_stream_kernel<0><<<sgrid, 128, 0, st>>>(c->d_states_x, Lx, nx, n, shift, c->d_ccnt, nullptr, nullptr);
+  b200sgd::scan_tile_sums_kernel<<<tiles, b200sgd::kScanBlock, 0, st>>>(c->d_ccnt, nbins, c->d_tilesum);
+  b200sgd::scan_tile_offsets_kernel<<<1, b200sgd::kScanBlock, 0, st>>>(c->d_tilesum, tiles, c->d_tilesum + tiles);
+  b200sgd::scan_apply_kernel<<<tiles, b200sgd::kScanBlock, 0, st>>>(c->d_ccnt, nbins, c->d_tilesum, c->d_tilesum + tiles, starts);
+  // the counters become the scatter's cursors
+  CUDA_TRY(cudaMemcpyAsync(c->d_ccnt, starts, sizeof(int32_t) * ((size_t)nbins + 1), cudaMemcpyDeviceToDevice, st));
+  if (!two_level) {
+    b200sgd::shuf2_stream_kernel<1><<<sgrid, 128, 0, st>>>(c->d_states_x, Lx, nx, n, shift, c->d_ccnt, c->d_pairs2, c->d_R);
+    b200sgd::shuf2_link_kernel<false><<<blocks, b200sgd::kLinkThreads, 0, st>>>(n, c->ngran, c->d_gstart, c->d_pairs2, c->d_last, c->d_R,
+                                                                               nullptr, nullptr, err);
+    *launches += 8;
+  } else {
+    b200sgd::shuf2_stream_kernel<1><<<sgrid, 128, 0, st>>>(c->d_states_x, Lx, nx, n, shift, c->d_ccnt, c->d_pairs1, nullptr);
+    b200sgd::shuf2_refine_kernel<<<(int)std::min<int64_t>(c->ncoarse, blocks), b200sgd::kLinkThreads, 0, st>>>(
+        c->ngran, c->ncoarse, c->cshift, c->d_cstart, c->d_pairs1, c->d_pairs2, c->d_gstart);
+    b200sgd::shuf2_range_cursor_kernel<<<(int)std::min<int64_t>((c->nranges + 255) / 256, blocks), 256, 0, st>>>(c->d_rcur, c->nranges,
+                                                                                                         b200sgd::kRangeLog);
+    // the coarse pairs are dead: their array takes the entries of R, by range
+    b200sgd::shuf2_link_kernel<true><<<blocks, b200sgd::kLinkThreads, 0, st>>>(n, c->ngran, c->d_gstart, c->d_pairs2, c->d_last, nullptr,
+                                                                              c->d_rcur, c->d_pairs1, err);
+    b200sgd::shuf2_place_kernel<<<(int)std::min<int64_t>(c->nranges, blocks), 256, 0, st>>>(n, c->nranges, c->d_rcur, c->d_pairs1, c->d_R);
+    *launches += 11;
+  }
+  b200sgd::shuf2_resolve_kernel<<<blocks, 256, 0, st>>>(n, c->d_last, c->d_R, in, out);
+  CUDA_TRY(cudaGetLastError());
+  *launches += 1;
+  return SGD_OK;
+}
+
 // Device part: upload the chunk states (copy stream), then K1..K5 on the SHUFFLE stream turn
 // d_perm[src] into d_perm[dst] -- concurrently with the epoch kernel that is still reading
 // d_perm[src] on the compute stream.  No host sync.
@@ -849,24 +924,9 @@ int enqueue_device_shuffle(sgd_ctx* c, int stage_buf, int src, int dst, int* lau
   CUDA_TRY(cudaStreamWaitEvent(c->shuf_stream, c->ev_done[dst], 0));  // last epoch that read d_perm[dst]
   CUDA_TRY(cudaStreamWaitEvent(c->shuf_stream, c->ev_perm[src], 0));  // d_perm[src] uploaded (sgd_set_permutation)
   const int blocks = (int)std::min<int64_t>((n + 255) / 256, (int64_t)c->num_sms * 16);
-  CUDA_TRY(cudaMemsetAsync(c->d_cnt, 0, sizeof(int32_t) * ((size_t)n + 1), c->shuf_stream));
-  b200sgd::shuf_targets_stream_kernel<<<(int)((c->nchunks + 127) / 128), 128, shuf_smem_bytes(), c->shuf_stream>>>(
-      c->d_states, c->chunk_len, c->nchunks, n, c->d_tgt, c->d_cnt);
-  b200sgd::scan_tile_sums_kernel<<<c->scan_tiles, b200sgd::kScanBlock, 0, c->shuf_stream>>>(c->d_cnt, n, c->d_tilesum);
-  b200sgd::scan_tile_offsets_kernel<<<1, b200sgd::kScanBlock, 0, c->shuf_stream>>>(c->d_tilesum, c->scan_tiles,
-                                                                             c->d_tilesum + c->scan_tiles);
-  b200sgd::scan_apply_kernel<<<c->scan_tiles, b200sgd::kScanBlock, 0, c->shuf_stream>>>(
-      c->d_cnt, n, c->d_tilesum, c->d_tilesum + c->scan_tiles, c->d_start);
-  // the fill cursors start at the lists' offsets; afterwards the array is free and takes the successors
-  CUDA_TRY(cudaMemcpyAsync(c->d_cnt, c->d_start, sizeof(int32_t) * ((size_t)n + 1), cudaMemcpyDeviceToDevice, c->shuf_stream));
-  b200sgd::shuf_fill_kernel<<<blocks, 256, shuf_smem_bytes(), c->shuf_stream>>>(c->d_tgt, n, c->d_cnt, c->d_hits);
-  b200sgd::shuf_order_kernel<<<blocks, 256, shuf_smem_bytes(), c->shuf_stream>>>(n, c->d_start, c->d_hits, c->d_first, c->d_cnt);
-  b200sgd::shuf_resolve_kernel<<<blocks, 256, shuf_smem_bytes(), c->shuf_stream>>>(c->d_tgt, n, c->d_cnt, c->d_first, c->d_perm[src],
-                                                            c->d_perm[dst]);
-  CUDA_TRY(cudaGetLastError());
+  SGD_TRY(enqueue_perm_kernels(c, c->shuf_stream, blocks, shuf_smem_bytes(), c->d_perm[src], c->d_perm[dst], launches));
   CUDA_TRY(cudaEventRecord(c->ev_done[2], c->shuf_stream));
   CUDA_TRY(cudaEventRecord(c->ev_shuf[dst], c->shuf_stream));
-  *launches += 7;
   return SGD_OK;
 }
 
@@ -932,22 +992,12 @@ int enqueue_own_map(sgd_ctx* c, int64_t k, int* launches) {
     blocks = (int)std::min<int64_t>((n + 255) / 256, (int64_t)idle_sms * 5);
   }
   int32_t* map = (int32_t*)((char*)c->d_xchg_block + c->src_off[b]);
-  CUDA_TRY(cudaMemsetAsync(c->d_cnt, 0, sizeof(int32_t) * ((size_t)n + 1), st));
-  b200sgd::shuf_targets_stream_kernel<<<(int)((c->nchunks + 127) / 128), 128, map_smem, st>>>(c->d_states, c->chunk_len, c->nchunks, n,
-                                                                                   c->d_tgt, c->d_cnt);
-  b200sgd::scan_tile_sums_kernel<<<c->scan_tiles, b200sgd::kScanBlock, 0, st>>>(c->d_cnt, n, c->d_tilesum);
-  b200sgd::scan_tile_offsets_kernel<<<1, b200sgd::kScanBlock, 0, st>>>(c->d_tilesum, c->scan_tiles, c->d_tilesum + c->scan_tiles);
-  b200sgd::scan_apply_kernel<<<c->scan_tiles, b200sgd::kScanBlock, 0, st>>>(c->d_cnt, n, c->d_tilesum, c->d_tilesum + c->scan_tiles,
-                                                                        c->d_start);
-  CUDA_TRY(cudaMemcpyAsync(c->d_cnt, c->d_start, sizeof(int32_t) * ((size_t)n + 1), cudaMemcpyDeviceToDevice, st));
-  b200sgd::shuf_fill_kernel<<<blocks, 256, map_smem, st>>>(c->d_tgt, n, c->d_cnt, c->d_hits);
-  b200sgd::shuf_order_kernel<<<blocks, 256, map_smem, st>>>(n, c->d_start, c->d_hits, c->d_first, c->d_cnt);
-  b200sgd::shuf_resolve_kernel<<<blocks, 256, map_smem, st>>>(c->d_tgt, n, c->d_cnt, c->d_first, nullptr, map);
+  SGD_TRY(enqueue_perm_kernels(c, st, blocks, map_smem, nullptr, map, launches));
   b200sgd::PeerFlagPtrs t{};
   for (int r = 0; r < N; ++r) t.p[r] = (uint32_t*)((char*)c->peer_block[r] + c->flag_off);
   b200sgd::shuf_set_flags_kernel<<<1, 32, 0, st>>>(t, N, kFlagReady + me * 2 + b, (uint32_t)k);
   CUDA_TRY(cudaGetLastError());
-  *launches += 8;
+  *launches += 1;
   return SGD_OK;
 }
 
@@ -1043,6 +1093,7 @@ int check_watchdog(sgd_ctx* c) {
     cudaMemset(c->d_bar + 1, 0, sizeof(unsigned int));
     return fail(c->cfg.nranks > 1 ? SGD_ERR_COMM : SGD_ERR_CUDA,
                 err == 5   ? "shared shuffle timed out (a peer rank did not deliver / apply its permutation map)"
+                : err == 6 ? "device shuffle: a granule of 256 positions collected more hits than the link kernel stages (B200SGD_SHUFFLE=1 selects the forward kernels)"
                 : err == 3 ? "dataflow reduction timed out (a CTA or a peer rank did not publish)"
                 : err == 4 ? "cluster exchange timed out (rows or partial sums did not arrive)"
                            : "grid barrier timed out (CTAs not co-resident?)");
@@ -1315,12 +1366,32 @@ int sgd_create(const sgd_config* cfg, const float* X, const float* y, sgd_ctx** 
     if (c->device_shuffle) {
       const size_t n = (size_t)c->R;
       c->scan_tiles = (int32_t)((n + b200sgd::kScanTile - 1) / b200sgd::kScanTile);
-      CUDA_TRY(cudaMalloc(&c->d_tgt, sizeof(uint32_t) * n));
-      CUDA_TRY(cudaMalloc(&c->d_cnt, sizeof(int32_t) * (n + 1)));
-      CUDA_TRY(cudaMalloc(&c->d_start, sizeof(int32_t) * (n + 1)));
-      CUDA_TRY(cudaMalloc(&c->d_hits, sizeof(int32_t) * n));
-      CUDA_TRY(cudaMalloc(&c->d_first, sizeof(int32_t) * n));
+      if (const char* e = std::getenv("B200SGD_SHUFFLE")) c->shuf_ver = std::min(3, std::max(1, std::atoi(e)));
       CUDA_TRY(cudaMalloc(&c->d_tilesum, sizeof(int32_t) * ((size_t)c->scan_tiles + 1)));
+      if (c->shuf_ver == 1) {
+        CUDA_TRY(cudaMalloc(&c->d_tgt, sizeof(uint32_t) * n));
+        CUDA_TRY(cudaMalloc(&c->d_cnt, sizeof(int32_t) * (n + 1)));
+        CUDA_TRY(cudaMalloc(&c->d_start, sizeof(int32_t) * (n + 1)));
+        CUDA_TRY(cudaMalloc(&c->d_hits, sizeof(int32_t) * n));
+        CUDA_TRY(cudaMalloc(&c->d_first, sizeof(int32_t) * n));
+      } else {
+        c->ngran = (int64_t)((n + b200sgd::kGran - 1) >> b200sgd::kGranLog);
+        c->cshift = 13;
+        while (c->cshift < 18 && (((int64_t)n + (1ll << c->cshift) - 1) >> c->cshift) > 8192) ++c->cshift;
+        c->ncoarse = ((int64_t)n + (1ll << c->cshift) - 1) >> c->cshift;
+        c->nranges = ((int64_t)n + (1ll << b200sgd::kRangeLog) - 1) >> b200sgd::kRangeLog;
+        CUDA_TRY(cudaMalloc(&c->d_pairs2, sizeof(uint2) * n));
+        CUDA_TRY(cudaMalloc(&c->d_last, sizeof(int32_t) * n));
+        CUDA_TRY(cudaMalloc(&c->d_R, sizeof(int32_t) * n));
+        CUDA_TRY(cudaMalloc(&c->d_gstart, sizeof(int32_t) * ((size_t)c->ngran + 1)));
+        // version 2 counts per granule, version 3 per coarse bucket: one counter array serves both
+        CUDA_TRY(cudaMalloc(&c->d_ccnt, sizeof(int32_t) * ((size_t)c->ngran + 1)));
+        CUDA_TRY(cudaMalloc(&c->d_cstart, sizeof(int32_t) * ((size_t)c->ncoarse + 1)));
+        if (c->shuf_ver == 3) {
+          CUDA_TRY(cudaMalloc(&c->d_pairs1, sizeof(uint2) * ((size_t)c->nranges << b200sgd::kRangeLog)));
+          CUDA_TRY(cudaMalloc(&c->d_rcur, sizeof(int32_t) * (size_t)c->nranges));
+        }
+      }
       // the epoch's rand() stream is regenerated on the device from up to 8192 chunk start states
       // (one thread per chunk: at 64M rows 1024 chunks took 10.4 ms, 8192 take ~1.3 ms; the host
       // pays ~0.6 us per state, hidden behind the running epoch)
@@ -1331,6 +1402,17 @@ int sgd_create(const sgd_config* cfg, const float* X, const float* y, sgd_ctx** 
       c->jump_chunk = b200sgd::GlibcRand::poly_z_pow((uint64_t)L);
       CUDA_TRY(cudaMalloc(&c->d_states, sizeof(uint32_t) * 31 * (size_t)c->nchunks));
       for (int i = 0; i < 2; ++i) CUDA_TRY(cudaMallocHost(&c->h_states[i], sizeof(uint32_t) * 31 * (size_t)c->nchunks));
+      if (c->shuf_ver != 1) {  // sub-chunk states are derived on the device (shuf2_expand_states_kernel)
+        constexpr int S = sgd_ctx::kSubChunks;
+        CUDA_TRY(cudaMalloc(&c->d_states_x, sizeof(uint32_t) * 31 * (size_t)c->nchunks * S));
+        std::vector<uint32_t> sj((size_t)31 * (S - 1));
+        for (int k = 1; k < S; ++k) {
+          const b200sgd::GlibcRand::Poly pz = b200sgd::GlibcRand::poly_z_pow((uint64_t)(L / S) * (uint64_t)k);
+          std::memcpy(sj.data() + (size_t)31 * (k - 1), pz.a, sizeof(pz.a));
+        }
+        CUDA_TRY(cudaMalloc(&c->d_subjump, sizeof(uint32_t) * sj.size()));
+        CUDA_TRY(cudaMemcpy(c->d_subjump, sj.data(), sizeof(uint32_t) * sj.size(), cudaMemcpyHostToDevice));
+      }
     }
     stamp("shuffle buffers");
     c->mae_blocks = c->num_sms * 8;
