@@ -191,11 +191,16 @@ struct sgd_ctx {
   b200sgd::GlibcRand::Poly jump_chunk{};
   int32_t *d_cnt = nullptr, *d_start = nullptr, *d_hits = nullptr, *d_first = nullptr, *d_tilesum = nullptr;
   int32_t scan_tiles = 0;
-  // backward formulation (shuffle2_kernels.cuh), B200SGD_SHUFFLE=2|3: 2 = scatter by granule, R in place;
-  // 3 (default) = two-level scatters (coarse buckets + refine, coarse ranges + place); 1 = the forward kernels
-  int shuf_ver = 3;
+  // B200SGD_SHUFFLE: 1 = the forward kernels (shuffle_kernels.cuh); backward formulation (shuffle2_kernels.cuh):
+  //   2 = pairs scattered by granule (global cursors), R written in place
+  //   3 = pairs by coarse bucket (global cursors) + refine, R by coarse range + place
+  //   4 = pairs by coarse bucket (per-block counts, scanned (bucket, block) matrix: no global atomics) + refine, R in place
+  //   5 = as 4, R by coarse range + place
+  int shuf_ver = 4;
   static constexpr int kSubChunks = 8;  // device-derived sub-chunk states per host chunk state
-  int cshift = 13;                      // log2 positions per coarse bucket (<= 8192 buckets)
+  int cshift = 14;                      // log2 positions per coarse bucket (<= kCoarseMax buckets)
+  int stream_grid = 1;                  // blocks of the stream kernels = columns of the count matrix
+  int32_t *d_mcnt = nullptr, *d_moff = nullptr;  // (bucket, block) count matrix and its exclusive scan
   int64_t ngran = 0, ncoarse = 0, nranges = 0;
   uint2 *d_pairs1 = nullptr, *d_pairs2 = nullptr;  // coarse-bucketed pairs (later: the entries of R by range) / pairs by granule
   int32_t *d_last = nullptr, *d_R = nullptr, *d_gstart = nullptr, *d_ccnt = nullptr, *d_cstart = nullptr, *d_rcur = nullptr;
@@ -296,6 +301,7 @@ void free_all(sgd_ctx* c) {
   cudaFree(c->d_tgt); cudaFree(c->d_cnt); cudaFree(c->d_start); cudaFree(c->d_hits); cudaFree(c->d_first);
   cudaFree(c->d_tilesum); cudaFree(c->d_states);
   cudaFree(c->d_pairs1); cudaFree(c->d_pairs2); cudaFree(c->d_last); cudaFree(c->d_R); cudaFree(c->d_gstart);
+  cudaFree(c->d_mcnt); cudaFree(c->d_moff);
   cudaFree(c->d_ccnt); cudaFree(c->d_cstart); cudaFree(c->d_rcur); cudaFree(c->d_states_x); cudaFree(c->d_subjump);
   if (c->own_stream) cudaStreamSynchronize(c->own_stream);
   if (c->h_states[0]) cudaFreeHost(c->h_states[0]);
@@ -871,42 +877,65 @@ int enqueue_perm_kernels(sgd_ctx* c, cudaStream_t st, int blocks, size_t smem, c
   // backward formulation (shuffle2_kernels.cuh)
   constexpr int S = sgd_ctx::kSubChunks;
   const int64_t Lx = c->chunk_len / S, nx = (n - 1 + Lx - 1) / Lx;  // sub-chunks in use (<= nchunks * S)
-  const int sgrid = (int)std::max<int64_t>(1, (nx + 127) / 128);
+  const int sgrid = c->stream_grid;
   unsigned int* err = c->d_bar + 1;
   b200sgd::shuf2_expand_states_kernel<<<(int)((c->nchunks * S + 127) / 128), 128, 0, st>>>(c->d_states, c->nchunks, c->d_subjump, S,
                                                                                      c->d_states_x);
-  const bool two_level = c->shuf_ver == 3;
-  const int64_t nbins = two_level ? c->ncoarse : c->ngran;  // K1a counts per coarse bucket / per granule
-  const int shift = two_level ? c->cshift : b200sgd::kGranLog;
-  int32_t* starts = two_level ? c->d_cstart : c->d_gstart;
-  const int tiles = (int)((nbins + b200sgd::kScanTile - 1) / b200sgd::kScanTile);
-  CUDA_TRY(cudaMemsetAsync(c->d_ccnt, 0, sizeof(int32_t) * ((size_t)nbins + 1), st));
-  b200sgd::shuf2_stream_kernel<0><<<sgrid, 128, 0, st>>>(c->d_states_x, Lx, nx, n, shift, c->d_ccnt, nullptr, nullptr);
-  b200sgd::scan_tile_sums_kernel<<<tiles, b200sgd::kScanBlock, 0, st>>>(c->d_ccnt, nbins, c->d_tilesum);
-  b200sgd::scan_tile_offsets_kernel<<<1, b200sgd::kScanBlock, 0, st>>>(c->d_tilesum, tiles, c->d_tilesum + tiles);
-  b200sgd::scan_apply_kernel<<<tiles, b200sgd::kScanBlock, 0, st>>>(c->d_ccnt, nbins, c->d_tilesum, c->d_tilesum + tiles, starts);
-  // the counters become the scatter's cursors
-  CUDA_TRY(cudaMemcpyAsync(c->d_ccnt, starts, sizeof(int32_t) * ((size_t)nbins + 1), cudaMemcpyDeviceToDevice, st));
-  if (!two_level) {
-    b200sgd::shuf2_stream_kernel<1><<<sgrid, 128, 0, st>>>(c->d_states_x, Lx, nx, n, shift, c->d_ccnt, c->d_pairs2, c->d_R);
+  auto scan = [&](const int32_t* in, int64_t cells, int32_t* out) {  // out[0 .. cells]: exclusive scan + total
+    const int tiles = (int)((cells + b200sgd::kScanTile - 1) / b200sgd::kScanTile);
+    b200sgd::scan_tile_sums_kernel<<<tiles, b200sgd::kScanBlock, 0, st>>>(in, cells, c->d_tilesum);
+    b200sgd::scan_tile_offsets_kernel<<<1, b200sgd::kScanBlock, 0, st>>>(c->d_tilesum, tiles, c->d_tilesum + tiles);
+    b200sgd::scan_apply_kernel<<<tiles, b200sgd::kScanBlock, 0, st>>>(in, cells, c->d_tilesum, c->d_tilesum + tiles, out);
+    *launches += 3;
+  };
+  const bool rscatter = c->shuf_ver == 3 || c->shuf_ver == 5;
+  int32_t* R_stream = rscatter ? nullptr : c->d_R;  // self swaps: written by the stream kernel, or by the place kernel
+  if (c->shuf_ver == 2) {
+    CUDA_TRY(cudaMemsetAsync(c->d_ccnt, 0, sizeof(int32_t) * ((size_t)c->ngran + 1), st));
+    b200sgd::shuf2_stream_kernel<0, false><<<sgrid, 128, 0, st>>>(c->d_states_x, Lx, nx, n, b200sgd::kGranLog, 0, c->d_ccnt, nullptr, nullptr);
+    scan(c->d_ccnt, c->ngran, c->d_gstart);
+    // the counters become the scatter's cursors
+    CUDA_TRY(cudaMemcpyAsync(c->d_ccnt, c->d_gstart, sizeof(int32_t) * ((size_t)c->ngran + 1), cudaMemcpyDeviceToDevice, st));
+    b200sgd::shuf2_stream_kernel<1, false><<<sgrid, 128, 0, st>>>(c->d_states_x, Lx, nx, n, b200sgd::kGranLog, 0, c->d_ccnt, c->d_pairs2, R_stream);
+    *launches += 5;
+  } else {
+    const int32_t* coff = c->d_cstart;
+    int64_t cstride = 1;
+    if (c->shuf_ver == 3) {
+      CUDA_TRY(cudaMemsetAsync(c->d_ccnt, 0, sizeof(int32_t) * ((size_t)c->ncoarse + 1), st));
+      b200sgd::shuf2_stream_kernel<0, false><<<sgrid, 128, 0, st>>>(c->d_states_x, Lx, nx, n, c->cshift, 0, c->d_ccnt, nullptr, nullptr);
+      scan(c->d_ccnt, c->ncoarse, c->d_cstart);
+      CUDA_TRY(cudaMemcpyAsync(c->d_ccnt, c->d_cstart, sizeof(int32_t) * ((size_t)c->ncoarse + 1), cudaMemcpyDeviceToDevice, st));
+      b200sgd::shuf2_stream_kernel<1, false><<<sgrid, 128, 0, st>>>(c->d_states_x, Lx, nx, n, c->cshift, 0, c->d_ccnt, c->d_pairs1, R_stream);
+      *launches += 2;
+    } else {
+      const int64_t cells = c->ncoarse * (int64_t)sgrid;
+      b200sgd::shuf2_stream_kernel<0, true><<<sgrid, 128, 0, st>>>(c->d_states_x, Lx, nx, n, c->cshift, (int)c->ncoarse, c->d_mcnt, nullptr, nullptr);
+      scan(c->d_mcnt, cells, c->d_moff);
+      b200sgd::shuf2_stream_kernel<1, true><<<sgrid, 128, 0, st>>>(c->d_states_x, Lx, nx, n, c->cshift, (int)c->ncoarse, c->d_moff, c->d_pairs1, R_stream);
+      coff = c->d_moff;
+      cstride = sgrid;
+    }
+    b200sgd::shuf2_refine_kernel<<<(int)std::min<int64_t>(c->ncoarse, blocks), b200sgd::kLinkThreads, 0, st>>>(
+        c->ngran, c->ncoarse, c->cshift, coff, cstride, c->d_pairs1, c->d_pairs2, c->d_gstart);
+    *launches += 4;
+  }
+  if (!rscatter) {
     b200sgd::shuf2_link_kernel<false><<<blocks, b200sgd::kLinkThreads, 0, st>>>(n, c->ngran, c->d_gstart, c->d_pairs2, c->d_last, c->d_R,
                                                                                nullptr, nullptr, err);
-    *launches += 8;
+    *launches += 1;
   } else {
-    b200sgd::shuf2_stream_kernel<1><<<sgrid, 128, 0, st>>>(c->d_states_x, Lx, nx, n, shift, c->d_ccnt, c->d_pairs1, nullptr);
-    b200sgd::shuf2_refine_kernel<<<(int)std::min<int64_t>(c->ncoarse, blocks), b200sgd::kLinkThreads, 0, st>>>(
-        c->ngran, c->ncoarse, c->cshift, c->d_cstart, c->d_pairs1, c->d_pairs2, c->d_gstart);
     b200sgd::shuf2_range_cursor_kernel<<<(int)std::min<int64_t>((c->nranges + 255) / 256, blocks), 256, 0, st>>>(c->d_rcur, c->nranges,
                                                                                                          b200sgd::kRangeLog);
     // the coarse pairs are dead: their array takes the entries of R, by range
     b200sgd::shuf2_link_kernel<true><<<blocks, b200sgd::kLinkThreads, 0, st>>>(n, c->ngran, c->d_gstart, c->d_pairs2, c->d_last, nullptr,
                                                                               c->d_rcur, c->d_pairs1, err);
     b200sgd::shuf2_place_kernel<<<(int)std::min<int64_t>(c->nranges, blocks), 256, 0, st>>>(n, c->nranges, c->d_rcur, c->d_pairs1, c->d_R);
-    *launches += 11;
+    *launches += 3;
   }
   b200sgd::shuf2_resolve_kernel<<<blocks, 256, 0, st>>>(n, c->d_last, c->d_R, in, out);
   CUDA_TRY(cudaGetLastError());
-  *launches += 1;
+  *launches += 2;
   return SGD_OK;
 }
 
@@ -1311,6 +1340,15 @@ int sgd_create(const sgd_config* cfg, const float* X, const float* y, sgd_ctx** 
       if (const char* e = std::getenv("B200SGD_WATCHDOG_MS")) ns = 1000000ull * (unsigned long long)std::max(1ll, std::atoll(e));
       CUDA_TRY(cudaMemcpyToSymbol(b200sgd::c_spin_timeout_ns, &ns, sizeof(ns)));
     }
+    // B200SGD_L2_FETCH=32|64|128: granularity in which the L2 fetches from DRAM (device-wide limit).  The
+    // permutation kernels and the row gather of narrow records are random accesses of 4 - 448 bytes; ncu
+    // shows the shuffle's resolve pass moving ~117 bytes of DRAM traffic per 4-byte random read.
+    if (const char* e = std::getenv("B200SGD_L2_FETCH")) {
+      const int g = std::atoi(e);
+      if (g == 32 || g == 64 || g == 128) {
+        if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)g) != cudaSuccess) cudaGetLastError();
+      }
+    }
     stamp("streams, events");
     SGD_TRY(configure_launch(c));
     stamp("configure_launch");
@@ -1366,7 +1404,7 @@ int sgd_create(const sgd_config* cfg, const float* X, const float* y, sgd_ctx** 
     if (c->device_shuffle) {
       const size_t n = (size_t)c->R;
       c->scan_tiles = (int32_t)((n + b200sgd::kScanTile - 1) / b200sgd::kScanTile);
-      if (const char* e = std::getenv("B200SGD_SHUFFLE")) c->shuf_ver = std::min(3, std::max(1, std::atoi(e)));
+      if (const char* e = std::getenv("B200SGD_SHUFFLE")) c->shuf_ver = std::min(5, std::max(1, std::atoi(e)));
       CUDA_TRY(cudaMalloc(&c->d_tilesum, sizeof(int32_t) * ((size_t)c->scan_tiles + 1)));
       if (c->shuf_ver == 1) {
         CUDA_TRY(cudaMalloc(&c->d_tgt, sizeof(uint32_t) * n));
@@ -1376,8 +1414,8 @@ int sgd_create(const sgd_config* cfg, const float* X, const float* y, sgd_ctx** 
         CUDA_TRY(cudaMalloc(&c->d_first, sizeof(int32_t) * n));
       } else {
         c->ngran = (int64_t)((n + b200sgd::kGran - 1) >> b200sgd::kGranLog);
-        c->cshift = 13;
-        while (c->cshift < 18 && (((int64_t)n + (1ll << c->cshift) - 1) >> c->cshift) > 8192) ++c->cshift;
+        c->cshift = 14;
+        while (c->cshift < 19 && (((int64_t)n + (1ll << c->cshift) - 1) >> c->cshift) > b200sgd::kCoarseMax) ++c->cshift;
         c->ncoarse = ((int64_t)n + (1ll << c->cshift) - 1) >> c->cshift;
         c->nranges = ((int64_t)n + (1ll << b200sgd::kRangeLog) - 1) >> b200sgd::kRangeLog;
         CUDA_TRY(cudaMalloc(&c->d_pairs2, sizeof(uint2) * n));
@@ -1387,7 +1425,7 @@ int sgd_create(const sgd_config* cfg, const float* X, const float* y, sgd_ctx** 
         // version 2 counts per granule, version 3 per coarse bucket: one counter array serves both
         CUDA_TRY(cudaMalloc(&c->d_ccnt, sizeof(int32_t) * ((size_t)c->ngran + 1)));
         CUDA_TRY(cudaMalloc(&c->d_cstart, sizeof(int32_t) * ((size_t)c->ncoarse + 1)));
-        if (c->shuf_ver == 3) {
+        if (c->shuf_ver >= 3) {
           CUDA_TRY(cudaMalloc(&c->d_pairs1, sizeof(uint2) * ((size_t)c->nranges << b200sgd::kRangeLog)));
           CUDA_TRY(cudaMalloc(&c->d_rcur, sizeof(int32_t) * (size_t)c->nranges));
         }
@@ -1412,6 +1450,19 @@ int sgd_create(const sgd_config* cfg, const float* X, const float* y, sgd_ctx** 
         }
         CUDA_TRY(cudaMalloc(&c->d_subjump, sizeof(uint32_t) * sj.size()));
         CUDA_TRY(cudaMemcpy(c->d_subjump, sj.data(), sizeof(uint32_t) * sj.size(), cudaMemcpyHostToDevice));
+        const int64_t Lx = L / S, nx = (c->R - 1 + Lx - 1) / Lx;
+        c->stream_grid = (int)std::max<int64_t>(1, (nx + 127) / 128);
+        if (c->shuf_ver >= 4) {
+          const size_t cells = (size_t)c->ncoarse * (size_t)c->stream_grid + 1;
+          CUDA_TRY(cudaMalloc(&c->d_mcnt, sizeof(int32_t) * cells));
+          CUDA_TRY(cudaMalloc(&c->d_moff, sizeof(int32_t) * cells));
+          const size_t tiles = (cells + b200sgd::kScanTile - 1) / b200sgd::kScanTile;
+          if (tiles > (size_t)c->scan_tiles) {  // small data sets: the matrix has more cells than rows
+            cudaFree(c->d_tilesum);
+            c->d_tilesum = nullptr;
+            CUDA_TRY(cudaMalloc(&c->d_tilesum, sizeof(int32_t) * (tiles + 1)));
+          }
+        }
       }
     }
     stamp("shuffle buffers");

@@ -76,28 +76,44 @@ __global__ void __launch_bounds__(128) shuf2_expand_states_kernel(const uint32_t
   }
 }
 
+constexpr int kCoarseMax = 4096;  // coarse buckets at most: their counters fit 16 KB of shared memory
+
 // K1a (MODE 0) / K1b (MODE 1): thread c regenerates chunk c of this epoch's rand() stream (values k in
 // [c*L, (c+1)*L), consumed by steps i = k+1) from its 31-word start state (host_rng.hpp chunk_states):
 // x[k] = x[k-31] + x[k-3] (mod 2^32), rand() = x >> 1, j = rand() % (i+1) (stl_algo.h).
-//   MODE 0: gcnt[j >> 8] += 1 for every hit (gcnt zero on entry)
-//   MODE 1: cursor[j >> 8] (a copy of the granules' region offsets) hands out the slot of the pair
-//           (j, i); self swaps and step 0 get their R entry here (R != nullptr).  Atomics of a third
-//           of a round (11 values) are issued back to back so that their round trips overlap; 88
-//           registers at most, so that a block of 128 fits beside a CTA of the step kernel.
-template <int MODE>
+//   MODE 0: bins[j >> shift] += 1 for every hit
+//   MODE 1: bins[j >> shift] (the offset of the bin's region) hands out the slot of the pair (j, i); self
+//           swaps and step 0 get their R entry here (R != nullptr).  The atomics of a third of a round (11
+//           values) are issued back to back so that their round trips overlap; 88 registers at most, so
+//           that a block of 128 fits beside a CTA of the step kernel.
+//   BLOCKBINS = false: bins are global counters / cursors -- one L2 atomic per element, and the L2 does
+//           ~30 G of them per second whatever they hit (measured: 64 M in 2.7 ms; 8 MB of DRAM traffic).
+//   BLOCKBINS = true : the bins (<= kCoarseMax coarse buckets) live in shared memory.  MODE 0 leaves the
+//           block's counts in column blockIdx of the matrix bins[bucket * gridDim + block]; the exclusive
+//           scan of that matrix in memory order gives every (bucket, block) its own region, MODE 1
+//           starts its shared cursors there: no global atomic at all, and a deterministic layout.
+template <int MODE, bool BLOCKBINS>
 __global__ void __launch_bounds__(128) shuf2_stream_kernel(const uint32_t* __restrict__ states, int64_t L,
-                                                           int64_t nchunks, int64_t n, int shift,
-                                                           int32_t* __restrict__ gcur, uint2* __restrict__ pairs,
+                                                           int64_t nchunks, int64_t n, int shift, int nbins,
+                                                           int32_t* __restrict__ gbins, uint2* __restrict__ pairs,
                                                            int32_t* __restrict__ R) {
+  __shared__ int32_t s_bins[BLOCKBINS ? kCoarseMax : 1];
+  int32_t* bins = BLOCKBINS ? s_bins : gbins;
+  if (BLOCKBINS) {
+    for (int b = threadIdx.x; b < nbins; b += blockDim.x)
+      s_bins[b] = MODE == 0 ? 0 : gbins[(int64_t)b * gridDim.x + blockIdx.x];
+    __syncthreads();
+  }
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (MODE == 1 && c == 0 && R != nullptr) R[0] = 0;
-  if (c >= nchunks) return;
   uint32_t r[31];
+  uint32_t k = 0, kend = 0;  // 32-bit step arithmetic (n < 2^31): k = index into the epoch's stream
+  if (c < nchunks) {
 #pragma unroll
-  for (int i = 0; i < 31; ++i) r[i] = states[c * 31 + i];
-  // 32-bit step arithmetic (n < 2^31): k = index into the epoch's stream, the epoch consumes n-1 values
-  uint32_t k = (uint32_t)(c * L);
-  const uint32_t kend = (uint32_t)((c * L + L < n - 1) ? (c * L + L) : (n - 1));
+    for (int i = 0; i < 31; ++i) r[i] = states[c * 31 + i];
+    k = (uint32_t)(c * L);
+    kend = (uint32_t)((c * L + L < n - 1) ? (c * L + L) : (n - 1));  // the epoch consumes n-1 values
+  }
   while (k < kend) {
 #pragma unroll
     for (int h = 0; h < 3; ++h) {  // values 0..10, 11..21 and 22..30 of the round
@@ -118,8 +134,8 @@ __global__ void __launch_bounds__(128) shuf2_stream_kernel(const uint32_t* __res
         const int i = h * kHalf + u;
         slot[u] = -1;
         if (i < 31 && k + (uint32_t)i < kend && jj[u] != k + (uint32_t)i + 1u) {
-          if (MODE == 0) atomicAdd(gcur + (jj[u] >> shift), 1);
-          else slot[u] = atomicAdd(gcur + (jj[u] >> shift), 1);
+          if (MODE == 0) atomicAdd(bins + (jj[u] >> shift), 1);
+          else slot[u] = atomicAdd(bins + (jj[u] >> shift), 1);
         }
       }
       if (MODE == 1) {
@@ -135,6 +151,10 @@ __global__ void __launch_bounds__(128) shuf2_stream_kernel(const uint32_t* __res
       }
     }
     k += 31;
+  }
+  if (BLOCKBINS && MODE == 0) {
+    __syncthreads();
+    for (int b = threadIdx.x; b < nbins; b += blockDim.x) gbins[(int64_t)b * gridDim.x + blockIdx.x] = s_bins[b];
   }
 }
 
@@ -170,8 +190,10 @@ __device__ __forceinline__ void block_scan_1024(int32_t* s, int32_t* s_part) {
 // them, <= 1024 granules each: their write fronts stay in L2 and complete sector by sector), and this
 // kernel, one block per coarse bucket, regroups a bucket by granule: count, scan, scatter -- the
 // bucket's region is small and written by one block.  It also produces the granules' offsets gstart[].
+// Bucket b's region starts at cstart[b * cstride] (cstride = the stream kernels' grid when the offsets
+// are the scanned (bucket, block) matrix).
 __global__ void __launch_bounds__(kLinkThreads) shuf2_refine_kernel(int64_t ngran, int64_t ncoarse, int cshift,
-                                                                    const int32_t* __restrict__ cstart,
+                                                                    const int32_t* __restrict__ cstart, int64_t cstride,
                                                                     const uint2* __restrict__ pairs1,
                                                                     uint2* __restrict__ pairs2,
                                                                     int32_t* __restrict__ gstart) {
@@ -180,7 +202,7 @@ __global__ void __launch_bounds__(kLinkThreads) shuf2_refine_kernel(int64_t ngra
   const int tid = threadIdx.x;
   const int gshift = cshift - kGranLog;  // granules per coarse bucket = 2^gshift <= 1024
   for (int64_t b = blockIdx.x; b < ncoarse; b += gridDim.x) {
-    const int32_t base = cstart[b], m = cstart[b + 1] - base;
+    const int32_t base = cstart[b * cstride], m = cstart[(b + 1) * cstride] - base;
     const int64_t g0 = b << gshift;
     for (int k = tid; k < 1024; k += kLinkThreads) s_h[k] = 0;
     __syncthreads();

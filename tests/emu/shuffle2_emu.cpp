@@ -3,8 +3,10 @@
 // map of the multi-GPU mode) with the host loop of host_rng.hpp (exact_shuffle, itself pinned by the
 // real glibc/libstdc++ golden vectors in tests/test_host.py).
 // usage: shuffle2_emu <rows> <epochs> <chunk_len> <grid of the link/resolve kernels> <variant 2|3> [coarse shift]
-//   variant 2: scatter by granule, R written in place; variant 3: two-level scatters (coarse buckets +
-//   refine for the pairs, coarse ranges + place for R)
+//   variant 2: scatter by granule (global cursors), R written in place
+//   variant 3: coarse buckets (global cursors) + refine, R by coarse ranges + place
+//   variant 4: coarse buckets (per-block counts in shared memory, scanned (bucket, block) matrix) + refine, R in place
+//   variant 5: as 4, R by coarse ranges + place
 #include "cuda_emu.hpp"
 
 #include <cstdio>
@@ -22,8 +24,8 @@ int main(int argc, char** argv) {
   const int64_t L = argc > 3 ? std::atoll(argv[3]) : 1024;
   const unsigned grid = argc > 4 ? (unsigned)std::atoi(argv[4]) : 7;
   const int variant = argc > 5 ? std::atoi(argv[5]) : 2;
-  int cshift = 13;
-  while (cshift < 18 && ((n + (1ll << cshift) - 1) >> cshift) > 8192) ++cshift;
+  int cshift = 14;
+  while (cshift < 19 && ((n + (1ll << cshift) - 1) >> cshift) > kCoarseMax) ++cshift;
   if (argc > 6) cshift = std::atoi(argv[6]);
   const int64_t ncoarse = (n + (1ll << cshift) - 1) >> cshift;
   const int64_t nranges = (n + (1ll << kRangeLog) - 1) >> kRangeLog;
@@ -41,6 +43,7 @@ int main(int argc, char** argv) {
   std::vector<uint32_t> states((size_t)31 * std::max<int64_t>(1, nchunks_h * S));
   std::vector<int32_t> gcnt((size_t)ngran + 1), gstart((size_t)ngran + 1), cursor((size_t)ngran + 1);
   std::vector<uint2> pairs((size_t)n), pairs1((size_t)(nranges << kRangeLog));
+  std::vector<int32_t> mcnt, moff;
   std::vector<int32_t> ccnt((size_t)ncoarse + 1), cstart((size_t)ncoarse + 1), ccur((size_t)ncoarse + 1), rcur((size_t)nranges);
   std::vector<int32_t> last((size_t)n, -7), R((size_t)n, INT32_MIN), perm((size_t)n), out((size_t)n), map((size_t)n);
   std::vector<int32_t> ref((size_t)n);
@@ -59,7 +62,7 @@ int main(int argc, char** argv) {
     const unsigned sblocks = (unsigned)((nchunks + 127) / 128);
     if (variant == 2) {
       emu_launch(sblocks, 128, [&] {
-        shuf2_stream_kernel<0>(states.data(), L, nchunks, n, kGranLog, gcnt.data(), nullptr, nullptr);
+        shuf2_stream_kernel<0, false>(states.data(), L, nchunks, n, kGranLog, 0, gcnt.data(), nullptr, nullptr);
       });
       int32_t acc = 0;  // the device uses the three scan kernels of shuffle_kernels.cuh (warp shuffles: not emulated)
       for (int64_t g = 0; g <= ngran; ++g) {
@@ -68,7 +71,7 @@ int main(int argc, char** argv) {
       }
       cursor = gstart;
       emu_launch(sblocks, 128, [&] {
-        shuf2_stream_kernel<1>(states.data(), L, nchunks, n, kGranLog, cursor.data(), pairs.data(), R.data());
+        shuf2_stream_kernel<1, false>(states.data(), L, nchunks, n, kGranLog, 0, cursor.data(), pairs.data(), R.data());
       });
       emu_launch(grid, kLinkThreads, [&] {
         shuf2_link_kernel<false>(n, ngran, gstart.data(), pairs.data(), last.data(), R.data(), nullptr, nullptr, &err);
@@ -76,26 +79,56 @@ int main(int argc, char** argv) {
     } else {
       std::fill(ccnt.begin(), ccnt.end(), 0);
       std::fill(gstart.begin(), gstart.end(), -12345);
-      emu_launch(sblocks, 128, [&] {
-        shuf2_stream_kernel<0>(states.data(), L, nchunks, n, cshift, ccnt.data(), nullptr, nullptr);
-      });
-      int32_t acc = 0;
-      for (int64_t b = 0; b <= ncoarse; ++b) {
-        cstart[(size_t)b] = acc;
-        if (b < ncoarse) acc += ccnt[(size_t)b];
+      const bool rscatter = variant == 3 || variant == 5;
+      int64_t cstride = 1;
+      const int32_t* coff = cstart.data();
+      if (variant == 3) {
+        emu_launch(sblocks, 128, [&] {
+          shuf2_stream_kernel<0, false>(states.data(), L, nchunks, n, cshift, 0, ccnt.data(), nullptr, nullptr);
+        });
+        int32_t acc = 0;
+        for (int64_t b = 0; b <= ncoarse; ++b) {
+          cstart[(size_t)b] = acc;
+          if (b < ncoarse) acc += ccnt[(size_t)b];
+        }
+        ccur = cstart;
+        emu_launch(sblocks, 128, [&] {
+          shuf2_stream_kernel<1, false>(states.data(), L, nchunks, n, cshift, 0, ccur.data(), pairs1.data(), nullptr);
+        });
+      } else {
+        mcnt.assign((size_t)ncoarse * sblocks + 1, -1);
+        emu_launch(sblocks, 128, [&] {
+          shuf2_stream_kernel<0, true>(states.data(), L, nchunks, n, cshift, (int)ncoarse, mcnt.data(), nullptr, nullptr);
+        });
+        moff.resize(mcnt.size());
+        int32_t acc = 0;
+        for (size_t q = 0; q + 1 < mcnt.size(); ++q) {
+          moff[q] = acc;
+          acc += mcnt[q];
+        }
+        moff.back() = acc;
+        mcnt = moff;  // MODE 1 reads its cursors' start values from the scanned matrix
+        emu_launch(sblocks, 128, [&] {
+          shuf2_stream_kernel<1, true>(states.data(), L, nchunks, n, cshift, (int)ncoarse, mcnt.data(), pairs1.data(),
+                                       rscatter ? nullptr : R.data());
+        });
+        cstride = sblocks;
+        coff = moff.data();
       }
-      ccur = cstart;
-      emu_launch(sblocks, 128, [&] {
-        shuf2_stream_kernel<1>(states.data(), L, nchunks, n, cshift, ccur.data(), pairs1.data(), nullptr);
-      });
       emu_launch(grid, kLinkThreads, [&] {
-        shuf2_refine_kernel(ngran, ncoarse, cshift, cstart.data(), pairs1.data(), pairs.data(), gstart.data());
+        shuf2_refine_kernel(ngran, ncoarse, cshift, coff, cstride, pairs1.data(), pairs.data(), gstart.data());
       });
+      if (!rscatter) {
+        emu_launch(grid, kLinkThreads, [&] {
+          shuf2_link_kernel<false>(n, ngran, gstart.data(), pairs.data(), last.data(), R.data(), nullptr, nullptr, &err);
+        });
+      } else {
       emu_launch(3, 256, [&] { shuf2_range_cursor_kernel(rcur.data(), nranges, kRangeLog); });
       emu_launch(grid, kLinkThreads, [&] {  // the entries of R go where the coarse pairs were
         shuf2_link_kernel<true>(n, ngran, gstart.data(), pairs.data(), last.data(), nullptr, rcur.data(), pairs1.data(), &err);
       });
       emu_launch(grid + 2, 256, [&] { shuf2_place_kernel(n, nranges, rcur.data(), pairs1.data(), R.data()); });
+      }
     }
     emu_launch(grid, 256, [&] { shuf2_resolve_kernel(n, last.data(), R.data(), perm.data(), out.data()); });
     emu_launch(grid + 1, 256, [&] { shuf2_resolve_kernel(n, last.data(), R.data(), nullptr, map.data()); });

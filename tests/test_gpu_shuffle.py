@@ -1,7 +1,7 @@
 """The device permutation must equal the reference's host loop (std::random_shuffle + glibc rand(),
-main.cu:90 / :207) bit for bit, cumulatively over epochs -- in all three formulations: the backward one
-with two-level scatters (csrc/shuffle2_kernels.cuh, the default, B200SGD_SHUFFLE=3), the backward one
-with direct scatters (=2) and the forward one of round 1 (csrc/shuffle_kernels.cuh, =1)."""
+main.cu:90 / :207) bit for bit, cumulatively over epochs -- in every formulation B200SGD_SHUFFLE selects: the backward one
+(csrc/shuffle2_kernels.cuh; 4 = the default, 2 / 3 / 5 = its other scatter strategies) and the forward
+one of round 1 (csrc/shuffle_kernels.cuh, = 1)."""
 import numpy as np
 import pytest
 
@@ -12,7 +12,7 @@ from oracle import loader as orc
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=[3, 2, 1], ids=["backward2level", "backward", "forward"])
+@pytest.fixture(params=[4, 5, 3, 2, 1], ids=["backward-blockbins", "backward-blockbins-rscatter", "backward-2level", "backward-direct", "forward"])
 def shuffle_version(request, monkeypatch):
     monkeypatch.setenv("B200SGD_SHUFFLE", str(request.param))  # read by sgd_create
     return request.param
@@ -56,7 +56,7 @@ def test_device_and_host_paths_agree_and_interleave(shuffle_version):
 @pytest.mark.parametrize("R", [4000000, 16777216, 67108864])   # configs 2/3, 4 and 5
 def test_device_shuffle_golden_kat(kat, R, shuffle_version):
     # golden values from the REAL glibc / libstdc++ (tests/golden/thirdparty_kat.json)
-    if shuffle_version != 3 and R > 4000000:
+    if shuffle_version != 4 and R > 4000000:
         pytest.skip("the non-default formulations are checked at 4M rows")
     recs = [r for r in kat["shuffle_kat"] if r["R"] == R]
     with pkg.SGDEngine(R, 1, 1000, 0.1) as eng:

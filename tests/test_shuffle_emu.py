@@ -19,10 +19,11 @@ def emu(tmp_path_factory):
     return exe
 
 
-# rows, epochs, sub-chunk length, grid of the grid-stride kernels, variant (2: direct scatters, 3: two-level)
+# rows, epochs, sub-chunk length, grid of the grid-stride kernels, variant (B200SGD_SHUFFLE 2..5)
 @pytest.mark.parametrize("args", [
-    (100000, 2, 128, 7, 3), (100000, 2, 1024, 7, 2), (32769, 2, 128, 1, 3), (300001, 2, 256, 40, 3),
-    (36865, 2, 128, 3, 2), (257, 2, 128, 2, 3), (1025, 2, 8, 2, 2), (524289, 1, 128, 64, 3),
+    (100000, 2, 128, 7, 4), (100000, 2, 128, 7, 5), (100000, 2, 128, 7, 3), (100000, 2, 1024, 7, 2),
+    (32769, 2, 128, 1, 4), (300001, 2, 256, 40, 4), (36865, 2, 128, 3, 5), (257, 2, 128, 2, 4),
+    (1025, 2, 8, 2, 4), (524289, 1, 128, 64, 4),
 ])
 def test_shuffle_kernels_on_the_host_match_the_host_loop(emu, args):
     out = subprocess.run([emu] + [str(a) for a in args], capture_output=True, text=True, timeout=600)
@@ -31,6 +32,6 @@ def test_shuffle_kernels_on_the_host_match_the_host_loop(emu, args):
 
 def test_coarse_bucket_shifts_of_very_large_data_sets(emu):
     # 2^31 rows would use 2^18 positions per coarse bucket (1024 granules): force the shift on a small case
-    for shift in (16, 18, 9):
-        out = subprocess.run([emu, "600000", "1", "128", "9", "3", str(shift)], capture_output=True, text=True, timeout=600)
+    for shift, variant in ((16, 4), (18, 4), (9, 5), (18, 3)):
+        out = subprocess.run([emu, "600000", "1", "128", "9", str(variant), str(shift)], capture_output=True, text=True, timeout=600)
         assert out.returncode == 0 and out.stdout.strip().endswith("OK"), out.stdout + out.stderr

@@ -1,11 +1,11 @@
 #!/usr/bin/env python
 """Wall time of the bit-exact device shuffle (sgd_shuffle, synchronous) by data set size and formulation
-(B200SGD_SHUFFLE: 3 = backward with two-level scatters, 2 = backward, 1 = forward / round 1).
-usage: shuffle_time.py [rows ...] [v=3,2,1]"""
+(B200SGD_SHUFFLE, see b200sgd_api.cu: 1 = forward / round 1, 2..5 = backward with different scatters).
+usage: shuffle_time.py [rows ...] [v=4,5,3,2,1]"""
 import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import cuda_sgd_sese_project_b200 as pkg
-vers = [3, 2, 1]
+vers = [4, 5, 3, 2, 1]
 sizes = []
 for a in sys.argv[1:]:
     if a.startswith("v="):
