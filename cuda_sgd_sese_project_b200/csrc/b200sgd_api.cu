@@ -196,8 +196,8 @@ struct sgd_ctx {
   //   3 = pairs by coarse bucket (global cursors) + refine, R by coarse range + place
   //   4 = pairs by coarse bucket (per-block counts, scanned (bucket, block) matrix: no global atomics) + refine, R in place
   //   5 = as 4, R by coarse range + place
-  int shuf_ver = 4;
-  static constexpr int kSubChunks = 8;  // device-derived sub-chunk states per host chunk state
+  int shuf_ver = 5;
+  static constexpr int kSubChunks = 64;  // device-derived sub-chunk states per host chunk state
   int cshift = 14;                      // log2 positions per coarse bucket (<= kCoarseMax buckets)
   int stream_grid = 1;                  // blocks of the stream kernels = columns of the count matrix
   int32_t *d_mcnt = nullptr, *d_moff = nullptr;  // (bucket, block) count matrix and its exclusive scan
@@ -1405,6 +1405,8 @@ int sgd_create(const sgd_config* cfg, const float* X, const float* y, sgd_ctx** 
       const size_t n = (size_t)c->R;
       c->scan_tiles = (int32_t)((n + b200sgd::kScanTile - 1) / b200sgd::kScanTile);
       if (const char* e = std::getenv("B200SGD_SHUFFLE")) c->shuf_ver = std::min(5, std::max(1, std::atoi(e)));
+      // the refine kernel bins at most 1024 granules per coarse bucket: beyond 2^30 rows scatter by granule directly
+      if (c->shuf_ver >= 3 && c->R > (1ll << 30)) c->shuf_ver = 2;
       CUDA_TRY(cudaMalloc(&c->d_tilesum, sizeof(int32_t) * ((size_t)c->scan_tiles + 1)));
       if (c->shuf_ver == 1) {
         CUDA_TRY(cudaMalloc(&c->d_tgt, sizeof(uint32_t) * n));
@@ -1415,7 +1417,8 @@ int sgd_create(const sgd_config* cfg, const float* X, const float* y, sgd_ctx** 
       } else {
         c->ngran = (int64_t)((n + b200sgd::kGran - 1) >> b200sgd::kGranLog);
         c->cshift = 14;
-        while (c->cshift < 19 && (((int64_t)n + (1ll << c->cshift) - 1) >> c->cshift) > b200sgd::kCoarseMax) ++c->cshift;
+        if (const char* e = std::getenv("B200SGD_COARSE_SHIFT")) c->cshift = std::min(18, std::max(14, std::atoi(e)));
+        while (c->cshift < 18 && (((int64_t)n + (1ll << c->cshift) - 1) >> c->cshift) > b200sgd::kCoarseMax) ++c->cshift;
         c->ncoarse = ((int64_t)n + (1ll << c->cshift) - 1) >> c->cshift;
         c->nranges = ((int64_t)n + (1ll << b200sgd::kRangeLog) - 1) >> b200sgd::kRangeLog;
         CUDA_TRY(cudaMalloc(&c->d_pairs2, sizeof(uint2) * n));
@@ -1433,8 +1436,10 @@ int sgd_create(const sgd_config* cfg, const float* X, const float* y, sgd_ctx** 
       // the epoch's rand() stream is regenerated on the device from up to 8192 chunk start states
       // (one thread per chunk: at 64M rows 1024 chunks took 10.4 ms, 8192 take ~1.3 ms; the host
       // pays ~0.6 us per state, hidden behind the running epoch)
+      // (backward kernels: 1024 host states at most, 64 sub-chunk states each derived on the device --
+      // the host's share of a shuffle drops from ~5 ms to ~0.6 ms at 64M rows)
       int64_t L = 1024;
-      while (L * 8192 < c->R) L *= 2;
+      while (L * (c->shuf_ver == 1 ? 8192 : 1024) < c->R) L *= 2;
       c->chunk_len = L;
       c->nchunks = (c->R - 1 + L - 1) / L;
       c->jump_chunk = b200sgd::GlibcRand::poly_z_pow((uint64_t)L);

@@ -39,6 +39,20 @@
 
 namespace b200sgd {
 
+// A random 4-byte read.  A plain ld.global of a line that misses pulls (almost) the whole 128-byte line out
+// of DRAM on B200 -- measured with tools/microbench_gather.cu: 3.45 L2 sectors and 92 bytes of DRAM traffic
+// per random 4-byte load; .cs / L1::no_allocate / L1::evict_first: 4 sectors, 119 bytes;
+// cudaLimitMaxL2FetchGranularity = 32: no change -- while the L2::64B qualifier fetches two sectors: 55 bytes.
+__device__ __forceinline__ int32_t ld_sparse(const int32_t* p) {
+#ifdef B200SGD_HOST_EMU
+  return *p;
+#else
+  int32_t v;
+  asm volatile("ld.global.L2::64B.b32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+#endif
+}
+
 constexpr int kGranLog = 8;                 // positions per granule = 256
 constexpr int kGran = 1 << kGranLog;
 constexpr int kLinkThreads = 256;
@@ -368,7 +382,7 @@ __global__ void __launch_bounds__(256) shuf2_resolve_kernel(int64_t n, const int
     while (any) {  // the four chains advance together
       int32_t nx[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) nx[u] = s[u] < 0 ? R[~s[u]] : s[u];
+      for (int u = 0; u < 4; ++u) nx[u] = s[u] < 0 ? ld_sparse(R + ~s[u]) : s[u];
       any = false;
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -380,7 +394,7 @@ __global__ void __launch_bounds__(256) shuf2_resolve_kernel(int64_t n, const int
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int64_t i = i0 + u * stride;
-      val[u] = (in != nullptr && i < n) ? in[s[u]] : s[u];
+      val[u] = (in != nullptr && i < n) ? ld_sparse(in + s[u]) : s[u];
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {

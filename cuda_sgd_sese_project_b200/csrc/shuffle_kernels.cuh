@@ -302,7 +302,9 @@ __global__ void __launch_bounds__(256) shuf_apply_kernel(const int32_t* __restri
 #pragma unroll
     for (int u = 0; u < 4; ++u) s[u] = (i + u * stride < n) ? __ldcs(src + i + u * stride) : 0;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) v[u] = __ldg(in + s[u]);
+    for (int u = 0; u < 4; ++u) {  // two sectors instead of the whole line per random read (shuffle2_kernels.cuh, ld_sparse)
+      asm volatile("ld.global.L2::64B.b32 %0, [%1];" : "=r"(v[u]) : "l"(in + s[u]));
+    }
 #pragma unroll
     for (int u = 0; u < 4; ++u)
       if (i + u * stride < n) out[i + u * stride] = v[u];

@@ -25,11 +25,11 @@ int main(int argc, char** argv) {
   const unsigned grid = argc > 4 ? (unsigned)std::atoi(argv[4]) : 7;
   const int variant = argc > 5 ? std::atoi(argv[5]) : 2;
   int cshift = 14;
-  while (cshift < 19 && ((n + (1ll << cshift) - 1) >> cshift) > kCoarseMax) ++cshift;
+  while (cshift < 18 && ((n + (1ll << cshift) - 1) >> cshift) > kCoarseMax) ++cshift;
   if (argc > 6) cshift = std::atoi(argv[6]);
   const int64_t ncoarse = (n + (1ll << cshift) - 1) >> cshift;
   const int64_t nranges = (n + (1ll << kRangeLog) - 1) >> kRangeLog;
-  const int S = 8;  // sub-chunks per host chunk (shuf2_expand_states_kernel)
+  const int S = 64;  // sub-chunks per host chunk (shuf2_expand_states_kernel)
   const int64_t Lh = L * S, nchunks_h = (n - 1 + Lh - 1) / Lh;
   const int64_t nchunks = (n - 1 + L - 1) / L;
   const int64_t ngran = (n + kGran - 1) / kGran;
