@@ -205,6 +205,14 @@ struct sgd_ctx {
   uint2 *d_pairs1 = nullptr, *d_pairs2 = nullptr;  // coarse-bucketed pairs (later: the entries of R by range) / pairs by granule
   int32_t *d_last = nullptr, *d_R = nullptr, *d_gstart = nullptr, *d_ccnt = nullptr, *d_cstart = nullptr, *d_rcur = nullptr;
   uint32_t *d_states_x = nullptr, *d_subjump = nullptr;
+  // Look-ahead: the rand() stream is never seeded, so the NEXT permutation is known in advance.  sgd_create
+  // and the tail of sgd_run / sgd_iteration enqueue it (into d_perm[cur ^ 1], on the shuffle stream, beside
+  // the data upload / the last epoch's step kernel); the next shuffle request just takes it.
+  bool lookahead = true;        // B200SGD_NO_LOOKAHEAD=1 switches it off
+  bool ahead = false;           // d_perm[cur ^ 1] is (being) filled with the permutation of shuffle shuf_no
+  bool ahead_shared = false;    // ... by the shared (multi-rank) path
+  int64_t reapply_k = 0;        // sgd_set_permutation replaced the input of shared shuffle k: apply its map again
+  b200sgd::GlibcRand rng_saved; // the generator before the look-ahead (unshared path: rolled back by sgd_set_permutation)
   bool host_ind_stale = false;  // h_ind lags behind the device permutation
   // several ranks: the permutation work is shared (shuffle_kernels.cuh): rank (k-1) % nranks computes
   // the position map of shuffle k ahead of time, everybody applies it with one gather pass
@@ -683,6 +691,7 @@ int upload_perm(sgd_ctx* c, int buf) {
   // the compute stream waits on ev_perm[buf] before it uses the buffer
   c->bucketed[buf] = false;
   CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->ev_done[buf], 0));
+  CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->ev_shuf[buf], 0));  // a discarded look-ahead may still be writing it
   CUDA_TRY(cudaMemcpyAsync(c->d_perm[buf], c->h_stage[buf], sizeof(int32_t) * (size_t)c->R,
                            cudaMemcpyHostToDevice, c->copy_stream));
   CUDA_TRY(cudaEventRecord(c->ev_perm[buf], c->copy_stream));
@@ -1030,9 +1039,35 @@ int enqueue_own_map(sgd_ctx* c, int64_t k, int* launches) {
   return SGD_OK;
 }
 
+// Every rank: d_perm[dst] = d_perm[src] o (position map of shuffle k), read from its owner's buffer over
+// NVLink once the owner has published it; then this rank's bucketed row lists.
+int apply_shared_map(sgd_ctx* c, int64_t k, int src, int dst, int* launches) {
+  const int N = c->cfg.nranks, me = c->cfg.rank;
+  const int owner = (int)((k - 1) % N), b = (int)(((k - 1) / N) & 1);
+  cudaStream_t st = c->shuf_stream;
+  CUDA_TRY(cudaStreamWaitEvent(st, c->ev_done[dst], 0));  // last epoch that read d_perm[dst]
+  CUDA_TRY(cudaStreamWaitEvent(st, c->ev_perm[src], 0));  // d_perm[src] uploaded (sgd_set_permutation)
+  uint32_t* flags = (uint32_t*)((char*)c->d_xchg_block + c->flag_off);
+  b200sgd::shuf_wait_flags_kernel<<<1, 32, 0, st>>>(flags, kFlagReady + owner * 2 + b, 1, 1, (uint32_t)k, c->d_bar + 1, watchdog_ns(c));
+  const int64_t n = c->R;
+  const int blocks = (int)std::min<int64_t>((n + 1023) / 1024, (int64_t)c->num_sms * 8);
+  const int32_t* map = (const int32_t*)((const char*)c->peer_block[owner] + c->src_off[b]);
+  b200sgd::shuf_apply_kernel<<<blocks, 256, 0, st>>>(map, c->d_perm[src], c->d_perm[dst], n);
+  b200sgd::PeerFlagPtrs t{};
+  t.p[0] = (uint32_t*)((char*)c->peer_block[owner] + c->flag_off);
+  b200sgd::shuf_set_flags_kernel<<<1, 32, 0, st>>>(t, 1, kFlagDone + b * 8 + me, (uint32_t)k);
+  CUDA_TRY(cudaGetLastError());
+  // the schedule of the new permutation right behind it (d_counts: only this stream uses it in this mode)
+  c->bucketed[dst] = false;
+  SGD_TRY(bucket_perm(c, dst, launches, st));
+  CUDA_TRY(cudaEventRecord(c->ev_shuf[dst], st));
+  *launches += 3;
+  return SGD_OK;
+}
+
 // Every rank: shuffle number k = shuf_no + 1 turns d_perm[src] into d_perm[dst] on the shuffle stream.
 int enqueue_shared_shuffle(sgd_ctx* c, int src, int dst, int* launches) {
-  const int N = c->cfg.nranks, me = c->cfg.rank;
+  const int N = c->cfg.nranks;
   const int64_t k = c->shuf_no + 1;
   if (c->shared_first == 0) {  // first shared shuffle: skip the maps of shuffles that were done the unshared way
     c->shared_first = k;
@@ -1052,26 +1087,8 @@ int enqueue_shared_shuffle(sgd_ctx* c, int src, int dst, int* launches) {
     c->own_next += N;
   }
   if (c->R > 1) c->rng.skip((uint64_t)(c->R - 1));  // the context's own generator stays in step (host-side fallbacks)
-  const int owner = (int)((k - 1) % N), b = (int)(((k - 1) / N) & 1);
-  cudaStream_t st = c->shuf_stream;
-  CUDA_TRY(cudaStreamWaitEvent(st, c->ev_done[dst], 0));  // last epoch that read d_perm[dst]
-  CUDA_TRY(cudaStreamWaitEvent(st, c->ev_perm[src], 0));  // d_perm[src] uploaded (sgd_set_permutation)
-  uint32_t* flags = (uint32_t*)((char*)c->d_xchg_block + c->flag_off);
-  b200sgd::shuf_wait_flags_kernel<<<1, 32, 0, st>>>(flags, kFlagReady + owner * 2 + b, 1, 1, (uint32_t)k, c->d_bar + 1, watchdog_ns(c));
-  const int64_t n = c->R;
-  const int blocks = (int)std::min<int64_t>((n + 1023) / 1024, (int64_t)c->num_sms * 8);
-  const int32_t* map = (const int32_t*)((const char*)c->peer_block[owner] + c->src_off[b]);
-  b200sgd::shuf_apply_kernel<<<blocks, 256, 0, st>>>(map, c->d_perm[src], c->d_perm[dst], n);
-  b200sgd::PeerFlagPtrs t{};
-  t.p[0] = (uint32_t*)((char*)c->peer_block[owner] + c->flag_off);
-  b200sgd::shuf_set_flags_kernel<<<1, 32, 0, st>>>(t, 1, kFlagDone + b * 8 + me, (uint32_t)k);
-  CUDA_TRY(cudaGetLastError());
-  // the schedule of the new permutation right behind it (d_counts: only this stream uses it in this mode)
-  c->bucketed[dst] = false;
-  SGD_TRY(bucket_perm(c, dst, launches, st));
-  CUDA_TRY(cudaEventRecord(c->ev_shuf[dst], st));
+  SGD_TRY(apply_shared_map(c, k, src, dst, launches));
   c->shuf_no = k;
-  *launches += 3;
   return SGD_OK;
 }
 
@@ -1080,6 +1097,44 @@ int enqueue_shared_shuffle(sgd_ctx* c, int src, int dst, int* launches) {
 int ensure_host_stage(sgd_ctx* c) {
   for (int i = 0; i < 2; ++i)
     if (!c->h_stage[i]) CUDA_TRY(cudaMallocHost(&c->h_stage[i], sizeof(int32_t) * (size_t)c->R));
+  return SGD_OK;
+}
+
+// One device shuffle d_perm[src] -> d_perm[dst], enqueued (no host sync): the shared way with several
+// connected ranks, else all of it on this GPU.
+int enqueue_next_shuffle(sgd_ctx* c, int src, int dst, int* launches) {
+  if (use_shared_shuffle(c)) return enqueue_shared_shuffle(c, src, dst, launches);
+  CUDA_TRY(cudaEventSynchronize(c->ev_perm[dst]));  // staging buffer free again
+  c->rng_saved = c->rng;
+  prepare_stream_states(c, dst);
+  SGD_TRY(enqueue_device_shuffle(c, dst, src, dst, launches));
+  c->shuf_no += 1;
+  return SGD_OK;
+}
+
+// A shuffle request: take the look-ahead if there is one, else enqueue the shuffle now.  Flips c->cur.
+int take_or_enqueue_shuffle(sgd_ctx* c, int* launches) {
+  const int buf = c->cur ^ 1;
+  if (c->ahead) {
+    c->ahead = false;  // d_perm[buf] is already being produced on the shuffle stream
+  } else if (c->reapply_k) {
+    SGD_TRY(apply_shared_map(c, c->reapply_k, c->cur, buf, launches));
+    c->reapply_k = 0;
+  } else {
+    SGD_TRY(enqueue_next_shuffle(c, c->cur, buf, launches));
+  }
+  c->cur = buf;
+  c->perm_valid = true;
+  c->host_ind_stale = true;
+  return SGD_OK;
+}
+
+// Enqueue the NEXT permutation into d_perm[cur ^ 1] without making it current.
+int enqueue_lookahead(sgd_ctx* c, int* launches) {
+  if (!c->device_shuffle || !c->lookahead || c->ahead || c->reapply_k) return SGD_OK;
+  c->ahead_shared = use_shared_shuffle(c);
+  SGD_TRY(enqueue_next_shuffle(c, c->cur, c->cur ^ 1, launches));
+  c->ahead = true;
   return SGD_OK;
 }
 
@@ -1525,6 +1580,10 @@ int sgd_create(const sgd_config* cfg, const float* X, const float* y, sgd_ctx** 
     c->host_ind_stale = true;
     CUDA_TRY(cudaDeviceSynchronize());
     stamp("weights, identity, sync");
+    // the first permutation does not depend on the data: it is produced beside the upload of the rows
+    c->lookahead = std::getenv("B200SGD_NO_LOOKAHEAD") == nullptr;
+    int la = 0;
+    SGD_TRY(enqueue_lookahead(c, &la));
     return SGD_OK;
   };
   int rc = setup();
@@ -1879,21 +1938,10 @@ int sgd_shuffle(sgd_ctx* c) {
   SGD_TRY(bind(c));
   const auto t0 = clk::now();
   if (c->device_shuffle) {
-    const int buf = c->cur ^ 1;
     int launches = 0;
-    if (use_shared_shuffle(c)) {
-      SGD_TRY(enqueue_shared_shuffle(c, c->cur, buf, &launches));
-    } else {
-      CUDA_TRY(cudaEventSynchronize(c->ev_perm[buf]));
-      prepare_stream_states(c, buf);
-      SGD_TRY(enqueue_device_shuffle(c, buf, c->cur, buf, &launches));
-      c->shuf_no += 1;
-    }
+    SGD_TRY(take_or_enqueue_shuffle(c, &launches));
     CUDA_TRY(cudaStreamSynchronize(c->shuf_stream));
     SGD_TRY(check_watchdog(c));
-    c->cur = buf;
-    c->perm_valid = true;
-    c->host_ind_stale = true;
     c->last_shuffle_ms = (float)ms_since(t0);
     c->last_shuffle_launches = launches;
     return SGD_OK;
@@ -1928,6 +1976,15 @@ int sgd_set_permutation(sgd_ctx* c, const int32_t* perm) {
     }
   }
   SGD_TRY(bind(c));
+  if (c->ahead) {  // the look-ahead shuffled the OLD permutation
+    if (c->ahead_shared) {
+      c->reapply_k = c->shuf_no;  // its position map stays valid: the next shuffle request applies it to the new one
+    } else {
+      c->rng = c->rng_saved;  // the next shuffle draws the same rand() values again
+      c->shuf_no -= 1;
+    }
+    c->ahead = false;
+  }
   SGD_TRY(ensure_host_stage(c));
   c->h_ind.resize((size_t)c->R);
   std::memcpy(c->h_ind.data(), perm, sizeof(int32_t) * (size_t)c->R);
@@ -1960,7 +2017,8 @@ int sgd_get_permutation(sgd_ctx* c, int32_t* perm) {
 }
 
 // ---- the step loop ------------------------------------------------------------------------------
-int sgd_epoch(sgd_ctx* c, int32_t epoch, sgd_timings* out) {
+namespace {
+int epoch_impl(sgd_ctx* c, int32_t epoch, sgd_timings* out, bool lookahead) {
   SGD_TRY(check_ctx(c));
   if (epoch < 1) return fail(SGD_ERR_ARG, "epoch is 1-based");
   if (!c->data_loaded) return fail(SGD_ERR_STATE, "no data loaded");
@@ -1974,6 +2032,7 @@ int sgd_epoch(sgd_ctx* c, int32_t epoch, sgd_timings* out) {
   SGD_TRY(launch_epoch(c, epoch, c->cur, &launches));
   CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
   CUDA_TRY(cudaEventRecord(c->ev_done[c->cur], c->stream));
+  if (lookahead) SGD_TRY(enqueue_lookahead(c, &launches));  // the next iteration's permutation, beside this epoch
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   SGD_TRY(check_watchdog(c));
   SGD_TRY(collect_losses(c));
@@ -1984,10 +2043,15 @@ int sgd_epoch(sgd_ctx* c, int32_t epoch, sgd_timings* out) {
   c->last_shuffle_launches = 0;
   return SGD_OK;
 }
+}  // namespace
+
+// sgd_epoch runs the step kernel on its own (what the sweeps and `kernel_alone` time); sgd_iteration, the
+// drop-in for one cuda_iteration / cublas_iteration call, also starts the next call's permutation.
+int sgd_epoch(sgd_ctx* c, int32_t epoch, sgd_timings* out) { return epoch_impl(c, epoch, out, false); }
 
 int sgd_iteration(sgd_ctx* c, int32_t epoch, sgd_timings* out) {
   SGD_TRY(sgd_shuffle(c));
-  return sgd_epoch(c, epoch, out);
+  return epoch_impl(c, epoch, out, true);
 }
 
 int sgd_run(sgd_ctx* c, int32_t first_epoch, int32_t num_epochs, sgd_timings* total) {
@@ -2013,21 +2077,7 @@ int sgd_run(sgd_ctx* c, int32_t first_epoch, int32_t num_epochs, sgd_timings* to
   int launches = 0;
   int rc = SGD_OK;
   auto stage_next = [&]() -> int {  // host part of the shuffle runs while the GPU runs the previous epoch
-    if (c->device_shuffle) {
-      const int buf = c->cur ^ 1;
-      if (use_shared_shuffle(c)) {
-        SGD_TRY(enqueue_shared_shuffle(c, c->cur, buf, &launches));
-      } else {
-        CUDA_TRY(cudaEventSynchronize(c->ev_perm[buf]));  // staging buffer free again
-        prepare_stream_states(c, buf);
-        SGD_TRY(enqueue_device_shuffle(c, buf, c->cur, buf, &launches));
-        c->shuf_no += 1;
-      }
-      c->cur = buf;
-      c->perm_valid = true;
-      c->host_ind_stale = true;
-      return SGD_OK;
-    }
+    if (c->device_shuffle) return take_or_enqueue_shuffle(c, &launches);
     SGD_TRY(sync_host_ind(c));
     SGD_TRY(ensure_host_stage(c));
     b200sgd::exact_shuffle(c->rng, c->h_ind.data(), c->R);
@@ -2054,6 +2104,7 @@ int sgd_run(sgd_ctx* c, int32_t first_epoch, int32_t num_epochs, sgd_timings* to
     };
     rc = enqueue();
     if (rc == SGD_OK && e + 1 < num_epochs) rc = stage_next();  // overlaps with the kernel above
+    else if (rc == SGD_OK) rc = enqueue_lookahead(c, &launches);  // the next call's first permutation, beside the last epoch
     if (rc == SGD_OK && c->loss_pending >= kLossSlots - 1) {      // very long runs: drain the loss slots
       if (cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail(SGD_ERR_CUDA, "epoch loop failed");
       if (rc == SGD_OK) rc = collect_losses(c);

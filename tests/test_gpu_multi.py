@@ -94,3 +94,57 @@ def test_four_ranks(tmp_path):
 
 def test_eight_ranks(tmp_path):
     _run(8, 80000, 64, 4000, 0.05, 2, tmp_path)
+
+
+def _worker_setperm(rank, world, port, R, C, B, out):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    import cuda_sgd_sese_project_b200 as pkg
+    from cuda_sgd_sese_project_b200.dist import connect_peers
+    from oracle import loader as orc
+    from tests.helpers import make_regression
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    X, y, _ = make_regression(R, C, seed=11)
+    eng = pkg.SGDEngine(R, C, B, 0.01, device=rank, rank=rank, nranks=world)
+    b, e = pkg.shard_range(R, rank, world)
+    eng.load_rows(b, X[b:e], y[b:e])
+    connect_peers(eng)
+    g = orc.Rand()
+    ind = np.arange(R, dtype=np.int32)
+    eng.run(1, 2)                           # shuffle 1 (own, from sgd_create's look-ahead), 2 (shared); 3 is ahead
+    g.shuffle(ind); g.shuffle(ind)
+    assert np.array_equal(eng.permutation(), ind)
+    start = ind[::-1].copy()
+    eng.set_permutation(start)              # the map of shuffle 3 is applied to the new permutation instead
+    eng.iteration(3)
+    g.shuffle(start)
+    assert np.array_equal(eng.permutation(), start)
+    eng.run(4, 2)
+    g.shuffle(start); g.shuffle(start)
+    assert np.array_equal(eng.permutation(), start)
+    np.save(out, eng.weights)
+    dist.barrier()
+    eng.close()
+    dist.destroy_process_group()
+
+
+def test_set_permutation_after_a_shared_lookahead(tmp_path):
+    import torch
+    import torch.multiprocessing as mp
+    world = 2
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    port = _free_port()
+    outs = [str(tmp_path / f"w{r}.npy") for r in range(world)]
+    ctx = mp.get_context("spawn")
+    procs = [ctx.Process(target=_worker_setperm, args=(r, world, port, 60000, 64, 2000, outs[r])) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    assert np.array_equal(np.load(outs[0]), np.load(outs[1]))

@@ -92,3 +92,47 @@ def test_odd_sizes_around_the_granule_and_range_boundaries(shuffle_version):
                 g.shuffle(ind)
                 eng.shuffle()
                 assert np.array_equal(eng.permutation(), ind), R
+
+
+def test_lookahead_is_transparent():
+    """sgd_create, sgd_run and sgd_iteration enqueue the NEXT permutation ahead of time (the rand() stream is
+    never seeded); shuffle requests, sgd_get_permutation and sgd_set_permutation must not see a difference."""
+    R = 50000
+    g = orc.Rand()
+    ind = np.arange(R, dtype=np.int32)
+    with pkg.SGDEngine(R, 4, 1000, 0.01) as eng:
+        eng.load_synthetic(seed=1)
+        eng.run(1, 2)                                   # shuffles 1, 2; 3 is now ahead
+        g.shuffle(ind); g.shuffle(ind)
+        assert np.array_equal(eng.permutation(), ind)
+        assert np.array_equal(eng.permutation(), ind)   # reading does not consume the look-ahead
+        eng.shuffle()                                   # takes shuffle 3
+        g.shuffle(ind)
+        assert np.array_equal(eng.permutation(), ind)
+        eng.run(4, 1)                                   # shuffle 4; 5 ahead
+        g.shuffle(ind)
+        assert np.array_equal(eng.permutation(), ind)
+        start = ind[::-1].copy()
+        eng.set_permutation(start)                      # discards the look-ahead: shuffle 5 must be drawn again
+        assert np.array_equal(eng.permutation(), start)
+        eng.shuffle()
+        g.shuffle(start)
+        assert np.array_equal(eng.permutation(), start)
+        eng.iteration(6)                                # shuffle 6 + epoch; 7 ahead
+        g.shuffle(start)
+        assert np.array_equal(eng.permutation(), start)
+        eng.iteration(7)
+        g.shuffle(start)
+        assert np.array_equal(eng.permutation(), start)
+
+
+def test_lookahead_off_gives_the_same_permutations(monkeypatch):
+    R = 40000
+    monkeypatch.setenv("B200SGD_NO_LOOKAHEAD", "1")
+    g = orc.Rand()
+    ind = np.arange(R, dtype=np.int32)
+    with pkg.SGDEngine(R, 4, 1000, 0.01) as eng:
+        eng.load_synthetic(seed=1)
+        eng.run(1, 2)
+        g.shuffle(ind); g.shuffle(ind)
+        assert np.array_equal(eng.permutation(), ind)
