@@ -886,7 +886,8 @@ int enqueue_perm_kernels(sgd_ctx* c, cudaStream_t st, int blocks, size_t smem, c
   // backward formulation (shuffle2_kernels.cuh)
   constexpr int S = sgd_ctx::kSubChunks;
   const int64_t Lx = c->chunk_len / S, nx = (n - 1 + Lx - 1) / Lx;  // sub-chunks in use (<= nchunks * S)
-  const int sgrid = c->stream_grid;
+  const int sgrid = c->stream_grid;            // virtual blocks of the stream kernels (columns of the count matrix)
+  const int pgrid = std::min(sgrid, blocks);   // blocks launched
   unsigned int* err = c->d_bar + 1;
   b200sgd::shuf2_expand_states_kernel<<<(int)((c->nchunks * S + 127) / 128), 128, 0, st>>>(c->d_states, c->nchunks, c->d_subjump, S,
                                                                                      c->d_states_x);
@@ -901,27 +902,27 @@ int enqueue_perm_kernels(sgd_ctx* c, cudaStream_t st, int blocks, size_t smem, c
   int32_t* R_stream = rscatter ? nullptr : c->d_R;  // self swaps: written by the stream kernel, or by the place kernel
   if (c->shuf_ver == 2) {
     CUDA_TRY(cudaMemsetAsync(c->d_ccnt, 0, sizeof(int32_t) * ((size_t)c->ngran + 1), st));
-    b200sgd::shuf2_stream_kernel<0, false><<<sgrid, 128, 0, st>>>(c->d_states_x, Lx, nx, n, b200sgd::kGranLog, 0, c->d_ccnt, nullptr, nullptr);
+    b200sgd::shuf2_stream_kernel<0, false><<<pgrid, 128, 0, st>>>(c->d_states_x, Lx, nx, n, b200sgd::kGranLog, 0, sgrid, c->d_ccnt, nullptr, nullptr);
     scan(c->d_ccnt, c->ngran, c->d_gstart);
     // the counters become the scatter's cursors
     CUDA_TRY(cudaMemcpyAsync(c->d_ccnt, c->d_gstart, sizeof(int32_t) * ((size_t)c->ngran + 1), cudaMemcpyDeviceToDevice, st));
-    b200sgd::shuf2_stream_kernel<1, false><<<sgrid, 128, 0, st>>>(c->d_states_x, Lx, nx, n, b200sgd::kGranLog, 0, c->d_ccnt, c->d_pairs2, R_stream);
+    b200sgd::shuf2_stream_kernel<1, false><<<pgrid, 128, 0, st>>>(c->d_states_x, Lx, nx, n, b200sgd::kGranLog, 0, sgrid, c->d_ccnt, c->d_pairs2, R_stream);
     *launches += 5;
   } else {
     const int32_t* coff = c->d_cstart;
     int64_t cstride = 1;
     if (c->shuf_ver == 3) {
       CUDA_TRY(cudaMemsetAsync(c->d_ccnt, 0, sizeof(int32_t) * ((size_t)c->ncoarse + 1), st));
-      b200sgd::shuf2_stream_kernel<0, false><<<sgrid, 128, 0, st>>>(c->d_states_x, Lx, nx, n, c->cshift, 0, c->d_ccnt, nullptr, nullptr);
+      b200sgd::shuf2_stream_kernel<0, false><<<pgrid, 128, 0, st>>>(c->d_states_x, Lx, nx, n, c->cshift, 0, sgrid, c->d_ccnt, nullptr, nullptr);
       scan(c->d_ccnt, c->ncoarse, c->d_cstart);
       CUDA_TRY(cudaMemcpyAsync(c->d_ccnt, c->d_cstart, sizeof(int32_t) * ((size_t)c->ncoarse + 1), cudaMemcpyDeviceToDevice, st));
-      b200sgd::shuf2_stream_kernel<1, false><<<sgrid, 128, 0, st>>>(c->d_states_x, Lx, nx, n, c->cshift, 0, c->d_ccnt, c->d_pairs1, R_stream);
+      b200sgd::shuf2_stream_kernel<1, false><<<pgrid, 128, 0, st>>>(c->d_states_x, Lx, nx, n, c->cshift, 0, sgrid, c->d_ccnt, c->d_pairs1, R_stream);
       *launches += 2;
     } else {
       const int64_t cells = c->ncoarse * (int64_t)sgrid;
-      b200sgd::shuf2_stream_kernel<0, true><<<sgrid, 128, 0, st>>>(c->d_states_x, Lx, nx, n, c->cshift, (int)c->ncoarse, c->d_mcnt, nullptr, nullptr);
+      b200sgd::shuf2_stream_kernel<0, true><<<pgrid, 128, 0, st>>>(c->d_states_x, Lx, nx, n, c->cshift, (int)c->ncoarse, sgrid, c->d_mcnt, nullptr, nullptr);
       scan(c->d_mcnt, cells, c->d_moff);
-      b200sgd::shuf2_stream_kernel<1, true><<<sgrid, 128, 0, st>>>(c->d_states_x, Lx, nx, n, c->cshift, (int)c->ncoarse, c->d_moff, c->d_pairs1, R_stream);
+      b200sgd::shuf2_stream_kernel<1, true><<<pgrid, 128, 0, st>>>(c->d_states_x, Lx, nx, n, c->cshift, (int)c->ncoarse, sgrid, c->d_moff, c->d_pairs1, R_stream);
       coff = c->d_moff;
       cstride = sgrid;
     }

@@ -103,72 +103,78 @@ constexpr int kCoarseMax = 4096;  // coarse buckets at most: their counters fit 
 //   BLOCKBINS = false: bins are global counters / cursors -- one L2 atomic per element, and the L2 does
 //           ~30 G of them per second whatever they hit (measured: 64 M in 2.7 ms; 8 MB of DRAM traffic).
 //   BLOCKBINS = true : the bins (<= kCoarseMax coarse buckets) live in shared memory.  MODE 0 leaves the
-//           block's counts in column blockIdx of the matrix bins[bucket * gridDim + block]; the exclusive
+//           block's counts in column `block` of the matrix bins[bucket * vblocks + block]; the exclusive
 //           scan of that matrix in memory order gives every (bucket, block) its own region, MODE 1
 //           starts its shared cursors there: no global atomic at all, and a deterministic layout.
 template <int MODE, bool BLOCKBINS>
 __global__ void __launch_bounds__(128) shuf2_stream_kernel(const uint32_t* __restrict__ states, int64_t L,
-                                                           int64_t nchunks, int64_t n, int shift, int nbins,
+                                                           int64_t nchunks, int64_t n, int shift, int nbins, int vblocks,
                                                            int32_t* __restrict__ gbins, uint2* __restrict__ pairs,
                                                            int32_t* __restrict__ R) {
   __shared__ int32_t s_bins[BLOCKBINS ? kCoarseMax : 1];
   int32_t* bins = BLOCKBINS ? s_bins : gbins;
-  if (BLOCKBINS) {
-    for (int b = threadIdx.x; b < nbins; b += blockDim.x)
-      s_bins[b] = MODE == 0 ? 0 : gbins[(int64_t)b * gridDim.x + blockIdx.x];
-    __syncthreads();
-  }
-  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (MODE == 1 && c == 0 && R != nullptr) R[0] = 0;
-  uint32_t r[31];
-  uint32_t k = 0, kend = 0;  // 32-bit step arithmetic (n < 2^31): k = index into the epoch's stream
-  if (c < nchunks) {
+  // `vblocks` virtual blocks of 128 chunks (= the columns of the count matrix), taken in turns by the grid:
+  // the map of several GPUs runs with one block per SM so that it never keeps the next epoch's cooperative
+  // step kernel from starting
+  for (int vb = blockIdx.x; vb < vblocks; vb += gridDim.x) {
+    if (BLOCKBINS) {
+      __syncthreads();  // the previous virtual block is done with the bins
+      for (int b = threadIdx.x; b < nbins; b += blockDim.x)
+        s_bins[b] = MODE == 0 ? 0 : gbins[(int64_t)b * vblocks + vb];
+      __syncthreads();
+    }
+    const int64_t c = (int64_t)vb * blockDim.x + threadIdx.x;
+    if (MODE == 1 && c == 0 && R != nullptr) R[0] = 0;
+    uint32_t r[31];
+    uint32_t k = 0, kend = 0;  // 32-bit step arithmetic (n < 2^31): k = index into the epoch's stream
+    if (c < nchunks) {
 #pragma unroll
-    for (int i = 0; i < 31; ++i) r[i] = states[c * 31 + i];
-    k = (uint32_t)(c * L);
-    kend = (uint32_t)((c * L + L < n - 1) ? (c * L + L) : (n - 1));  // the epoch consumes n-1 values
-  }
-  while (k < kend) {
+      for (int i = 0; i < 31; ++i) r[i] = states[c * 31 + i];
+      k = (uint32_t)(c * L);
+      kend = (uint32_t)((c * L + L < n - 1) ? (c * L + L) : (n - 1));  // the epoch consumes n-1 values
+    }
+    while (k < kend) {
 #pragma unroll
-    for (int h = 0; h < 3; ++h) {  // values 0..10, 11..21 and 22..30 of the round
-      constexpr int kHalf = 11;
-      uint32_t jj[kHalf];
-      int32_t slot[kHalf];
-#pragma unroll
-      for (int u = 0; u < kHalf; ++u) {
-        const int i = h * kHalf + u;
-        if (i < 31) {
-          const uint32_t v = r[i] + (i < 3 ? r[28 + i] : r[i - 3]);  // r[i-3] already holds a NEW value
-          r[i] = v;
-          jj[u] = (v >> 1) % (k + (uint32_t)i + 2u);  // step = k + i + 1; j = rand() % (step + 1)
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < kHalf; ++u) {
-        const int i = h * kHalf + u;
-        slot[u] = -1;
-        if (i < 31 && k + (uint32_t)i < kend && jj[u] != k + (uint32_t)i + 1u) {
-          if (MODE == 0) atomicAdd(bins + (jj[u] >> shift), 1);
-          else slot[u] = atomicAdd(bins + (jj[u] >> shift), 1);
-        }
-      }
-      if (MODE == 1) {
+      for (int h = 0; h < 3; ++h) {  // values 0..10, 11..21 and 22..30 of the round
+        constexpr int kHalf = 11;
+        uint32_t jj[kHalf];
+        int32_t slot[kHalf];
 #pragma unroll
         for (int u = 0; u < kHalf; ++u) {
           const int i = h * kHalf + u;
-          if (i < 31 && k + (uint32_t)i < kend) {
-            const uint32_t step = k + (uint32_t)i + 1u;
-            if (slot[u] >= 0) pairs[slot[u]] = make_uint2(jj[u], step);
-            else if (R != nullptr) R[step] = (int32_t)step;  // self swap: the value stays
+          if (i < 31) {
+            const uint32_t v = r[i] + (i < 3 ? r[28 + i] : r[i - 3]);  // r[i-3] already holds a NEW value
+            r[i] = v;
+            jj[u] = (v >> 1) % (k + (uint32_t)i + 2u);  // step = k + i + 1; j = rand() % (step + 1)
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < kHalf; ++u) {
+          const int i = h * kHalf + u;
+          slot[u] = -1;
+          if (i < 31 && k + (uint32_t)i < kend && jj[u] != k + (uint32_t)i + 1u) {
+            if (MODE == 0) atomicAdd(bins + (jj[u] >> shift), 1);
+            else slot[u] = atomicAdd(bins + (jj[u] >> shift), 1);
+          }
+        }
+        if (MODE == 1) {
+#pragma unroll
+          for (int u = 0; u < kHalf; ++u) {
+            const int i = h * kHalf + u;
+            if (i < 31 && k + (uint32_t)i < kend) {
+              const uint32_t step = k + (uint32_t)i + 1u;
+              if (slot[u] >= 0) pairs[slot[u]] = make_uint2(jj[u], step);
+              else if (R != nullptr) R[step] = (int32_t)step;  // self swap: the value stays
+            }
           }
         }
       }
+      k += 31;
     }
-    k += 31;
-  }
-  if (BLOCKBINS && MODE == 0) {
-    __syncthreads();
-    for (int b = threadIdx.x; b < nbins; b += blockDim.x) gbins[(int64_t)b * gridDim.x + blockIdx.x] = s_bins[b];
+    if (BLOCKBINS && MODE == 0) {
+      __syncthreads();
+      for (int b = threadIdx.x; b < nbins; b += blockDim.x) gbins[(int64_t)b * vblocks + vb] = s_bins[b];
+    }
   }
 }
 

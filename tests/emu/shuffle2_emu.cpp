@@ -60,9 +60,10 @@ int main(int argc, char** argv) {
     std::fill(last.begin(), last.end(), -7);
     std::fill(R.begin(), R.end(), INT32_MIN);
     const unsigned sblocks = (unsigned)((nchunks + 127) / 128);
+    const unsigned pblocks = std::max(1u, std::min(sblocks, grid / 2 + 1));  // the grid takes the virtual blocks in turns
     if (variant == 2) {
-      emu_launch(sblocks, 128, [&] {
-        shuf2_stream_kernel<0, false>(states.data(), L, nchunks, n, kGranLog, 0, gcnt.data(), nullptr, nullptr);
+      emu_launch(pblocks, 128, [&] {
+        shuf2_stream_kernel<0, false>(states.data(), L, nchunks, n, kGranLog, 0, (int)sblocks, gcnt.data(), nullptr, nullptr);
       });
       int32_t acc = 0;  // the device uses the three scan kernels of shuffle_kernels.cuh (warp shuffles: not emulated)
       for (int64_t g = 0; g <= ngran; ++g) {
@@ -70,8 +71,8 @@ int main(int argc, char** argv) {
         if (g < ngran) acc += gcnt[(size_t)g];
       }
       cursor = gstart;
-      emu_launch(sblocks, 128, [&] {
-        shuf2_stream_kernel<1, false>(states.data(), L, nchunks, n, kGranLog, 0, cursor.data(), pairs.data(), R.data());
+      emu_launch(pblocks, 128, [&] {
+        shuf2_stream_kernel<1, false>(states.data(), L, nchunks, n, kGranLog, 0, (int)sblocks, cursor.data(), pairs.data(), R.data());
       });
       emu_launch(grid, kLinkThreads, [&] {
         shuf2_link_kernel<false>(n, ngran, gstart.data(), pairs.data(), last.data(), R.data(), nullptr, nullptr, &err);
@@ -83,8 +84,8 @@ int main(int argc, char** argv) {
       int64_t cstride = 1;
       const int32_t* coff = cstart.data();
       if (variant == 3) {
-        emu_launch(sblocks, 128, [&] {
-          shuf2_stream_kernel<0, false>(states.data(), L, nchunks, n, cshift, 0, ccnt.data(), nullptr, nullptr);
+        emu_launch(pblocks, 128, [&] {
+          shuf2_stream_kernel<0, false>(states.data(), L, nchunks, n, cshift, 0, (int)sblocks, ccnt.data(), nullptr, nullptr);
         });
         int32_t acc = 0;
         for (int64_t b = 0; b <= ncoarse; ++b) {
@@ -92,13 +93,13 @@ int main(int argc, char** argv) {
           if (b < ncoarse) acc += ccnt[(size_t)b];
         }
         ccur = cstart;
-        emu_launch(sblocks, 128, [&] {
-          shuf2_stream_kernel<1, false>(states.data(), L, nchunks, n, cshift, 0, ccur.data(), pairs1.data(), nullptr);
+        emu_launch(pblocks, 128, [&] {
+          shuf2_stream_kernel<1, false>(states.data(), L, nchunks, n, cshift, 0, (int)sblocks, ccur.data(), pairs1.data(), nullptr);
         });
       } else {
         mcnt.assign((size_t)ncoarse * sblocks + 1, -1);
-        emu_launch(sblocks, 128, [&] {
-          shuf2_stream_kernel<0, true>(states.data(), L, nchunks, n, cshift, (int)ncoarse, mcnt.data(), nullptr, nullptr);
+        emu_launch(pblocks, 128, [&] {
+          shuf2_stream_kernel<0, true>(states.data(), L, nchunks, n, cshift, (int)ncoarse, (int)sblocks, mcnt.data(), nullptr, nullptr);
         });
         moff.resize(mcnt.size());
         int32_t acc = 0;
@@ -108,8 +109,8 @@ int main(int argc, char** argv) {
         }
         moff.back() = acc;
         mcnt = moff;  // MODE 1 reads its cursors' start values from the scanned matrix
-        emu_launch(sblocks, 128, [&] {
-          shuf2_stream_kernel<1, true>(states.data(), L, nchunks, n, cshift, (int)ncoarse, mcnt.data(), pairs1.data(),
+        emu_launch(pblocks, 128, [&] {
+          shuf2_stream_kernel<1, true>(states.data(), L, nchunks, n, cshift, (int)ncoarse, (int)sblocks, mcnt.data(), pairs1.data(),
                                        rscatter ? nullptr : R.data());
         });
         cstride = sblocks;
