@@ -192,7 +192,12 @@ int64_t sgd_local_row_begin(const sgd_ctx* ctx);
  * sgd_iteration = sgd_shuffle + sgd_epoch: the drop-in for one call of cuda_iteration /
  *   cublas_iteration (main.cu:56, :168).
  * sgd_run: replaces the epoch loop main.cu:456-508 with the next permutation produced while the
- *   current epoch runs. */
+ *   current epoch runs.
+ * Look-ahead: the reference never seeds rand(), so the permutation sequence is fixed; sgd_create, the last
+ *   epoch of sgd_run and sgd_iteration already enqueue the NEXT permutation on the device (beside the
+ *   upload / the step kernel) and the next shuffle request takes it.  Not observable through this
+ *   interface: sgd_get_permutation returns the current one, sgd_set_permutation discards the look-ahead
+ *   and the next shuffle is drawn from the same rand() values.  sgd_epoch alone never starts one. */
 int sgd_shuffle(sgd_ctx* ctx);
 int sgd_set_permutation(sgd_ctx* ctx, const int32_t* perm); /* testing.cu:80-84 style, R entries */
 int sgd_get_permutation(sgd_ctx* ctx, int32_t* perm);       /* R entries, global row numbers     */
