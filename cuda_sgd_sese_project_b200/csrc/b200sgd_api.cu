@@ -200,6 +200,7 @@ struct sgd_ctx {
   static constexpr int kSubChunks = 64;  // device-derived sub-chunk states per host chunk state
   int cshift = 14;                      // log2 positions per coarse bucket (<= kCoarseMax buckets)
   int stream_grid = 1;                  // blocks of the stream kernels = columns of the count matrix
+  bool shuf_confine_default = false;    // one GPU: permutation kernels on the SMs the step grid leaves idle
   int32_t *d_mcnt = nullptr, *d_moff = nullptr;  // (bucket, block) count matrix and its exclusive scan
   int64_t ngran = 0, ncoarse = 0, nranges = 0;
   uint2 *d_pairs1 = nullptr, *d_pairs2 = nullptr;  // coarse-bucketed pairs (later: the entries of R by range) / pairs by granule
@@ -889,6 +890,14 @@ int enqueue_perm_kernels(sgd_ctx* c, cudaStream_t st, int blocks, size_t smem, c
   const int sgrid = c->stream_grid;            // virtual blocks of the stream kernels (columns of the count matrix)
   const int pgrid = std::min(sgrid, blocks);   // blocks launched
   unsigned int* err = c->d_bar + 1;
+  // Confinement (smem != 0: B200SGD_SHUF_SMEM_KB, or B200SGD_SHUF_CONFINE=1 on one GPU): every kernel asks for
+  // so much dynamic shared memory that static + dynamic = `smem` bytes -- more than an SM has left beside a CTA
+  // of the step kernel -- so the block scheduler keeps the permutation work on the SMs the step grid leaves
+  // idle (28 of 148 with 15 clusters of 8) and off the consumers' shared-memory pipe.
+  auto dyn = [&](size_t static_bytes) -> size_t { return smem > static_bytes ? smem - static_bytes : 0; };
+  const size_t dyn_stream = dyn(sizeof(int32_t) * b200sgd::kCoarseMax), dyn_plain = dyn(0);
+  const size_t dyn_link = dyn(sizeof(int32_t) * (b200sgd::kLinkPos + b200sgd::kLinkThreads + b200sgd::kLinkCap + 8));
+  const size_t dyn_refine = dyn(sizeof(int32_t) * (1024 + b200sgd::kLinkThreads)), dyn_place = dyn(sizeof(int32_t) << b200sgd::kRangeLog);
   b200sgd::shuf2_expand_states_kernel<<<(int)((c->nchunks * S + 127) / 128), 128, 0, st>>>(c->d_states, c->nchunks, c->d_subjump, S,
                                                                                      c->d_states_x);
   auto scan = [&](const int32_t* in, int64_t cells, int32_t* out) {  // out[0 .. cells]: exclusive scan + total
@@ -902,48 +911,48 @@ int enqueue_perm_kernels(sgd_ctx* c, cudaStream_t st, int blocks, size_t smem, c
   int32_t* R_stream = rscatter ? nullptr : c->d_R;  // self swaps: written by the stream kernel, or by the place kernel
   if (c->shuf_ver == 2) {
     CUDA_TRY(cudaMemsetAsync(c->d_ccnt, 0, sizeof(int32_t) * ((size_t)c->ngran + 1), st));
-    b200sgd::shuf2_stream_kernel<0, false><<<pgrid, 128, 0, st>>>(c->d_states_x, Lx, nx, n, b200sgd::kGranLog, 0, sgrid, c->d_ccnt, nullptr, nullptr);
+    b200sgd::shuf2_stream_kernel<0, false><<<pgrid, 128, dyn_plain, st>>>(c->d_states_x, Lx, nx, n, b200sgd::kGranLog, 0, sgrid, c->d_ccnt, nullptr, nullptr);
     scan(c->d_ccnt, c->ngran, c->d_gstart);
     // the counters become the scatter's cursors
     CUDA_TRY(cudaMemcpyAsync(c->d_ccnt, c->d_gstart, sizeof(int32_t) * ((size_t)c->ngran + 1), cudaMemcpyDeviceToDevice, st));
-    b200sgd::shuf2_stream_kernel<1, false><<<pgrid, 128, 0, st>>>(c->d_states_x, Lx, nx, n, b200sgd::kGranLog, 0, sgrid, c->d_ccnt, c->d_pairs2, R_stream);
+    b200sgd::shuf2_stream_kernel<1, false><<<pgrid, 128, dyn_plain, st>>>(c->d_states_x, Lx, nx, n, b200sgd::kGranLog, 0, sgrid, c->d_ccnt, c->d_pairs2, R_stream);
     *launches += 5;
   } else {
     const int32_t* coff = c->d_cstart;
     int64_t cstride = 1;
     if (c->shuf_ver == 3) {
       CUDA_TRY(cudaMemsetAsync(c->d_ccnt, 0, sizeof(int32_t) * ((size_t)c->ncoarse + 1), st));
-      b200sgd::shuf2_stream_kernel<0, false><<<pgrid, 128, 0, st>>>(c->d_states_x, Lx, nx, n, c->cshift, 0, sgrid, c->d_ccnt, nullptr, nullptr);
+      b200sgd::shuf2_stream_kernel<0, false><<<pgrid, 128, dyn_plain, st>>>(c->d_states_x, Lx, nx, n, c->cshift, 0, sgrid, c->d_ccnt, nullptr, nullptr);
       scan(c->d_ccnt, c->ncoarse, c->d_cstart);
       CUDA_TRY(cudaMemcpyAsync(c->d_ccnt, c->d_cstart, sizeof(int32_t) * ((size_t)c->ncoarse + 1), cudaMemcpyDeviceToDevice, st));
-      b200sgd::shuf2_stream_kernel<1, false><<<pgrid, 128, 0, st>>>(c->d_states_x, Lx, nx, n, c->cshift, 0, sgrid, c->d_ccnt, c->d_pairs1, R_stream);
+      b200sgd::shuf2_stream_kernel<1, false><<<pgrid, 128, dyn_plain, st>>>(c->d_states_x, Lx, nx, n, c->cshift, 0, sgrid, c->d_ccnt, c->d_pairs1, R_stream);
       *launches += 2;
     } else {
       const int64_t cells = c->ncoarse * (int64_t)sgrid;
-      b200sgd::shuf2_stream_kernel<0, true><<<pgrid, 128, 0, st>>>(c->d_states_x, Lx, nx, n, c->cshift, (int)c->ncoarse, sgrid, c->d_mcnt, nullptr, nullptr);
+      b200sgd::shuf2_stream_kernel<0, true><<<pgrid, 128, dyn_stream, st>>>(c->d_states_x, Lx, nx, n, c->cshift, (int)c->ncoarse, sgrid, c->d_mcnt, nullptr, nullptr);
       scan(c->d_mcnt, cells, c->d_moff);
-      b200sgd::shuf2_stream_kernel<1, true><<<pgrid, 128, 0, st>>>(c->d_states_x, Lx, nx, n, c->cshift, (int)c->ncoarse, sgrid, c->d_moff, c->d_pairs1, R_stream);
+      b200sgd::shuf2_stream_kernel<1, true><<<pgrid, 128, dyn_stream, st>>>(c->d_states_x, Lx, nx, n, c->cshift, (int)c->ncoarse, sgrid, c->d_moff, c->d_pairs1, R_stream);
       coff = c->d_moff;
       cstride = sgrid;
     }
-    b200sgd::shuf2_refine_kernel<<<(int)std::min<int64_t>(c->ncoarse, blocks), b200sgd::kLinkThreads, 0, st>>>(
+    b200sgd::shuf2_refine_kernel<<<(int)std::min<int64_t>(c->ncoarse, blocks), b200sgd::kLinkThreads, dyn_refine, st>>>(
         c->ngran, c->ncoarse, c->cshift, coff, cstride, c->d_pairs1, c->d_pairs2, c->d_gstart);
     *launches += 4;
   }
   if (!rscatter) {
-    b200sgd::shuf2_link_kernel<false><<<blocks, b200sgd::kLinkThreads, 0, st>>>(n, c->ngran, c->d_gstart, c->d_pairs2, c->d_last, c->d_R,
+    b200sgd::shuf2_link_kernel<false><<<blocks, b200sgd::kLinkThreads, dyn_link, st>>>(n, c->ngran, c->d_gstart, c->d_pairs2, c->d_last, c->d_R,
                                                                                nullptr, nullptr, err);
     *launches += 1;
   } else {
     b200sgd::shuf2_range_cursor_kernel<<<(int)std::min<int64_t>((c->nranges + 255) / 256, blocks), 256, 0, st>>>(c->d_rcur, c->nranges,
                                                                                                          b200sgd::kRangeLog);
     // the coarse pairs are dead: their array takes the entries of R, by range
-    b200sgd::shuf2_link_kernel<true><<<blocks, b200sgd::kLinkThreads, 0, st>>>(n, c->ngran, c->d_gstart, c->d_pairs2, c->d_last, nullptr,
+    b200sgd::shuf2_link_kernel<true><<<blocks, b200sgd::kLinkThreads, dyn_link, st>>>(n, c->ngran, c->d_gstart, c->d_pairs2, c->d_last, nullptr,
                                                                               c->d_rcur, c->d_pairs1, err);
-    b200sgd::shuf2_place_kernel<<<(int)std::min<int64_t>(c->nranges, blocks), 256, 0, st>>>(n, c->nranges, c->d_rcur, c->d_pairs1, c->d_R);
+    b200sgd::shuf2_place_kernel<<<(int)std::min<int64_t>(c->nranges, blocks), 256, dyn_place, st>>>(n, c->nranges, c->d_rcur, c->d_pairs1, c->d_R);
     *launches += 3;
   }
-  b200sgd::shuf2_resolve_kernel<<<blocks, 256, 0, st>>>(n, c->d_last, c->d_R, in, out);
+  b200sgd::shuf2_resolve_kernel<<<blocks, 256, dyn_plain, st>>>(n, c->d_last, c->d_R, in, out);
   CUDA_TRY(cudaGetLastError());
   *launches += 2;
   return SGD_OK;
@@ -962,8 +971,20 @@ int enqueue_device_shuffle(sgd_ctx* c, int stage_buf, int src, int dst, int* lau
   CUDA_TRY(cudaStreamWaitEvent(c->shuf_stream, c->ev_perm[stage_buf], 0));
   CUDA_TRY(cudaStreamWaitEvent(c->shuf_stream, c->ev_done[dst], 0));  // last epoch that read d_perm[dst]
   CUDA_TRY(cudaStreamWaitEvent(c->shuf_stream, c->ev_perm[src], 0));  // d_perm[src] uploaded (sgd_set_permutation)
-  const int blocks = (int)std::min<int64_t>((n + 255) / 256, (int64_t)c->num_sms * 16);
-  SGD_TRY(enqueue_perm_kernels(c, c->shuf_stream, blocks, shuf_smem_bytes(), c->d_perm[src], c->d_perm[dst], launches));
+  int blocks = (int)std::min<int64_t>((n + 255) / 256, (int64_t)c->num_sms * 16);
+  size_t smem = shuf_smem_bytes();
+  {  // B200SGD_SHUF_CONFINE=1|0: keep the permutation kernels off the step kernel's SMs (see enqueue_perm_kernels)
+    const char* e = std::getenv("B200SGD_SHUF_CONFINE");
+    const bool want = e ? e[0] == '1' : c->shuf_confine_default;
+    const size_t sm_total = 233472, step_cta = c->smem_bytes + 1024;   // bytes of an SM; a step CTA with its reserve
+    const size_t room = sm_total > step_cta ? sm_total - step_cta : 0;  // what a second block could get, its 1 KB reserve included
+    const int idle_sms = c->num_sms - c->grid;
+    if (want && smem == 0 && c->shuf_ver >= 2 && idle_sms >= 16 && room < ((size_t)46 << 10)) {
+      smem = room;  // static + dynamic = room, plus the block's own 1 KB reserve: does not fit
+      blocks = (int)std::min<int64_t>((n + 255) / 256, (int64_t)idle_sms * 6);
+    }
+  }
+  SGD_TRY(enqueue_perm_kernels(c, c->shuf_stream, blocks, smem, c->d_perm[src], c->d_perm[dst], launches));
   CUDA_TRY(cudaEventRecord(c->ev_done[2], c->shuf_stream));
   CUDA_TRY(cudaEventRecord(c->ev_shuf[dst], c->shuf_stream));
   return SGD_OK;
