@@ -1,7 +1,8 @@
 // shuffle2_kernels.cuh -- the reference's per-epoch permutation, bit-exact, on the device: the BACKWARD
 // formulation (round 2).  Same contract as shuffle_kernels.cuh (std::random_shuffle driven by glibc
 // rand(), main.cu:90 / :207:  for i = 1..n-1: j_i = rand() % (i+1); if (i != j_i) swap(v[i], v[j_i])),
-// 2.5 instead of 6.5 random DRAM accesses per element.
+// 1.5 random DRAM reads per element (0.5 on the chains, 1 for the final gather) instead of 6.5 random
+// accesses; 12 instead of 30 GB of DRAM traffic per shuffle of 64M rows.
 //
 //   Ask every final position p where its value came from.  Walk the loop backwards from time n-1: the
 //   content of p was last replaced by the LATEST step that targets p, h = last(hits(p)), hits(p) =
@@ -20,12 +21,20 @@
 //   on average.  out[p] = in[src(p)], or src itself (the position map several GPUs share, see
 //   shuffle_kernels.cuh).
 //
-//   hits(p) are built without a random access per element per pass: positions are cut into granules of
-//   256; K1a counts the hits per granule (the rand() stream is regenerated per chunk from the host's
-//   jump-ahead states, as before), a scan gives every granule its region, K1b regenerates the stream and
-//   scatters the pairs (j_i, i) into the regions, K2 ("link") loads runs of granules into shared memory,
-//   bins the pairs per position, sorts the (tiny) lists and writes last[] (in order) and R[] (the one
-//   random write per element), K3 resolves.
+//   hits(p) are built by regrouping the pairs (j_i, i) by position in two steps, without a global atomic or
+//   a random DRAM access per element (default pipeline, B200SGD_SHUFFLE=5; b200sgd_api.cu enqueue_perm_kernels):
+//     K0  expand  : 64 sub-chunk start states of the rand() stream per host state (jump-ahead polynomials)
+//     K1a stream<0,1>: regenerate the stream, count the hits per COARSE bucket (2^14..2^18 positions) in
+//                   shared memory; the block's counts go into its column of a (bucket, block) matrix
+//         scan    : exclusive scan of the matrix in memory order = one region per (bucket, block)
+//     K1b stream<1,1>: regenerate again, scatter the pairs into the regions (shared-memory cursors)
+//     K1c refine  : one block per coarse bucket: regroup its pairs by granule (256 positions)
+//     K2  link    : runs of granules in shared memory: bin per position, sort the (tiny) lists, write
+//                   last[] in order and the entries (i, R[i]) into the coarse range i >> 12
+//     K2b place   : one block per range: entries put in place in shared memory, R[] written in order
+//     K3  resolve : src(p), then out[p] = in[src(p)]
+//   Other strategies (A/B, tests): 2 = pairs straight into granule regions through global cursors, R written
+//   in place; 3 = coarse buckets through global cursors; 4 = as 5 with R written in place.
 //
 // The kernels use block-level primitives only (__syncthreads, shared / global atomicAdd): tests/emu/ runs
 // the SAME source on the host (one OS thread per CUDA thread) against the host loop -- the GPU pool has no
