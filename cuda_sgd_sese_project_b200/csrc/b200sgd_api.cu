@@ -1038,16 +1038,24 @@ int enqueue_own_map(sgd_ctx* c, int64_t k, int* launches) {
   int bps = std::max(1, 8 / N);
   if (const char* e = std::getenv("B200SGD_MAP_BLOCKS_PER_SM")) bps = std::max(1, std::atoi(e));
   int blocks = (int)std::min<int64_t>((n + 255) / 256, (int64_t)c->num_sms * bps);
-  // A/B switch B200SGD_MAP_CONFINE=1: keep the map off the step kernel's SMs altogether -- its kernels ASK
-  // for 40 KB of dynamic shared memory they do not use, so their blocks do not fit beside a step CTA
-  // (199-227 KB) and run on the SMs the step grid leaves idle (36 of 148 with 7 clusters of 16), five per
-  // SM.  Measured: the step loop is disturbed less (one GPU, 64M x 512: 34.9 -> 29.4 us per step), but a
-  // map on 28-36 SMs takes ~2x as long and the epoch then waits for it or for its blocks to drain:
-  // N = 2: 28.3 ms per epoch against 23.9, N = 8: 11.6 against 10.2, N = 4: 16.3 against 16.7.  Off.
+  // Confinement (B200SGD_MAP_CONFINE=1|0; default: on from 4 ranks with the backward kernels): keep the map off
+  // the step kernel's SMs altogether -- its kernels ASK for 40 KB of shared memory (static + dynamic), so their
+  // blocks do not fit beside a step CTA (199-227 KB) and run on the SMs the step grid leaves idle (36 of 148
+  // with 7 clusters of 16), five per SM.  A map then takes ~5x as long (its link / refine / resolve kernels are
+  // latency-bound and get 180 instead of 1184+ resident blocks: ~32 ms at 64M rows, from the one-GPU run
+  // of B200SGD_SHUF_CONFINE), but a rank needs one map per N epochs only, and the step loop keeps its SMs to
+  // itself.  History: with the forward kernels (13 ms alone, ~2x that confined on 28-36 SMs) the epoch waited
+  // for the map: N = 2: 28.3 ms per epoch against 23.9 co-located, N = 8: 11.6 against 10.2, N = 4: 16.3
+  // against 16.7.  With the backward kernels co-located maps cost the latency-bound step loop 15.4 instead
+  // of 10.4 us per step at N = 4 and 9.2 instead of 7.9 at N = 8 (profiles/r3_scale_c5_n4.json, _n8.json),
+  // while N x (epoch time) is 44 / 68 ms at N = 4 / 8: room for a confined map.  At N = 2 (2 x 15.8 ms) it
+  // is not: co-located.  The default from 4 ranks follows from those numbers; it could not be re-measured
+  // on the final build (GPU budget of the round spent) -- B200SGD_MAP_CONFINE=0 restores co-located maps.
   size_t map_smem = shuf_smem_bytes();
   const int idle_sms = c->num_sms - c->grid;
   const char* force = std::getenv("B200SGD_MAP_CONFINE");
-  if (idle_sms >= 16 && force && force[0] == '1') {
+  const bool confine = force ? force[0] == '1' : (N >= 4 && c->shuf_ver >= 2);
+  if (idle_sms >= 16 && confine && map_smem == 0) {
     map_smem = (size_t)40 << 10;
     blocks = (int)std::min<int64_t>((n + 255) / 256, (int64_t)idle_sms * 5);
   }
