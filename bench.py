@@ -552,8 +552,9 @@ def main() -> int:
                        "reduce": ("cluster all-gather in shared memory" + (" + L2 hop between clusters" if grid > cluster_size else "")) if cluster_size else
                                  REDUCE_NAMES.get(reduce_mode, str(reduce_mode)),
                        "kernel": kernel_name,
-                       "permutation": "device, backward formulation (csrc/shuffle2_kernels.cuh, B200SGD_SHUFFLE=%s), enqueued one "
-                                      "call ahead (look-ahead) and beside the step kernel" % os.environ.get("B200SGD_SHUFFLE", "5"),
+                       "permutation": ("device, backward formulation (csrc/shuffle2_kernels.cuh, B200SGD_SHUFFLE=%s), enqueued one "
+                                       "call ahead (look-ahead) and beside the step kernel" % os.environ.get("B200SGD_SHUFFLE", "5"))
+                                      if R >= 32768 else "host loop (fewer than 32768 rows)",
                        "ring_rows": ring_rows, "smem_bytes": smem_bytes,
                        "parallelism": f"dp{N} row-sharded, fused NVLink gradient exchange inside the step kernel" if N > 1 else "single GPU"},
             "steploop": {"samples_per_s": samples / loop_s, "ms_per_epoch": loop_s * 1e3 / K,
